@@ -1,0 +1,495 @@
+// DiffNet denoiser + shallow-diffusion ancestral sampler on the conv_gemm kernel.
+//
+// Reference (relative to /root/reference/train_bisinger/):
+//   usr/diff/net.py:107-130 (DiffNet.forward), :58-78 (ResidualBlock), :32-44 (SinusoidalPosEmb)
+//   usr/diff/shallow_diffusion_tts.py:149-166 (p_sample), :245-272 (infer loop), :275-279 (spec norm)
+//
+// Data layout in HBM (rows = b*T + t, channels-last):
+//   xt      f32  [B][M][T]      the sampler state x_t in the reference layout [B,1,M,T]
+//   xin     bf16 [rows][M]      hi/lo copy of x_t as the A operand of the input projection
+//   cond    bf16 [rows][H]      hi/lo copy of decoder_inp (step-invariant)
+//   xres    f32  [rows][C]      residual stream x
+//   xa      bf16 [rows][C]      hi/lo of (x + d_l): the zero-padded input of layer l's dilated conv
+//   z       bf16 [rows][C]      hi/lo of the gated activation
+//   skip    f32  [rows][C]      running sum of skip connections
+//   s, h    bf16 [rows][C]      head operands: sum(skip)/sqrt(L) and relu(skip_projection)
+// Per step: 1 + 2L + 2 launches of conv_gemm_kernel; all K steps are captured in one CUDA graph when the
+// noise is generated on the device.
+#include <cmath>
+#include <map>
+#include <memory>
+
+#include "plans.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+
+// d[t][l][:] = diffusion_projection_l( mlp( SinusoidalPosEmb(t) ) )   -- depends on t only => LUT
+// net.py:32-44 (embedding), :94-98 + diffusion.py:68-70 (Linear, Mish, Linear), :62,67 (per-layer Linear)
+__global__ void step_lut_kernel(const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2,
+                                const float* __restrict__ b2, const float* __restrict__ wd, const float* __restrict__ bd,
+                                int C, int L, float* __restrict__ lut) {
+    extern __shared__ float sm[];
+    float* emb = sm;          // [C]
+    float* hid = sm + C;      // [4C]
+    float* e = hid + 4 * C;   // [C]
+    const int t = blockIdx.x;
+    const int half = C / 2;
+    for (int j = threadIdx.x; j < C; j += blockDim.x) {
+        const int jj = j < half ? j : j - half;
+        const float w = expf(static_cast<float>(jj) * -(logf(10000.0f) / static_cast<float>(half - 1)));
+        const float a = static_cast<float>(t) * w;
+        emb[j] = j < half ? sinf(a) : cosf(a);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 4 * C; o += blockDim.x) {
+        float acc = b0[o];
+        const float* wr = w0 + static_cast<size_t>(o) * C;
+        for (int i = 0; i < C; ++i) acc = fmaf(wr[i], emb[i], acc);
+        const float sp = acc > 20.0f ? acc : log1pf(expf(acc));   // F.softplus (threshold 20)
+        hid[o] = acc * tanhf(sp);                                  // Mish
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < C; o += blockDim.x) {
+        float acc = b2[o];
+        const float* wr = w2 + static_cast<size_t>(o) * 4 * C;
+        for (int i = 0; i < 4 * C; ++i) acc = fmaf(wr[i], hid[i], acc);
+        e[o] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < L * C; idx += blockDim.x) {
+        const int l = idx / C, o = idx % C;
+        float acc = bd[l * C + o];
+        const float* wr = wd + (static_cast<size_t>(l) * C + o) * C;
+        for (int i = 0; i < C; ++i) acc = fmaf(wr[i], e[i], acc);
+        lut[(static_cast<size_t>(t) * L + l) * C + o] = acc;
+    }
+}
+
+// f32 [n] -> bf16 hi/lo
+__global__ void split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
+    const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { float hf; split_bf16(f[k], hf, h[k], l[k]); }
+        *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<uint2*>(h);
+        if (lo) *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<uint2*>(l);
+    } else {
+        for (size_t k = i; k < n; ++k) {
+            float hf; __nv_bfloat16 h, l;
+            split_bf16(src[k], hf, h, l);
+            hi[k] = h;
+            if (lo) lo[k] = l;
+        }
+    }
+}
+
+// x_K: q_sample(norm_spec(fs2_mel)^T, t=K-1) (shallow_diffusion_tts.py:246-252,203-208,275-276) or the Gaussian
+// start (:253-256); also used to import a caller-provided x for bsg_diffnet_forward (mode 2).
+// One thread per (b, t); writes xt [B][M][T] and the bf16 operand copy xin [rows][M].
+__global__ void init_x_kernel(int mode, const float* __restrict__ fs2_mel, const float* __restrict__ noise,
+                              const float* __restrict__ smin, const float* __restrict__ smax, float sa, float sb,
+                              const unsigned long long* __restrict__ seed_ptr, int B, int T, int M, float* __restrict__ xt,
+                              __nv_bfloat16* __restrict__ xin_hi, __nv_bfloat16* __restrict__ xin_lo) {
+    const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= static_cast<long long>(B) * T) return;
+    const int b = static_cast<int>(r / T), t = static_cast<int>(r % T);
+    for (int c = 0; c < M; ++c) {
+        const long long xi = (static_cast<long long>(b) * M + c) * T + t;
+        float x;
+        if (mode == 2) {
+            x = noise[xi];   // plain import of x
+        } else {
+            float z = noise ? noise[xi] : philox_normal(__ldg(seed_ptr), 0xFFFFFFFFu, static_cast<uint64_t>(xi));
+            if (mode == 0) {
+                const float mn = smin[c], mx = smax[c];
+                const float xs = (fs2_mel[r * M + c] - mn) / (mx - mn) * 2.0f - 1.0f;
+                x = sa * xs + sb * z;
+            } else {
+                x = z;
+            }
+            xt[xi] = x;
+        }
+        float hf; __nv_bfloat16 h, l;
+        split_bf16(x, hf, h, l);
+        xin_hi[r * M + c] = h;
+        if (xin_lo) xin_lo[r * M + c] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct DiffusionPlan::Workspace {
+    int B = 0, T = 0;
+    DevBuf xt, xin_hi, xin_lo, cond_hi, cond_lo, xres, xa_hi, xa_lo, z_hi, z_lo, skip, s_hi, s_lo, h_hi, h_lo, mel, mel2ph, eps;
+    CUtensorMap m_xin[2], m_cond[2], m_xa[2], m_z[2], m_s[2], m_h[2];
+    cudaGraphExec_t graph = nullptr;
+    bool graph_has_mask = false;
+    ~Workspace() {
+        if (graph) cudaGraphExecDestroy(graph);
+    }
+};
+
+static std::vector<float> take(const float*& p, size_t n) {
+    std::vector<float> v(p, p + n);
+    p += n;
+    return v;
+}
+
+DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t n_w, const bsg_schedule& s, const float* spec_min,
+                             const float* spec_max, int device)
+    : cfg(c), device(device) {
+    B200_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    B200_CHECK(prop.major == 10, "bisinger_b200 requires an sm_100 (B200) device; found sm_" + std::to_string(prop.major) +
+                                     std::to_string(prop.minor) + " -- there is no fallback path");
+    const int M = c.in_dims, H = c.hidden_size, C = c.residual_channels, L = c.residual_layers;
+    B200_CHECK(C == 256 && H == 256, "this build is specialised for residual_channels == hidden_size == 256");
+    B200_CHECK(M == 80, "this build is specialised for 80 mel bins");
+    B200_CHECK(L >= 1 && c.k_step >= 1 && c.k_step <= c.timesteps, "bad layer/step counts");
+    B200_CHECK(c.precision == BSG_PRECISION_BF16 || c.precision == BSG_PRECISION_BF16X3, "bad precision");
+    terms = c.precision == BSG_PRECISION_BF16X3 ? 3 : 1;
+    const size_t expect = static_cast<size_t>(C) * M + C + 4 * C * C + 4 * C + 4 * C * C + C +
+                          static_cast<size_t>(L) * (2 * C * C * 3 + 2 * C + C * C + C + 2 * C * H + 2 * C + 2 * C * C + 2 * C) +
+                          static_cast<size_t>(C) * C + C + static_cast<size_t>(M) * C + M;
+    B200_CHECK(n_w == expect, "weight blob has " + std::to_string(n_w) + " floats, expected " + std::to_string(expect));
+
+    const float* p = w;
+    auto w_in = take(p, static_cast<size_t>(C) * M);
+    auto b_in = take(p, C);
+    auto w0 = take(p, 4 * C * C);
+    auto b0 = take(p, 4 * C);
+    auto w2 = take(p, 4 * C * C);
+    auto b2 = take(p, C);
+    std::vector<float> wd_all, bd_all;
+    layers.resize(L);
+    for (int l = 0; l < L; ++l) {
+        auto wdil = take(p, static_cast<size_t>(2 * C) * C * 3);   // [2C][C][3]
+        auto bdil = take(p, 2 * C);
+        auto wdp = take(p, static_cast<size_t>(C) * C);
+        auto bdp = take(p, C);
+        auto wc = take(p, static_cast<size_t>(2 * C) * H);         // [2C][H][1]
+        auto bc = take(p, 2 * C);
+        auto wo = take(p, static_cast<size_t>(2 * C) * C);         // [2C][C][1]
+        auto bo = take(p, 2 * C);
+        wd_all.insert(wd_all.end(), wdp.begin(), wdp.end());
+        bd_all.insert(bd_all.end(), bdp.begin(), bdp.end());
+        // G1 weights: [2C rows][K = 3*C (taps) + H (cond)], rows permuted so that every 256-row N tile holds the
+        // gate rows of 128 channels followed by the filter rows of the same channels (gate = first half of the
+        // conv output, filter = second half: net.py:73).
+        const int K1 = 3 * C + H;
+        std::vector<float> g1(static_cast<size_t>(2 * C) * K1), gb(2 * C);
+        for (int tile = 0; tile < 2; ++tile)
+            for (int part = 0; part < 2; ++part)
+                for (int j = 0; j < 128; ++j) {
+                    const int dst = tile * 256 + part * 128 + j;
+                    const int src = part * C + tile * 128 + j;
+                    float* row = &g1[static_cast<size_t>(dst) * K1];
+                    for (int tap = 0; tap < 3; ++tap)
+                        for (int ci = 0; ci < C; ++ci) row[tap * C + ci] = wdil[(static_cast<size_t>(src) * C + ci) * 3 + tap];
+                    for (int ci = 0; ci < H; ++ci) row[3 * C + ci] = wc[static_cast<size_t>(src) * H + ci];
+                    gb[dst] = bdil[src] + bc[src];
+                }
+        layers[l].g1.pack(g1, 2 * C, K1);
+        upload(layers[l].g1_bias, gb);
+        layers[l].g2.pack(wo, 2 * C, C);
+        upload(layers[l].g2_bias, bo);
+        layers[l].dilation = 1 << (l % c.dilation_cycle);
+    }
+    auto w_skip = take(p, static_cast<size_t>(C) * C);
+    auto b_skip = take(p, C);
+    auto w_out = take(p, static_cast<size_t>(M) * C);
+    auto b_out = take(p, M);
+    inproj.pack(w_in, C, M);
+    upload(inproj_bias, b_in);
+    skipproj.pack(w_skip, C, C);
+    upload(skipproj_bias, b_skip);
+    outproj.pack(w_out, M, C);
+    upload(outproj_bias, b_out);
+
+    // step-embedding LUT on the device
+    {
+        DevBuf d_w0, d_b0, d_w2, d_b2, d_wd, d_bd;
+        upload(d_w0, w0); upload(d_b0, b0); upload(d_w2, w2); upload(d_b2, b2); upload(d_wd, wd_all); upload(d_bd, bd_all);
+        lut.alloc(static_cast<size_t>(c.k_step) * L * C * sizeof(float));
+        step_lut_kernel<<<c.k_step, 256, 6 * C * sizeof(float)>>>(d_w0.as<float>(), d_b0.as<float>(), d_w2.as<float>(),
+                                                                   d_b2.as<float>(), d_wd.as<float>(), d_bd.as<float>(), C, L,
+                                                                   lut.as<float>());
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaDeviceSynchronize());
+    }
+    // schedule (host copies; baked into kernel parameters per step)
+    sched.resize(c.timesteps);
+    for (int t = 0; t < c.timesteps; ++t) {
+        sched[t].sqrt_ac = s.sqrt_alphas_cumprod[t];
+        sched[t].sqrt_1mac = s.sqrt_one_minus_alphas_cumprod[t];
+        sched[t].c0 = s.sqrt_recip_alphas_cumprod[t];
+        sched[t].c1 = s.sqrt_recipm1_alphas_cumprod[t];
+        sched[t].c2 = s.posterior_mean_coef1[t];
+        sched[t].c3 = s.posterior_mean_coef2[t];
+        sched[t].sigma = t == 0 ? 0.0f : std::exp(0.5f * s.posterior_log_variance_clipped[t]);   // nonzero_mask (:165)
+    }
+    upload(d_spec_min, std::vector<float>(spec_min, spec_min + M));
+    upload(d_spec_max, std::vector<float>(spec_max, spec_max + M));
+    d_seed.alloc(sizeof(unsigned long long));
+
+    // set the dynamic-smem attribute of every instantiation outside of any stream capture
+    ConvGemmArgs none{};
+    for (int epi : {EPI_INPROJ, EPI_GATE, EPI_RES_SKIP, EPI_RELU_BF16}) launch_conv_gemm(256, terms, epi, none, nullptr);
+    launch_conv_gemm(80, terms, EPI_POSTERIOR, none, nullptr);
+}
+
+DiffusionPlan::~DiffusionPlan() = default;
+
+DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
+    const auto key = std::make_pair(B, T);
+    auto it = ws.find(key);
+    if (it != ws.end()) return *it->second;
+    // keep at most a few shapes alive (graphs + buffers); drop everything when the table grows
+    if (ws.size() >= 4) ws.clear();
+    auto w = std::make_unique<Workspace>();
+    const int M = cfg.in_dims, H = cfg.hidden_size, C = cfg.residual_channels;
+    const size_t rows = static_cast<size_t>(B) * T;
+    w->B = B;
+    w->T = T;
+    const bool lo = terms == 3;
+    w->xt.alloc(rows * M * 4);
+    w->eps.alloc(rows * M * 4);
+    w->xin_hi.alloc(rows * M * 2);
+    w->cond_hi.alloc(rows * H * 2);
+    w->xres.alloc(rows * C * 4);
+    w->xa_hi.alloc(rows * C * 2);
+    w->z_hi.alloc(rows * C * 2);
+    w->skip.alloc(rows * C * 4);
+    w->s_hi.alloc(rows * C * 2);
+    w->h_hi.alloc(rows * C * 2);
+    w->mel.alloc(rows * M * 4);
+    w->mel2ph.alloc(rows * 8);
+    if (lo) {
+        w->xin_lo.alloc(rows * M * 2);
+        w->cond_lo.alloc(rows * H * 2);
+        w->xa_lo.alloc(rows * C * 2);
+        w->z_lo.alloc(rows * C * 2);
+        w->s_lo.alloc(rows * C * 2);
+        w->h_lo.alloc(rows * C * 2);
+    }
+    auto mk = [&](CUtensorMap (&m)[2], const DevBuf& hi, const DevBuf& lo_, int ch) {
+        m[0] = make_act_tmap(hi.p, B, T, ch);
+        m[1] = lo ? make_act_tmap(lo_.p, B, T, ch) : m[0];
+    };
+    mk(w->m_xin, w->xin_hi, w->xin_lo, M);
+    mk(w->m_cond, w->cond_hi, w->cond_lo, H);
+    mk(w->m_xa, w->xa_hi, w->xa_lo, C);
+    mk(w->m_z, w->z_hi, w->z_lo, C);
+    mk(w->m_s, w->s_hi, w->s_lo, C);
+    mk(w->m_h, w->h_hi, w->h_lo, C);
+    auto& ref = *w;
+    ws[key] = std::move(w);
+    return ref;
+}
+
+static void set_w(ConvGemmArgs& a, PackedW& w, int n_tile) { w.maps(n_tile, a.wmap[0], a.wmap[1]); }
+
+// One DiffNet evaluation at diffusion step t (net.py:107-130) followed by `tail`:
+//   tail == 0: posterior update of xt (p_sample), tail == 1: write eps to ws.eps
+void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail,
+                                 cudaStream_t st) {
+    const int M = cfg.in_dims, H = cfg.hidden_size, C = cfg.residual_channels, L = cfg.residual_layers;
+    const int B = w.B, T = w.T;
+    const bool lo = terms == 3;
+    const float* lut_t = lut.as<float>() + static_cast<size_t>(t) * L * C;
+    auto nz = [&](const DevBuf& b) { return lo ? b.as<__nv_bfloat16>() : nullptr; };
+
+    {   // input projection + ReLU (net.py:116-118); writes x and (x + d_0)
+        ConvGemmArgs a{};
+        set_geometry(a, B, T, C, 256);
+        a.amap[0] = w.m_xin[0]; a.amap[1] = w.m_xin[1];
+        set_w(a, inproj, 256);
+        a.n_seg = 1;
+        a.seg[0] = Segment{0, 0, 0, (M + kBlockK - 1) / kBlockK, 0};
+        a.epi.bias = inproj_bias.as<float>();
+        a.epi.f32_a = w.xres.as<float>();
+        a.epi.out_hi = w.xa_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.xa_lo);
+        a.epi.dvec = lut_t;
+        a.epi.out_pitch = C;
+        launch_conv_gemm(256, terms, EPI_INPROJ, a, st);
+        ++launches, ++g_launch_count;
+    }
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = layers[l];
+        {   // dilated conv(x + d) + conditioner projection -> sigmoid*tanh gate (net.py:67-74)
+            ConvGemmArgs a{};
+            set_geometry(a, B, T, 2 * C, 256);
+            a.amap[0] = w.m_xa[0]; a.amap[1] = w.m_xa[1];
+            a.amap[2] = w.m_cond[0]; a.amap[3] = w.m_cond[1];
+            set_w(a, ly.g1, 256);
+            a.n_seg = 4;
+            for (int tap = 0; tap < 3; ++tap) a.seg[tap] = Segment{0, (tap - 1) * ly.dilation, 0, C / kBlockK, tap * C};
+            a.seg[3] = Segment{1, 0, 0, H / kBlockK, 3 * C};
+            a.epi.bias = ly.g1_bias.as<float>();
+            a.epi.out_hi = w.z_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.z_lo);
+            a.epi.out_pitch = C;
+            launch_conv_gemm(256, terms, EPI_GATE, a, st);
+            ++launches, ++g_launch_count;
+        }
+        {   // output projection -> residual / skip (net.py:76-78), skip sum (net.py:126)
+            ConvGemmArgs a{};
+            set_geometry(a, B, T, 2 * C, 256);
+            a.amap[0] = w.m_z[0]; a.amap[1] = w.m_z[1];
+            set_w(a, ly.g2, 256);
+            a.n_seg = 1;
+            a.seg[0] = Segment{0, 0, 0, C / kBlockK, 0};
+            a.epi.bias = ly.g2_bias.as<float>();
+            a.epi.f32_a = w.xres.as<float>();
+            a.epi.f32_b = w.skip.as<float>();
+            a.epi.out_hi = w.xa_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.xa_lo);
+            a.epi.out2_hi = w.s_hi.as<__nv_bfloat16>(); a.epi.out2_lo = nz(w.s_lo);
+            a.epi.dvec = (l + 1 < L) ? lut_t + static_cast<size_t>(l + 1) * C : nullptr;
+            a.epi.out_pitch = C;
+            a.epi.flags = (l == 0 ? 1 : 0) | (l == L - 1 ? 2 : 0);
+            a.epi.c0 = 1.0f / std::sqrt(static_cast<float>(L));
+            launch_conv_gemm(256, terms, EPI_RES_SKIP, a, st);
+            ++launches, ++g_launch_count;
+        }
+    }
+    {   // skip_projection + ReLU (net.py:127-128)
+        ConvGemmArgs a{};
+        set_geometry(a, B, T, C, 256);
+        a.amap[0] = w.m_s[0]; a.amap[1] = w.m_s[1];
+        set_w(a, skipproj, 256);
+        a.n_seg = 1;
+        a.seg[0] = Segment{0, 0, 0, C / kBlockK, 0};
+        a.epi.bias = skipproj_bias.as<float>();
+        a.epi.out_hi = w.h_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.h_lo);
+        a.epi.out_pitch = C;
+        launch_conv_gemm(256, terms, EPI_RELU_BF16, a, st);
+        ++launches, ++g_launch_count;
+    }
+    {   // output_projection (net.py:129) fused with the DDPM posterior update (shallow_diffusion_tts.py:149-166)
+        ConvGemmArgs a{};
+        set_geometry(a, B, T, M, 80);
+        a.amap[0] = w.m_h[0]; a.amap[1] = w.m_h[1];
+        set_w(a, outproj, 80);
+        a.n_seg = 1;
+        a.seg[0] = Segment{0, 0, 0, C / kBlockK, 0};
+        a.epi.bias = outproj_bias.as<float>();
+        if (tail == 1) {
+            a.epi.f32_a = w.eps.as<float>();
+            a.epi.flags = 1;
+        } else {
+            const StepCoef& sc = sched[t];
+            a.epi.f32_a = w.xt.as<float>();
+            a.epi.f32_b = last ? w.mel.as<float>() : nullptr;
+            a.epi.out_hi = last ? nullptr : w.xin_hi.as<__nv_bfloat16>();
+            a.epi.out_lo = last ? nullptr : nz(w.xin_lo);
+            a.epi.aux0 = noise_k;
+            a.epi.aux1 = d_spec_min.as<float>();
+            a.epi.aux2 = d_spec_max.as<float>();
+            a.epi.mel2ph = use_mask ? w.mel2ph.as<int64_t>() : nullptr;
+            a.epi.c0 = sc.c0; a.epi.c1 = sc.c1; a.epi.c2 = sc.c2; a.epi.c3 = sc.c3; a.epi.c4 = sc.sigma;
+            a.epi.seed_ptr = d_seed.as<unsigned long long>();
+            a.epi.step = static_cast<unsigned>(k_exec);
+        }
+        a.epi.out_pitch = M;
+        launch_conv_gemm(80, terms, EPI_POSTERIOR, a, st);
+        ++launches, ++g_launch_count;
+    }
+}
+
+void DiffusionPlan::sample(const float* cond, const float* fs2_mel, const float* start_noise, const float* step_noise,
+                           unsigned long long seed, const int64_t* mel2ph, int B, int T, float* mel_out, float* x_final,
+                           cudaStream_t st) {
+    B200_CHECK(B > 0 && T > 0, "empty batch");
+    B200_CHECK(cond != nullptr && mel_out != nullptr, "cond and mel_out are required");
+    B200_CUDA(cudaSetDevice(device));
+    Workspace& w = workspace(B, T);
+    const int M = cfg.in_dims, H = cfg.hidden_size, K = cfg.k_step;
+    const size_t rows = static_cast<size_t>(B) * T;
+    const bool lo = terms == 3;
+
+    B200_CUDA(cudaMemcpyAsync(d_seed.p, &seed, sizeof(seed), cudaMemcpyHostToDevice, st));
+    {
+        const size_t n = rows * H;
+        split_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256 + 1), 256, 0, st>>>(cond, w.cond_hi.as<__nv_bfloat16>(),
+                                                                                    lo ? w.cond_lo.as<__nv_bfloat16>() : nullptr, n);
+        ++launches, ++g_launch_count;
+        const int mode = fs2_mel ? 0 : 1;
+        init_x_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(
+            mode, fs2_mel, start_noise, d_spec_min.as<float>(), d_spec_max.as<float>(), sched[K - 1].sqrt_ac, sched[K - 1].sqrt_1mac,
+            d_seed.as<unsigned long long>(), B, T, M, w.xt.as<float>(), w.xin_hi.as<__nv_bfloat16>(),
+            lo ? w.xin_lo.as<__nv_bfloat16>() : nullptr);
+        ++launches, ++g_launch_count;
+        B200_CUDA(cudaGetLastError());
+    }
+    const bool use_mask = mel2ph != nullptr;
+    if (use_mask) B200_CUDA(cudaMemcpyAsync(w.mel2ph.p, mel2ph, rows * 8, cudaMemcpyDeviceToDevice, st));
+
+    if (step_noise == nullptr && use_graphs) {
+        if (w.graph && w.graph_has_mask != use_mask) {
+            cudaGraphExecDestroy(w.graph);
+            w.graph = nullptr;
+        }
+        if (!w.graph) {
+            cudaStream_t cs;
+            B200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            const unsigned long long before = launches;
+            B200_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            try {
+                for (int k = 0; k < K; ++k) enqueue_step(w, K - 1 - k, k, nullptr, k == K - 1, use_mask, 0, cs);
+            } catch (...) {
+                cudaStreamEndCapture(cs, &g);
+                if (g) cudaGraphDestroy(g);
+                cudaStreamDestroy(cs);
+                throw;
+            }
+            B200_CUDA(cudaStreamEndCapture(cs, &g));
+            graph_nodes = launches - before;
+            launches = before;
+            g_launch_count -= graph_nodes;
+            B200_CUDA(cudaGraphInstantiate(&w.graph, g, 0));
+            cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            w.graph_has_mask = use_mask;
+        }
+        B200_CUDA(cudaGraphLaunch(w.graph, st));
+        launches += graph_nodes, g_launch_count += graph_nodes;
+    } else {
+        const size_t per_step = rows * M;
+        for (int k = 0; k < K; ++k)
+            enqueue_step(w, K - 1 - k, k, step_noise ? step_noise + static_cast<size_t>(k) * per_step : nullptr, k == K - 1, use_mask, 0,
+                         st);
+    }
+    B200_CUDA(cudaMemcpyAsync(mel_out, w.mel.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
+    if (x_final) B200_CUDA(cudaMemcpyAsync(x_final, w.xt.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
+}
+
+void DiffusionPlan::denoise(const float* spec, int t, const float* cond, int B, int T, float* eps_out, cudaStream_t st) {
+    B200_CHECK(B > 0 && T > 0, "empty batch");
+    B200_CHECK(t >= 0 && t < cfg.k_step, "diffusion step outside the plan's LUT (0 <= t < k_step)");
+    B200_CUDA(cudaSetDevice(device));
+    Workspace& w = workspace(B, T);
+    const int M = cfg.in_dims, H = cfg.hidden_size;
+    const size_t rows = static_cast<size_t>(B) * T;
+    const bool lo = terms == 3;
+    const size_t n = rows * H;
+    split_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256 + 1), 256, 0, st>>>(cond, w.cond_hi.as<__nv_bfloat16>(),
+                                                                                lo ? w.cond_lo.as<__nv_bfloat16>() : nullptr, n);
+    init_x_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(2, nullptr, spec, nullptr, nullptr, 0.f, 0.f, nullptr, B, T, M,
+                                                                             nullptr, w.xin_hi.as<__nv_bfloat16>(),
+                                                                             lo ? w.xin_lo.as<__nv_bfloat16>() : nullptr);
+    launches += 2, g_launch_count += 2;
+    B200_CUDA(cudaGetLastError());
+    enqueue_step(w, t, 0, nullptr, false, false, 1, st);
+    B200_CUDA(cudaMemcpyAsync(eps_out, w.eps.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
+}
+
+}  // namespace b200

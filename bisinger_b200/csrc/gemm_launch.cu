@@ -1,0 +1,83 @@
+// Instantiations + host dispatcher of conv_gemm_kernel, and TMA tensor-map encoding.
+#include <mutex>
+
+#include "runtime.h"
+
+namespace b200 {
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    if (!fn) throw Error("cuTensorMapEncodeTiled not available from the CUDA driver");
+    return fn;
+}
+
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    CUtensorMap m;
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    B200_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base must be 16-byte aligned");
+    for (int i = 0; i + 1 < rank; ++i) B200_CHECK(gstr[i] % 16 == 0, "tensor map strides must be multiples of 16 bytes");
+    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                                    gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return m;
+}
+
+int device_sm_count() {
+    int dev = 0, n = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    return n;
+}
+
+namespace {
+
+template <int N_TILE, int TERMS, int EPI>
+void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
+    using S = GemmSmem<N_TILE, TERMS>;
+    auto kern = conv_gemm_kernel<N_TILE, TERMS, EPI>;
+    static std::once_flag once;   // per instantiation
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal); });
+    B200_CUDA(attr_err);
+    static int sms = 0;
+    if (sms == 0) sms = device_sm_count();
+    if (args.num_tiles <= 0) return;
+    const int grid = args.num_tiles < sms ? args.num_tiles : sms;
+    kern<<<grid, kGemmThreads, S::kTotal, stream>>>(args);
+    B200_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+#define B200_CASE(NT, TM, EP) \
+    if (n_tile == NT && terms == TM && epi == EP) return launch_inst<NT, TM, EP>(args, stream);
+
+void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream) {
+    // unit-test GEMMs
+    B200_CASE(256, 1, EPI_F32) B200_CASE(256, 3, EPI_F32) B200_CASE(128, 1, EPI_F32) B200_CASE(128, 3, EPI_F32)
+    B200_CASE(64, 1, EPI_F32) B200_CASE(32, 1, EPI_F32)
+    // DiffNet
+    B200_CASE(256, 1, EPI_INPROJ) B200_CASE(256, 3, EPI_INPROJ)
+    B200_CASE(256, 1, EPI_GATE) B200_CASE(256, 3, EPI_GATE)
+    B200_CASE(256, 1, EPI_RES_SKIP) B200_CASE(256, 3, EPI_RES_SKIP)
+    B200_CASE(256, 1, EPI_RELU_BF16) B200_CASE(256, 3, EPI_RELU_BF16)
+    B200_CASE(80, 1, EPI_POSTERIOR) B200_CASE(80, 3, EPI_POSTERIOR)
+    // HiFi-GAN
+    B200_CASE(256, 1, EPI_BIAS_ACT) B200_CASE(128, 1, EPI_BIAS_ACT) B200_CASE(64, 1, EPI_BIAS_ACT) B200_CASE(32, 1, EPI_BIAS_ACT)
+    throw Error("conv_gemm: no instantiation for n_tile=" + std::to_string(n_tile) + " terms=" + std::to_string(terms) +
+                " epi=" + std::to_string(epi));
+}
+
+}  // namespace b200

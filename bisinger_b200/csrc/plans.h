@@ -1,0 +1,94 @@
+// Plan objects behind the C-ABI handles of include/bisinger_b200.h
+#pragma once
+#include <map>
+#include <memory>
+#include <utility>
+#include <vector>
+
+#include "../../include/bisinger_b200.h"
+#include "runtime.h"
+
+namespace b200 {
+
+extern unsigned long long g_launch_count;   // process-wide kernel-launch counter (bsg_kernel_launch_count)
+
+class DiffusionPlan {
+public:
+    DiffusionPlan(const bsg_diffnet_config& cfg, const float* weights, size_t n_weights, const bsg_schedule& sched,
+                  const float* spec_min, const float* spec_max, int device);
+    ~DiffusionPlan();
+
+    void sample(const float* cond, const float* fs2_mel, const float* start_noise, const float* step_noise,
+                unsigned long long seed, const int64_t* mel2ph, int B, int T, float* mel_out, float* x_final, cudaStream_t st);
+    void denoise(const float* spec, int t, const float* cond, int B, int T, float* eps_out, cudaStream_t st);
+
+    bsg_diffnet_config cfg;
+    int device;
+    int terms = 1;
+    bool use_graphs = true;
+    unsigned long long launches = 0;
+
+private:
+    struct Workspace;
+    struct Layer {
+        PackedW g1, g2;
+        DevBuf g1_bias, g2_bias;
+        int dilation = 1;
+    };
+    struct StepCoef {
+        float sqrt_ac, sqrt_1mac, c0, c1, c2, c3, sigma;
+    };
+    Workspace& workspace(int B, int T);
+    void enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail, cudaStream_t st);
+
+    std::vector<Layer> layers;
+    PackedW inproj, skipproj, outproj;
+    DevBuf inproj_bias, skipproj_bias, outproj_bias;
+    DevBuf lut, d_spec_min, d_spec_max, d_seed;
+    std::vector<StepCoef> sched;
+    std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
+    unsigned long long graph_nodes = 0;
+};
+
+class HifiganPlan {
+public:
+    HifiganPlan(const bsg_hifigan_config& cfg, const float* weights, size_t n_weights, int device);
+    ~HifiganPlan();
+    void forward(const float* mel, const float* f0, const float* rand_ini, const float* src_noise, unsigned long long seed, int B,
+                 int T, float* wav, cudaStream_t st);
+    void source(const float* f0, const float* rand_ini, const float* src_noise, unsigned long long seed, int B, int T, float* har,
+                cudaStream_t st);
+
+    bsg_hifigan_config cfg;
+    int device;
+    int hop = 1;
+    unsigned long long launches = 0;
+
+private:
+    struct Workspace;
+    struct Conv {            // one packed convolution
+        PackedW w;
+        DevBuf bias;
+        int cin = 0, cout = 0, k = 1, dilation = 1;
+    };
+    struct Stage {
+        int cin = 0, cout = 0, rate = 1, ksize = 1;
+        std::vector<Conv> up_phase;                // one 2-tap (generally ceil(k/u)-tap) conv per output phase
+        std::vector<std::vector<int>> up_shifts;   // row shifts of each phase's taps
+        DevBuf up_bias;
+        DevBuf noise_w, noise_b;                   // noise_convs[i] (f32, CUDA-core kernel)
+        int noise_k = 1, noise_stride = 1, noise_pad = 0;
+        std::vector<Conv> convs1, convs2;          // [num_kernels * num_dilations]
+    };
+    Workspace& workspace(int B, int T);
+    void run_source(Workspace& w, const float* f0, const float* rand_ini, const float* src_noise, unsigned long long seed, int B, int T,
+                    cudaStream_t st);
+
+    Conv conv_pre;
+    std::vector<Stage> stages;
+    DevBuf post_w, post_b, src_lin;   // conv_post weights [7][C] f32, bias; l_linear weight[9]+bias
+    DevBuf d_seed;
+    std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
+};
+
+}  // namespace b200

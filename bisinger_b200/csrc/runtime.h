@@ -1,0 +1,156 @@
+// Host-side runtime helpers: error handling, device buffers, TMA tensor-map encoding, launch glue.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "conv_gemm.cuh"
+
+namespace b200 {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define B200_CUDA(expr)                                                                                  \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw ::b200::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                                std::to_string(__LINE__) + ")");                                         \
+    } while (0)
+
+#define B200_CHECK(cond, msg)                                                                            \
+    do {                                                                                                 \
+        if (!(cond)) throw ::b200::Error(std::string("check failed: ") + #cond + ": " + (msg));          \
+    } while (0)
+
+// RAII device allocation (plan-owned workspaces / packed weights)
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    void alloc(size_t n) {
+        release();
+        if (n == 0) n = 16;
+        B200_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    void ensure(size_t n) {
+        if (n > bytes) alloc(n);
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+template <class T>
+inline void upload(DevBuf& d, const std::vector<T>& h) {
+    d.alloc(h.size() * sizeof(T));
+    B200_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+}
+
+// round-to-nearest-even fp32 -> bf16 on the host (packer)
+inline uint16_t f32_to_bf16_bits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>(u >> 16);
+}
+inline float bf16_bits_to_f32(uint16_t b) {
+    uint32_t u = static_cast<uint32_t>(b) << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+// bf16 tensor, dims given innermost-first; strides (bytes) for dims 1..rank-1; SWIZZLE_128B, zero OOB fill.
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+
+// activations [B][L][C] (channels-last), box = 64 channels x 128 rows
+inline CUtensorMap make_act_tmap(const void* base, int B, int L, int C, int row_pitch_elems = 0) {
+    if (row_pitch_elems == 0) row_pitch_elems = C;
+    const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(row_pitch_elems) * 2, static_cast<uint64_t>(row_pitch_elems) * 2 * L};
+    const uint32_t box[3] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(kTileM), 1};
+    return make_tmap_bf16(base, 3, dims, strides, box);
+}
+// packed weights [N][K] (K-major), box = 64 x n_tile
+inline CUtensorMap make_w_tmap(const void* base, int N, int K, int n_tile, int row_pitch_elems = 0) {
+    if (row_pitch_elems == 0) row_pitch_elems = K;
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(row_pitch_elems) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(n_tile)};
+    return make_tmap_bf16(base, 2, dims, strides, box);
+}
+
+int device_sm_count();
+
+// Launch one instantiation of conv_gemm_kernel (defined in gemm_launch.cu)
+void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream);
+
+// fills the tile-geometry fields of args from (B, L, N_total, n_tile)
+inline void set_geometry(ConvGemmArgs& a, int B, int L, int n_total, int n_tile) {
+    a.B = B;
+    a.L = L;
+    a.tiles_per_batch = (L + kTileM - 1) / kTileM;
+    a.n_tiles_n = n_total / n_tile;
+    a.num_tiles = B * a.tiles_per_batch * a.n_tiles_n;
+    a.w_row0 = 0;
+}
+
+// Packed bf16 (hi, lo) weight matrix on the device
+struct PackedW {
+    DevBuf hi, lo;
+    int N = 0, K = 0;
+    CUtensorMap tm[2];     // cached TMA descriptors (hi, lo) for box = 64 x tm_ntile
+    int tm_ntile = 0;
+    void maps(int n_tile, CUtensorMap& mhi, CUtensorMap& mlo) {
+        if (tm_ntile != n_tile) {
+            tm[0] = make_w_tmap(hi.p, N, K, n_tile);
+            tm[1] = make_w_tmap(lo.p, N, K, n_tile);
+            tm_ntile = n_tile;
+        }
+        mhi = tm[0];
+        mlo = tm[1];
+    }
+    // w: row-major [N][K] fp32 on the host
+    void pack(const std::vector<float>& w, int n, int k) {
+        N = n;
+        K = k;
+        std::vector<uint16_t> h(w.size()), l(w.size());
+        for (size_t i = 0; i < w.size(); ++i) {
+            h[i] = f32_to_bf16_bits(w[i]);
+            l[i] = f32_to_bf16_bits(w[i] - bf16_bits_to_f32(h[i]));
+        }
+        upload(hi, h);
+        upload(lo, l);
+    }
+};
+
+}  // namespace b200

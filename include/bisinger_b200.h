@@ -1,0 +1,167 @@
+/* bisinger_b200 -- C-ABI of the B200-native synthesis hot path (libbisinger_b200.so).
+ *
+ * The reference (BiSinger-SVS/BiSinger) has no FFI: its "operator API" for this path is three Python
+ * call sites.  Each entry point below replaces one of them; INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.  Paths are relative to /root/reference/train_bisinger/.
+ *
+ *   bsg_diffusion_*  <->  GaussianDiffusion.forward(infer=True) sampler loop over DiffNet
+ *                         usr/diff/shallow_diffusion_tts.py:245-272 (p_sample :149-166),
+ *                         usr/diff/net.py:107-130 (DiffNet.forward), :58-78 (ResidualBlock)
+ *   bsg_hifigan_*    <->  HifiGanGenerator.forward(mel, f0)   modules/hifigan/hifigan.py:144-173
+ *                         + SourceModuleHnNSF / SineGen       modules/parallel_wavegan/models/source.py:45-138,386-399
+ *                         (called from HifiGAN.spec2wav vocoders/hifigan.py:55-69 and
+ *                          run_vocoder inference/m4singer/base_svs_infer.py:142-151)
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, non-zero on error; the message of the
+ *     last error on the calling thread is returned by bsg_last_error().  Nothing throws across the ABI.
+ *   - "device pointer" arguments are CUDA device pointers on the plan's device, owned by the caller.
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are asynchronous
+ *     with respect to the host unless stated otherwise.
+ *   - a plan owns its packed weights, look-up tables, workspaces and captured CUDA graphs.  A plan is bound
+ *     to one device and must not be used from two threads at once (one plan per replica process).
+ *   - there is no CPU fallback: if no sm_100 device is present, plan creation fails.
+ */
+#ifndef BISINGER_B200_H_
+#define BISINGER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSG_ABI_VERSION 1
+
+/* contraction precision of the tensor-core GEMMs */
+#define BSG_PRECISION_BF16 0   /* bf16 operands, fp32 accumulate                                   */
+#define BSG_PRECISION_BF16X3 1 /* bf16 hi/lo split operands, 3 MMAs per product, fp32 accumulate   */
+
+typedef struct bsg_diffusion_plan bsg_diffusion_plan;
+typedef struct bsg_hifigan_plan bsg_hifigan_plan;
+
+int bsg_abi_version(void);
+const char* bsg_last_error(void);
+/* number of kernels launched by this library on the calling process so far (eager launches + nodes of
+ * replayed graphs); bench.py reports the difference over the timed region as "gpu_launches". */
+unsigned long long bsg_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * DiffNet + shallow-diffusion sampler
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int in_dims;            /* mel bins M (80)                      hparams['audio_num_mel_bins']        */
+    int hidden_size;        /* encoder hidden H (256)               hparams['hidden_size']               */
+    int residual_channels;  /* C (256)                              hparams['residual_channels']         */
+    int residual_layers;    /* L (20)                               hparams['residual_layers']           */
+    int dilation_cycle;     /* 4                                    hparams['dilation_cycle_length']     */
+    int timesteps;          /* length of the schedule buffers       GaussianDiffusion.num_timesteps      */
+    int k_step;             /* number of reverse steps K            GaussianDiffusion.K_step             */
+    int precision;          /* BSG_PRECISION_*                                                            */
+} bsg_diffnet_config;
+
+/* Schedule buffers of the GaussianDiffusion module (host pointers, each [timesteps] float32), read from the
+ * module (they may come from a checkpoint), never recomputed: shallow_diffusion_tts.py:103-123. */
+typedef struct {
+    const float* sqrt_alphas_cumprod;
+    const float* sqrt_one_minus_alphas_cumprod;
+    const float* sqrt_recip_alphas_cumprod;
+    const float* sqrt_recipm1_alphas_cumprod;
+    const float* posterior_mean_coef1;
+    const float* posterior_mean_coef2;
+    const float* posterior_log_variance_clipped;
+} bsg_schedule;
+
+/* weights_host: the DiffNet state_dict flattened to float32 in registration order (usr/diff/net.py:91-104):
+ *   input_projection.{weight[C][M][1],bias[C]}, mlp.0.{weight[4C][C],bias}, mlp.2.{weight[C][4C],bias},
+ *   residual_layers.i.{dilated_conv.{weight[2C][C][3],bias[2C]}, diffusion_projection.{weight[C][C],bias},
+ *                      conditioner_projection.{weight[2C][H][1],bias}, output_projection.{weight[2C][C][1],bias}} (i<L),
+ *   skip_projection.{weight[C][C][1],bias}, output_projection.{weight[M][C][1],bias}
+ * spec_min / spec_max: host float32 [M] (GaussianDiffusion.spec_min/max, shallow_diffusion_tts.py:125-126). */
+int bsg_diffusion_plan_create(const bsg_diffnet_config* cfg, const float* weights_host, size_t n_weights,
+                              const bsg_schedule* sched, const float* spec_min, const float* spec_max, int device,
+                              bsg_diffusion_plan** out);
+void bsg_diffusion_plan_destroy(bsg_diffusion_plan* plan);
+
+/* Infer branch of GaussianDiffusion.forward (shallow_diffusion_tts.py:245-272) after the FastSpeech2 handoff.
+ *   cond        device f32 [B][T][H]    ret['decoder_inp'] (the reference transposes a view of it, :235)
+ *   fs2_mel     device f32 [B][T][M]    ret['mel_out'] of the FastSpeech2 decoder; NULL => Gaussian start
+ *                                       (x_K = start_noise, hparams['gaussian_start'], :253-256)
+ *   start_noise device f32 [B][1][M][T] noise of q_sample (:204) / gaussian start; NULL => drawn on device
+ *   step_noise  device f32 [K][B][1][M][T], entry k is used at t = K-1-k (:266-267); NULL => drawn on device
+ *                                       (Philox4x32-10 keyed by `seed`); the CUDA-graph path is used when NULL
+ *   mel2ph      device i64 [B][T] or NULL; mel_out is multiplied by (mel2ph > 0) (:269-272)
+ *   mel_out     device f32 [B][T][M]    de-normalised mel (denorm_spec, :278-279)
+ *   x_final     device f32 [B][1][M][T] or NULL: the normalised x_0 before denorm (for tests)            */
+int bsg_diffusion_sample(bsg_diffusion_plan* plan, const float* cond, const float* fs2_mel, const float* start_noise,
+                         const float* step_noise, unsigned long long seed, const int64_t* mel2ph, int B, int T,
+                         float* mel_out, float* x_final, void* stream);
+
+/* One DiffNet evaluation eps = denoise_fn(x, t, cond) (usr/diff/net.py:107-130) -- the drop-in for
+ * DiffNet.forward used by B200DiffNet and by the parity tests.
+ *   spec device f32 [B][1][M][T], t = diffusion step (same for the whole batch, as at :267),
+ *   cond device f32 [B][T][H]  (NOTE: channels-last, i.e. the un-transposed decoder_inp),
+ *   eps_out device f32 [B][1][M][T]                                                                    */
+int bsg_diffnet_forward(bsg_diffusion_plan* plan, const float* spec, int t, const float* cond, int B, int T,
+                        float* eps_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * HiFi-GAN / NSF generator
+ * ------------------------------------------------------------------------------------------------ */
+#define BSG_MAX_UPSAMPLES 8
+#define BSG_MAX_RESBLOCK_KERNELS 4
+#define BSG_MAX_RESBLOCK_DILATIONS 4
+
+typedef struct {
+    int num_mels;                 /* 80 (conv_pre input channels, hifigan.py:117)                          */
+    int upsample_initial_channel; /* h['upsample_initial_channel']                                         */
+    int num_upsamples;            /* len(h['upsample_rates'])                                              */
+    int upsample_rates[BSG_MAX_UPSAMPLES];
+    int upsample_kernel_sizes[BSG_MAX_UPSAMPLES];
+    int num_kernels;              /* len(h['resblock_kernel_sizes'])                                       */
+    int resblock_kernel_sizes[BSG_MAX_RESBLOCK_KERNELS];
+    int num_dilations;            /* len of each h['resblock_dilation_sizes'][j] (ResBlock1: 3)            */
+    int resblock_dilation_sizes[BSG_MAX_RESBLOCK_KERNELS][BSG_MAX_RESBLOCK_DILATIONS];
+    int use_pitch_embed;          /* 1 => NSF harmonic source + noise_convs (hifigan.py:110-116)           */
+    int audio_sample_rate;        /* h['audio_sample_rate']                                                */
+    int harmonic_num;             /* 8 (hifigan.py:112)                                                    */
+    int precision;                /* BSG_PRECISION_BF16                                                    */
+} bsg_hifigan_config;
+
+/* weights_host: the generator state_dict AFTER remove_weight_norm() (hifigan.py:175-182), float32, in this order:
+ *   m_source.l_linear.{weight[1][9],bias[1]}            (only if use_pitch_embed)
+ *   conv_pre.{weight[C0][80][7],bias}
+ *   for i < num_upsamples: ups.i.{weight[Cin][Cout][k],bias[Cout]}
+ *   for i < num_upsamples: noise_convs.i.{weight[Cout][1][k],bias} (only if use_pitch_embed)
+ *   for r < num_upsamples*num_kernels: for m < num_dilations: resblocks.r.convs1.m.{weight[C][C][k],bias}
+ *                                      for m < num_dilations: resblocks.r.convs2.m.{weight[C][C][k],bias}
+ *   conv_post.{weight[1][C][7],bias[1]}                                                                   */
+int bsg_hifigan_plan_create(const bsg_hifigan_config* cfg, const float* weights_host, size_t n_weights, int device,
+                            bsg_hifigan_plan** out);
+void bsg_hifigan_plan_destroy(bsg_hifigan_plan* plan);
+
+/* HifiGanGenerator.forward (hifigan.py:144-173).
+ *   mel       device f32 [B][num_mels][T]
+ *   f0        device f32 [B][T] in Hz (0 = unvoiced) or NULL (no NSF branch)
+ *   rand_ini  device f32 [B][harmonic_num+1] initial phases (SineGen, source.py:54-57; column 0 is ignored) or NULL
+ *   src_noise device f32 [B][T*hop][harmonic_num+1] ~ N(0,1) (source.py:133) or NULL => drawn on device from `seed`
+ *   wav       device f32 [B][T*hop]                                                                        */
+int bsg_hifigan_forward(bsg_hifigan_plan* plan, const float* mel, const float* f0, const float* rand_ini,
+                        const float* src_noise, unsigned long long seed, int B, int T, float* wav, void* stream);
+
+/* NSF harmonic source only (hifigan.py:147-149): har_source device f32 [B][T*hop].  Exposed for parity tests. */
+int bsg_hifigan_source(bsg_hifigan_plan* plan, const float* f0, const float* rand_ini, const float* src_noise,
+                       unsigned long long seed, int B, int T, float* har_source, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Kernel self-test: C[b][l][n] = bias[n] + sum_taps A[b][l+shift][:] . W[n][tap][:] through the same tcgen05
+ * implicit-GEMM kernel the plans use.  Device pointers; A f32 [B][L][Cin], W f32 host [N][ntaps][Cin].
+ * ------------------------------------------------------------------------------------------------ */
+int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias_host, int B, int L, int Cin, int N,
+                      int ntaps, const int* shifts, int n_tile, int precision, float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BISINGER_B200_H_ */

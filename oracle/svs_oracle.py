@@ -1,0 +1,326 @@
+"""CPU oracle for the BiSinger synthesis hot path (TEST INFRASTRUCTURE ONLY).
+
+This file is a plain-PyTorch fp32 *restatement* of the reference algorithm for the
+path named in BASELINE.json (shallow-diffusion reverse loop over DiffNet + HiFi-GAN/NSF
+generator forward).  It is the checker for the CUDA path: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs
+may import it.  The product package ``bisinger_b200`` never imports anything from
+``oracle/`` and has no CPU fallback.
+
+Pinning: the reference ships no tests or golden vectors for this path, so
+"parity unpinned" by reference-owned tests.  Instead the restatement is pinned against
+the *executed reference modules* (``oracle/ref_shim.py`` imports them unmodified from
+/root/reference in the build container): ``oracle/make_golden.py`` writes
+``tests/golden/*.npz`` from the real reference and ``tests/test_oracle.py`` checks this
+file against those fixtures (and, when /root/reference is present, against the live
+reference modules).
+
+Every function cites the reference file:line it follows; paths are relative to
+/root/reference/train_bisinger/.
+
+Optional ``operand`` argument: None = exact fp32 (the oracle proper).  "bf16"/"fp16"
+rounds the *operands* of every contraction to that type and accumulates in fp32 -- a model
+of what a tensor-core path computes, used by tests to tell precision effects from bugs.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+LRELU_SLOPE = 0.1  # modules/hifigan/hifigan.py:11
+
+
+def _rnd(x: Tensor, operand: Optional[str]) -> Tensor:
+    if operand is None:
+        return x
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[operand]
+    return x.to(dt).to(torch.float32)
+
+
+# --------------------------------------------------------------------------------------
+# DiffNet (usr/diff/net.py)
+# --------------------------------------------------------------------------------------
+
+def sinusoidal_pos_emb(t: Tensor, dim: int) -> Tensor:
+    """usr/diff/net.py:32-44 -- emb = [sin(t*w_j), cos(t*w_j)], w_j = exp(-j ln(1e4)/(dim/2-1))."""
+    half = dim // 2
+    w = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    e = t.to(torch.float32)[:, None] * w[None, :]
+    return torch.cat((e.sin(), e.cos()), dim=-1)
+
+
+def mish(x: Tensor) -> Tensor:
+    """usr/diff/diffusion.py:68-70."""
+    return x * torch.tanh(F.softplus(x))
+
+
+def step_embedding(p: Dict[str, Tensor], t: Tensor, C: int) -> Tensor:
+    """usr/diff/net.py:119-120 -- SinusoidalPosEmb -> Linear -> Mish -> Linear.  [B] -> [B, C]."""
+    e = sinusoidal_pos_emb(t, C)
+    e = F.linear(e, p["mlp.0.weight"], p["mlp.0.bias"])
+    e = mish(e)
+    return F.linear(e, p["mlp.2.weight"], p["mlp.2.bias"])
+
+
+def n_residual_layers(p: Dict[str, Tensor]) -> int:
+    n = 0
+    while f"residual_layers.{n}.dilated_conv.weight" in p:
+        n += 1
+    return n
+
+
+def residual_block(p: Dict[str, Tensor], i: int, dilation: int, x: Tensor, cond: Tensor,
+                   step: Tensor, operand: Optional[str] = None):
+    """usr/diff/net.py:66-78.  x [B,C,T], cond [B,H,T], step [B,C] -> (x', skip)."""
+    pre = f"residual_layers.{i}."
+    d = F.linear(step, p[pre + "diffusion_projection.weight"], p[pre + "diffusion_projection.bias"])
+    c = F.conv1d(_rnd(cond, operand), _rnd(p[pre + "conditioner_projection.weight"], operand),
+                 p[pre + "conditioner_projection.bias"])
+    y = x + d[:, :, None]
+    y = F.conv1d(_rnd(y, operand), _rnd(p[pre + "dilated_conv.weight"], operand),
+                 p[pre + "dilated_conv.bias"], padding=dilation, dilation=dilation) + c
+    gate, filt = torch.chunk(y, 2, dim=1)
+    y = torch.sigmoid(gate) * torch.tanh(filt)
+    y = F.conv1d(_rnd(y, operand), _rnd(p[pre + "output_projection.weight"], operand),
+                 p[pre + "output_projection.bias"])
+    residual, skip = torch.chunk(y, 2, dim=1)
+    return (x + residual) / math.sqrt(2.0), skip
+
+
+def diffnet_forward(p: Dict[str, Tensor], spec: Tensor, t: Tensor, cond: Tensor,
+                    dilation_cycle: int = 4, operand: Optional[str] = None) -> Tensor:
+    """usr/diff/net.py:107-130.  spec [B,1,M,T], t [B] int, cond [B,H,T] -> [B,1,M,T]."""
+    C = p["input_projection.weight"].shape[0]
+    L = n_residual_layers(p)
+    x = spec[:, 0]
+    x = F.conv1d(_rnd(x, operand), _rnd(p["input_projection.weight"], operand), p["input_projection.bias"])
+    x = F.relu(x)
+    step = step_embedding(p, t, C)
+    skip_sum = None
+    for i in range(L):
+        x, s = residual_block(p, i, 2 ** (i % dilation_cycle), x, cond, step, operand)
+        skip_sum = s if skip_sum is None else skip_sum + s
+    x = skip_sum / math.sqrt(L)
+    x = F.conv1d(_rnd(x, operand), _rnd(p["skip_projection.weight"], operand), p["skip_projection.bias"])
+    x = F.relu(x)
+    x = F.conv1d(_rnd(x, operand), _rnd(p["output_projection.weight"], operand), p["output_projection.bias"])
+    return x[:, None]
+
+
+# --------------------------------------------------------------------------------------
+# Gaussian diffusion schedule + ancestral sampler (usr/diff/shallow_diffusion_tts.py)
+# --------------------------------------------------------------------------------------
+
+def linear_beta_schedule(timesteps: int, max_beta: float) -> np.ndarray:
+    """usr/diff/shallow_diffusion_tts.py:44-49 (float64 numpy)."""
+    return np.linspace(1e-4, max_beta, timesteps)
+
+
+def cosine_beta_schedule(timesteps: int, s: float = 0.008) -> np.ndarray:
+    """usr/diff/shallow_diffusion_tts.py:52-62."""
+    steps = timesteps + 1
+    x = np.linspace(0, steps, steps)
+    ac = np.cos(((x / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = 1 - (ac[1:] / ac[:-1])
+    return np.clip(betas, a_min=0, a_max=0.999)
+
+
+def schedule_buffers(betas: np.ndarray) -> Dict[str, Tensor]:
+    """usr/diff/shallow_diffusion_tts.py:89-123 -- float64 math, buffers cast to fp32."""
+    betas = np.asarray(betas, dtype=np.float64)
+    alphas = 1. - betas
+    ac = np.cumprod(alphas, axis=0)
+    ac_prev = np.append(1., ac[:-1])
+    pv = betas * (1. - ac_prev) / (1. - ac)
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+    return {
+        "betas": f32(betas),
+        "alphas_cumprod": f32(ac),
+        "alphas_cumprod_prev": f32(ac_prev),
+        "sqrt_alphas_cumprod": f32(np.sqrt(ac)),
+        "sqrt_one_minus_alphas_cumprod": f32(np.sqrt(1. - ac)),
+        "log_one_minus_alphas_cumprod": f32(np.log(1. - ac)),
+        "sqrt_recip_alphas_cumprod": f32(np.sqrt(1. / ac)),
+        "sqrt_recipm1_alphas_cumprod": f32(np.sqrt(1. / ac - 1)),
+        "posterior_variance": f32(pv),
+        "posterior_log_variance_clipped": f32(np.log(np.maximum(pv, 1e-20))),
+        "posterior_mean_coef1": f32(betas * np.sqrt(ac_prev) / (1. - ac)),
+        "posterior_mean_coef2": f32((1. - ac_prev) * np.sqrt(alphas) / (1. - ac)),
+    }
+
+
+def norm_spec(x: Tensor, spec_min: Tensor, spec_max: Tensor) -> Tensor:
+    """usr/diff/shallow_diffusion_tts.py:275-276."""
+    return (x - spec_min) / (spec_max - spec_min) * 2 - 1
+
+
+def denorm_spec(x: Tensor, spec_min: Tensor, spec_max: Tensor) -> Tensor:
+    """usr/diff/shallow_diffusion_tts.py:278-279."""
+    return (x + 1) / 2 * (spec_max - spec_min) + spec_min
+
+
+def q_sample(sched: Dict[str, Tensor], x_start: Tensor, t: int, noise: Tensor) -> Tensor:
+    """usr/diff/shallow_diffusion_tts.py:203-208 (t broadcast over batch as at :252)."""
+    return sched["sqrt_alphas_cumprod"][t] * x_start + sched["sqrt_one_minus_alphas_cumprod"][t] * noise
+
+
+def p_sample(p: Dict[str, Tensor], sched: Dict[str, Tensor], x: Tensor, t: int, cond: Tensor,
+             noise: Tensor, dilation_cycle: int = 4, operand: Optional[str] = None,
+             clip_denoised: bool = True) -> Tensor:
+    """usr/diff/shallow_diffusion_tts.py:149-166 (+ :134-147).  One ancestral step with
+    injected noise z (the reference draws randn(x.shape) every step, also at t == 0)."""
+    B = x.shape[0]
+    tt = torch.full((B,), t, dtype=torch.long)
+    eps = diffnet_forward(p, x, tt, cond, dilation_cycle, operand)
+    x_recon = sched["sqrt_recip_alphas_cumprod"][t] * x - sched["sqrt_recipm1_alphas_cumprod"][t] * eps
+    if clip_denoised:
+        x_recon = x_recon.clamp(-1., 1.)
+    mean = sched["posterior_mean_coef1"][t] * x_recon + sched["posterior_mean_coef2"][t] * x
+    nonzero = 0.0 if t == 0 else 1.0
+    return mean + nonzero * (0.5 * sched["posterior_log_variance_clipped"][t]).exp() * noise
+
+
+def diffusion_infer(p: Dict[str, Tensor], sched: Dict[str, Tensor], spec_min: Tensor, spec_max: Tensor,
+                    cond_btH: Tensor, K_step: int, step_noise: Tensor,
+                    fs2_mel: Optional[Tensor] = None, start_noise: Optional[Tensor] = None,
+                    mel2ph: Optional[Tensor] = None, gaussian_start: bool = False,
+                    dilation_cycle: int = 4, operand: Optional[str] = None,
+                    return_trace: bool = False):
+    """Infer branch of GaussianDiffusion.forward, usr/diff/shallow_diffusion_tts.py:235,245-272.
+
+    cond_btH   [B,T,H]   = ret['decoder_inp'] (transposed to [B,H,T] at :235)
+    fs2_mel    [B,T,M]   = ret['mel_out'] of the FastSpeech2 decoder (shallow start, :246-252)
+    start_noise[B,1,M,T] = the randn_like of q_sample (:204) or the randn of gaussian_start (:256)
+    step_noise [K,B,1,M,T], index k is the k-th *executed* step, i.e. t = K_step-1-k (:266-267)
+    returns mel_out [B,T,M] (de-normalised, masked by mel2ph>0 as at :269-272)
+    """
+    cond = cond_btH.transpose(1, 2)
+    if gaussian_start:
+        x = start_noise
+    else:
+        xs = norm_spec(fs2_mel, spec_min, spec_max).transpose(1, 2)[:, None]
+        x = q_sample(sched, xs, K_step - 1, start_noise)
+    trace = []
+    for k, t in enumerate(reversed(range(K_step))):
+        x = p_sample(p, sched, x, t, cond, step_noise[k], dilation_cycle, operand)
+        if return_trace:
+            trace.append(x.clone())
+    out = denorm_spec(x[:, 0].transpose(1, 2), spec_min, spec_max)
+    if mel2ph is not None:
+        out = out * (mel2ph > 0).float()[:, :, None]
+    return (out, x, trace) if return_trace else out
+
+
+# --------------------------------------------------------------------------------------
+# NSF harmonic source (modules/parallel_wavegan/models/source.py)
+# --------------------------------------------------------------------------------------
+
+def sinegen(f0_up: Tensor, rand_ini: Tensor, noise: Tensor, sampling_rate: int, harmonic_num: int = 8,
+            sine_amp: float = 0.1, noise_std: float = 0.003, voiced_threshold: float = 0.0):
+    """SineGen.forward/_f02sine, source.py:45-74,105-138 (flag_for_pulse False).
+
+    f0_up [B,L,1]; rand_ini [B,dim] (column 0 forced to 0 as at :56); noise [B,L,dim] ~ N(0,1).
+    returns (sine_waves [B,L,dim], uv [B,L,1])
+    """
+    dim = harmonic_num + 1
+    mult = torch.arange(1, dim + 1, dtype=torch.float32)
+    f0_buf = f0_up[:, :, :1] * mult[None, None, :]                      # :112-118
+    rad = (f0_buf / sampling_rate) % 1                                   # :51
+    ri = rand_ini.clone()
+    ri[:, 0] = 0                                                         # :56
+    rad = rad.clone()
+    rad[:, 0, :] = rad[:, 0, :] + ri                                     # :57
+    tmp_over_one = torch.cumsum(rad, 1) % 1                              # :67
+    over_idx = (tmp_over_one[:, 1:, :] - tmp_over_one[:, :-1, :]) < 0    # :68-69
+    shift = torch.zeros_like(rad)
+    shift[:, 1:, :] = over_idx * -1.0                                    # :70-71
+    sines = torch.sin(torch.cumsum(rad + shift, dim=1) * 2 * np.pi)      # :73-74
+    sine_waves = sines * sine_amp                                        # :121
+    uv = torch.ones_like(f0_up) * (f0_up > voiced_threshold)             # :38-43,126
+    noise_amp = uv * noise_std + (1 - uv) * sine_amp / 3                 # :131
+    sine_waves = sine_waves * uv + noise_amp * noise                     # :133-137
+    return sine_waves, uv
+
+
+def nsf_source(p: Dict[str, Tensor], f0: Tensor, hop: int, rand_ini: Tensor, noise: Tensor,
+               sampling_rate: int, harmonic_num: int = 8) -> Tensor:
+    """hifigan.py:147-149 + SourceModuleHnNSF.forward source.py:386-399.
+    f0 [B,T] -> har_source [B,1,L] (nearest up-sample x hop, sines, Linear 9->1, tanh)."""
+    f0_up = f0[:, :, None].repeat_interleave(hop, dim=1)                 # nn.Upsample(nearest)
+    sine_wavs, _uv = sinegen(f0_up, rand_ini, noise, sampling_rate, harmonic_num)
+    merged = torch.tanh(F.linear(sine_wavs, p["m_source.l_linear.weight"], p["m_source.l_linear.bias"]))
+    return merged.transpose(1, 2)
+
+
+# --------------------------------------------------------------------------------------
+# HiFi-GAN generator (modules/hifigan/hifigan.py), weight-norm already folded
+# --------------------------------------------------------------------------------------
+
+def resblock1(p: Dict[str, Tensor], pre: str, x: Tensor, k: int, dilations: Sequence[int],
+              operand: Optional[str] = None) -> Tensor:
+    """ResBlock1.forward, hifigan.py:54-61."""
+    for m, d in enumerate(dilations):
+        xt = F.leaky_relu(x, LRELU_SLOPE)
+        xt = F.conv1d(_rnd(xt, operand), _rnd(p[f"{pre}convs1.{m}.weight"], operand), p[f"{pre}convs1.{m}.bias"],
+                      dilation=d, padding=(k * d - d) // 2)
+        xt = F.leaky_relu(xt, LRELU_SLOPE)
+        xt = F.conv1d(_rnd(xt, operand), _rnd(p[f"{pre}convs2.{m}.weight"], operand), p[f"{pre}convs2.{m}.bias"],
+                      dilation=1, padding=(k - 1) // 2)
+        x = xt + x
+    return x
+
+
+def hifigan_forward(p: Dict[str, Tensor], h: dict, mel: Tensor, f0: Optional[Tensor],
+                    rand_ini: Optional[Tensor] = None, src_noise: Optional[Tensor] = None,
+                    operand: Optional[str] = None, return_source: bool = False):
+    """HifiGanGenerator.forward, hifigan.py:144-173.  mel [B,80,T], f0 [B,T] -> wav [B,1,T*hop]."""
+    rates = list(h["upsample_rates"])
+    ksz = list(h["upsample_kernel_sizes"])
+    rk = list(h["resblock_kernel_sizes"])
+    rd = list(h["resblock_dilation_sizes"])
+    hop = int(np.prod(rates))
+    har = None
+    if f0 is not None:
+        har = nsf_source(p, f0, hop, rand_ini, src_noise, h["audio_sample_rate"])
+    x = F.conv1d(_rnd(mel, operand), _rnd(p["conv_pre.weight"], operand), p["conv_pre.bias"], padding=3)
+    for i, (u, k) in enumerate(zip(rates, ksz)):
+        x = F.leaky_relu(x, LRELU_SLOPE)
+        x = F.conv_transpose1d(_rnd(x, operand), _rnd(p[f"ups.{i}.weight"], operand), p[f"ups.{i}.bias"],
+                               stride=u, padding=(k - u) // 2)
+        if har is not None:
+            if i + 1 < len(rates):
+                s = int(np.prod(rates[i + 1:]))
+                xs = F.conv1d(har, p[f"noise_convs.{i}.weight"], p[f"noise_convs.{i}.bias"], stride=s, padding=s // 2)
+            else:
+                xs = F.conv1d(har, p[f"noise_convs.{i}.weight"], p[f"noise_convs.{i}.bias"])
+            xs = F.relu(xs)
+            C = xs.shape[1]
+            xs = F.layer_norm(xs.transpose(1, -1), (C,)).transpose(1, -1)
+            x = x + xs
+        acc = None
+        for j in range(len(rk)):
+            r = resblock1(p, f"resblocks.{i * len(rk) + j}.", x, rk[j], rd[j], operand)
+            acc = r if acc is None else acc + r
+        x = acc / len(rk)
+    x = F.leaky_relu(x)            # default slope 0.01, hifigan.py:169
+    x = F.conv1d(x, p["conv_post.weight"], p["conv_post.bias"], padding=3)
+    x = torch.tanh(x)
+    return (x, har) if return_source else x
+
+
+# --------------------------------------------------------------------------------------
+# Metrics used by the parity tests
+# --------------------------------------------------------------------------------------
+
+def snr_db(ref: Tensor, out: Tensor) -> float:
+    ref = ref.double().flatten()
+    out = out.double().flatten()
+    num = (ref * ref).sum()
+    den = ((ref - out) ** 2).sum().clamp_min(1e-300)
+    return float(10.0 * torch.log10(num / den))
