@@ -141,7 +141,64 @@ def stage_bench():
                   "algorithmic TFLOP/s %.1f" % (flops / ms / 1e9), "launches/sample", (_lib.launch_count() - n0) // 3)
 
 
-STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench}
+def _voc_setup():
+    import torch
+    import synth, svs_oracle as O
+    from bisinger_b200.vocoder import B200HifiGanGenerator
+    h = synth.HIFIGAN_CONFIG
+    sd = synth.hifigan_state(4321)
+    gen = B200HifiGanGenerator(h)
+    gen.load_folded_state_dict(sd, strict=True)
+    gen.build_plan(torch.device("cuda", 0))
+    return h, sd, gen, O, synth
+
+
+def stage_vocoder():
+    import torch
+    h, sd, gen, O, synth = _voc_setup()
+    for (B, T) in ((2, 64), (1, 300), (3, 131)):
+        inp = synth.vocoder_inputs(11, B, T)
+        t0 = time.time()
+        ref, har_ref = O.hifigan_forward(sd, h, inp["mel"], inp["f0"], inp["rand_ini"], inp["src_noise"], return_source=True)
+        emu = O.hifigan_forward(sd, h, inp["mel"], inp["f0"], inp["rand_ini"], inp["src_noise"], operand="bf16")
+        t1 = time.time()
+        har = gen.plan.source(inp["f0"], inp["rand_ini"], inp["src_noise"]).cpu()
+        print("SOURCE", (B, T), "max|har-ref| %.3e" % (har - har_ref[:, 0]).abs().max().item(), "har rms %.3f" % har_ref.pow(2).mean().sqrt().item())
+        out = gen(inp["mel"].cuda(), inp["f0"].cuda(), inp["rand_ini"].cuda(), inp["src_noise"].cuda()).cpu()
+        print("VOCODER", (B, T), "SNR dB %.2f" % O.snr_db(ref, out), "emulated-bf16 SNR %.2f" % O.snr_db(ref, emu), "SNR vs emu %.2f" % O.snr_db(emu, out),
+              "max abs %.3e" % (out - ref).abs().max().item(), "oracle_s %.2f" % (t1 - t0), "nan", int(torch.isnan(out).sum()))
+        out2 = gen(inp["mel"].cuda(), None).cpu()
+        ref2 = O.hifigan_forward(sd, h, inp["mel"], None)
+        print("   no-f0 path SNR dB %.2f" % O.snr_db(ref2, out2))
+        out3 = gen(inp["mel"].cuda(), inp["f0"].cuda(), seed=3)
+        print("   device-RNG path finite", bool(torch.isfinite(out3).all()), "rms %.3f" % out3.pow(2).mean().sqrt().item())
+
+
+def stage_vbench():
+    import torch
+    from bisinger_b200 import _lib
+    h, sd, gen, O, synth = _voc_setup()
+    for (B, T) in ((1, 938), (32, 1875), (8, 11250)):
+        g = torch.Generator().manual_seed(1)
+        mel = (torch.rand(B, 80, T, generator=g) * 5 - 6).cuda()
+        f0 = (torch.rand(B, T, generator=g) * 300 + 100).cuda()
+        for i in range(2):
+            gen(mel, f0, seed=i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for i in range(3):
+            gen(mel, f0, seed=10 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        flops = 375734272.0 * B * T
+        print("VBENCH", (B, T), "ms %.2f" % ms, "audio_s/s %.1f" % (B * T / 187.5 / (ms / 1e3)), "algorithmic TFLOP/s %.1f" % (flops / ms / 1e9),
+              "launches", (_lib.launch_count() - n0) // 3, "mem GB %.1f" % (torch.cuda.mem_get_info()[1] / 1e9 - torch.cuda.mem_get_info()[0] / 1e9))
+
+
+STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench, "vocoder": stage_vocoder, "vbench": stage_vbench}
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--run":
