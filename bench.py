@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the BiSinger synthesis hot path on B200 (contract: see the task brief / DESIGN.md §7).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|bf16]
+
+Metric (BASELINE.json): seconds of audio synthesised per wall-second, diffusion mel (K=100 DiffNet sampler) + HiFi-GAN/NSF
+vocoder.  Workload at every N: cfg3 = one batch of 32 x 10 s phrases (T = 1875 mel frames, 24 kHz, hop 128) per rank per
+step, random-init models of the named architecture and synthetic conditioner outputs (cond / fs2_mel / f0); the FastSpeech2
+conditioner is outside the hot path and is not run.  Ranks are independent replicas (weak scaling, no
+collective on the data path); time = max over ranks of the CUDA-event time of the K timed steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, HOP, MEL, HID = 24000, 128, 80, 256
+K_STEP, MAX_BETA = 100, 0.06
+BATCH, FRAMES = 32, 1875                      # cfg3: 32 phrases x 10 s
+FLOPS_DIFFNET_FRAME_STEP = 26_427_392         # SURVEY.md §8d (2*MAC, what the reference computes)
+FLOPS_GATE_GEMM_FRAME = 2 * (3 * 256 + 256) * 512   # dilated conv k=3 256->512 + conditioner 1x1 256->512 per frame per layer
+FLOPS_HIFIGAN_FRAME = 375_734_272
+METRIC = "audio_seconds_per_second"
+UNIT = "audio-s/s"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1394.9))), hbm=float(d.get("hbm_gbs", 6549.8)),
+                    source="MEASURED_PEAKS.json (sustained bf16 cuBLAS)")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback of B200_PROFILING.md (sustained ~1.4 PFLOP/s)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_models(dev, precision):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import synth   # seeded random-init weights of the named architecture (no checkpoints reachable)
+    import torch
+    from bisinger_b200 import B200DiffNet, B200GaussianDiffusion
+    from bisinger_b200.diffusion import linear_beta_schedule
+    from bisinger_b200.vocoder import B200HifiGanGenerator
+    net = B200DiffNet(MEL)
+    net.load_state_dict(synth.diffnet_state(1234), strict=True)
+    gd = B200GaussianDiffusion(None, MEL, net, timesteps=K_STEP, K_step=K_STEP, betas=linear_beta_schedule(K_STEP, MAX_BETA),
+                               spec_min=synth.SPEC_MIN, spec_max=synth.SPEC_MAX, precision=precision,
+                               hparams=dict(hidden_size=HID, residual_layers=20, residual_channels=256, dilation_cycle_length=4,
+                                            keep_bins=MEL, gaussian_start=False))
+    gd.to(dev)
+    gd.build_plan()
+    gen = B200HifiGanGenerator(synth.HIFIGAN_CONFIG)
+    gen.load_folded_state_dict(synth.hifigan_state(4321), strict=True)
+    gen.to(dev)
+    gen.build_plan(dev)
+    return gd, gen, synth
+
+
+def host_inputs(synth, B, T, seed):
+    import torch
+    k = synth.kernel_inputs(seed, B, T, 1)
+    v = synth.vocoder_inputs(seed + 1, B, T)
+    return k["cond"].contiguous(), k["fs2_mel"].contiguous(), v["f0"].contiguous()
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bisinger_b200 import launch_count
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path for the product arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gd, gen, synth = build_models(dev, args.precision)
+    B, T = args.batch, args.frames
+    audio_s = B * T * HOP / SR
+    cond_h, mel_h, f0_h = host_inputs(synth, B, T, 1000 + rank)
+    cond_p, mel_p, f0_p = cond_h.pin_memory(), mel_h.pin_memory(), f0_h.pin_memory()
+    wav_p = torch.empty((B, T * HOP), dtype=torch.float32).pin_memory()
+    cond_d, mel_d, f0_d = cond_p.to(dev), mel_p.to(dev), f0_p.to(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_resident(i):
+        mel = gd.sample(cond_d, mel_d, seed=i)                          # [B,T,80]
+        return gen(mel.transpose(1, 2).contiguous(), f0_d, seed=i)      # [B,1,T*hop]
+
+    def step_e2e(i):
+        c = cond_p.to(dev, non_blocking=True); m = mel_p.to(dev, non_blocking=True); f = f0_p.to(dev, non_blocking=True)
+        mel = gd.sample(c, m, seed=i)
+        wav = gen(mel.transpose(1, 2).contiguous(), f, seed=i)
+        wav_p.copy_(wav[:, 0], non_blocking=True)
+        return wav
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, sample_clocks=False):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        cs = ClockSampler(local) if sample_clocks else None
+        if cs:
+            cs.start()
+        n0 = launch_count()
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = cs.stop() if cs else None
+        n1 = launch_count()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, n1 - n0, clocks
+
+    for i in range(args.warmup):
+        step_resident(i)
+    ms, launches, clocks = timed(step_resident, args.steps, sample_clocks=True)
+    for i in range(max(1, args.warmup // 2)):
+        step_e2e(i)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    value = world * args.steps * audio_s / (ms / 1e3)
+    e2e = world * args.steps * audio_s / (ms_e2e / 1e3)
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"cfg3: full hot path, batch {B} x {T * HOP / SR:.0f} s phrases (T={T}) per GPU per step, K={K_STEP} "
+                               f"DiffNet sampler (20x256, CUDA-graph captured) + HiFi-GAN/NSF vocoder (hop 128, 512 ch); random-init "
+                               f"weights, synthetic cond/fs2_mel/f0 (FastSpeech2 conditioner not part of the path)",
+                   "global_batch": B * world, "frames": T, "k_step": K_STEP, "parallelism": f"replicas x{world}",
+                   "contraction": args.precision + (" (3 tensor-core MMAs per product: hi*hi + lo*hi + hi*lo)" if args.precision == "bf16x3" else ""),
+                   "l2": "per-step working set ~6 GB >> 126 MB L2, no flush needed"},
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(cond_p.numel() + mel_p.numel() + f0_p.numel()) * 4,
+                "d2h_bytes_per_step": int(wav_p.numel()) * 4},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if rank == 0:
+        peaks = read_peaks()
+        reps = 200
+        k_ms = gd.plan.time_kernel(0, B, T, reps)
+        gate_flops = FLOPS_GATE_GEMM_FRAME * B * T
+        achieved = gate_flops / (k_ms * 1e-3) / 1e12
+        line["roofline"] = {
+            "bound": "tensor", "kernel": "conv_gemm_kernel<256,%d,EPI_GATE> (dilated conv + conditioner GEMM, gate epilogue)" % (3 if args.precision == "bf16x3" else 1),
+            "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops"], 4),
+            "traffic": None, "avg_launch_ms": round(k_ms, 4), "algorithmic_flops_per_launch": gate_flops,
+            "issued_mma_flops_per_algorithmic_flop": 3 if args.precision == "bf16x3" else 1,
+            "peak_source": peaks["source"] + ", of measured",
+            "share_of_step": round(20 * K_STEP * k_ms / (ms / args.steps), 3),
+        }
+        line["pipeline_algorithmic_tflops"] = round((FLOPS_DIFFNET_FRAME_STEP * K_STEP + FLOPS_HIFIGAN_FRAME) * B * T * world * args.steps / (ms * 1e-3) / 1e12, 1)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(steps=1, warmup=1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_reference(steps: int, warmup: int):
+    """The reference algorithm on the host cores: the oracle port (oracle/svs_oracle.py, a restatement pinned against the
+    executed reference) -- the reference tree itself does not travel to the GPU box.  Bounded sample of the cfg3 workload: ONE
+    of the 32 phrases (B=1, T=1875, K=100 sampler + vocoder), all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+
+    import svs_oracle as O
+    import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, T = 1, FRAMES
+    sd, vsd = synth.diffnet_state(1234), synth.hifigan_state(4321)
+    sched = O.schedule_buffers(O.linear_beta_schedule(K_STEP, MAX_BETA))
+    smin, smax = torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX)
+    inp = synth.kernel_inputs(1000, B, T, K_STEP)
+    vin = synth.vocoder_inputs(1001, B, T)
+
+    def one():
+        with torch.no_grad():
+            mel = O.diffusion_infer(sd, sched, smin, smax, inp["cond"], K_STEP, inp["step_noise"], inp["fs2_mel"], inp["start_noise"])
+            return O.hifigan_forward(vsd, synth.HIFIGAN_CONFIG, mel.transpose(1, 2), vin["f0"], vin["rand_ini"], vin["src_noise"])
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    audio = steps * B * T * HOP / SR
+    return {"value": round(audio / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} x (1 phrase of 10 s, T={T}, K={K_STEP} sampler + vocoder), fp32 torch CPU, {cores} threads",
+            "seconds": round(dt, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_reference(steps=args.steps, warmup=min(args.warmup, 1))
+    ms = base["seconds"] * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(ms / args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg3 hot path (K=100 DiffNet sampler + HiFi-GAN/NSF vocoder) -- reference algorithm on the host CPU; each "
+                               "step is a bounded sample: 1 of the 32 phrases (10 s, T=1875)", "parallelism": "host threads"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun as the driver would
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,7 @@ class HifiganConfig(C.Structure):
 EXPORTS = (
     "bsg_abi_version", "bsg_last_error", "bsg_kernel_launch_count",
     "bsg_diffusion_plan_create", "bsg_diffusion_plan_destroy", "bsg_diffusion_sample", "bsg_diffnet_forward",
+    "bsg_diffusion_time_kernel",
     "bsg_hifigan_plan_create", "bsg_hifigan_plan_destroy", "bsg_hifigan_forward", "bsg_hifigan_source",
     "bsg_selftest_conv",
 )
@@ -73,6 +74,7 @@ def lib() -> C.CDLL:
     L.bsg_diffusion_plan_destroy.restype = None
     L.bsg_diffusion_sample.argtypes = [vp, fp, fp, fp, fp, C.c_ulonglong, fp, ip, ip, fp, fp, vp]
     L.bsg_diffnet_forward.argtypes = [vp, fp, ip, fp, ip, ip, fp, vp]
+    L.bsg_diffusion_time_kernel.argtypes = [vp, ip, ip, ip, ip, C.POINTER(C.c_float), vp]
     L.bsg_hifigan_plan_create.argtypes = [C.POINTER(HifiganConfig), C.POINTER(C.c_float), C.c_size_t, C.c_int, C.POINTER(vp)]
     L.bsg_hifigan_plan_destroy.argtypes = [vp]
     L.bsg_hifigan_plan_destroy.restype = None

@@ -66,6 +66,13 @@ int bsg_diffnet_forward(bsg_diffusion_plan* plan, const float* spec, int t, cons
     });
 }
 
+int bsg_diffusion_time_kernel(bsg_diffusion_plan* plan, int which, int B, int T, int reps, float* avg_ms, void* stream) {
+    return guarded([&] {
+        B200_CHECK(plan && avg_ms, "null argument");
+        *avg_ms = plan->impl.time_kernel(which, B, T, reps, static_cast<cudaStream_t>(stream));
+    });
+}
+
 int bsg_hifigan_plan_create(const bsg_hifigan_config* cfg, const float* weights_host, size_t n_weights, int device,
                             bsg_hifigan_plan** out) {
     return guarded([&] {

@@ -298,6 +298,80 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
 
 static void set_w(ConvGemmArgs& a, PackedW& w, int n_tile) { w.maps(n_tile, a.wmap[0], a.wmap[1]); }
 
+
+// dilated conv(x + d) + conditioner projection -> sigmoid*tanh gate (net.py:67-74)
+ConvGemmArgs DiffusionPlan::gate_args(Workspace& w, int l) {
+    const int H = cfg.hidden_size, C = cfg.residual_channels;
+    Layer& ly = layers[l];
+    ConvGemmArgs a{};
+    set_geometry(a, w.B, w.T, 2 * C, 256);
+    a.amap[0] = w.m_xa[0]; a.amap[1] = w.m_xa[1];
+    a.amap[2] = w.m_cond[0]; a.amap[3] = w.m_cond[1];
+    set_w(a, ly.g1, 256);
+    a.n_seg = 4;
+    for (int tap = 0; tap < 3; ++tap) a.seg[tap] = Segment{0, (tap - 1) * ly.dilation, 0, C / kBlockK, tap * C};
+    a.seg[3] = Segment{1, 0, 0, H / kBlockK, 3 * C};
+    a.epi.bias = ly.g1_bias.as<float>();
+    a.epi.out_hi = w.z_hi.as<__nv_bfloat16>();
+    a.epi.out_lo = terms == 3 ? w.z_lo.as<__nv_bfloat16>() : nullptr;
+    a.epi.out_pitch = C;
+    return a;
+}
+
+// output projection -> residual / skip (net.py:76-78), skip sum (net.py:126)
+ConvGemmArgs DiffusionPlan::resskip_args(Workspace& w, int l, const float* lut_t) {
+    const int C = cfg.residual_channels, L = cfg.residual_layers;
+    Layer& ly = layers[l];
+    const bool lo = terms == 3;
+    ConvGemmArgs a{};
+    set_geometry(a, w.B, w.T, 2 * C, 256);
+    a.amap[0] = w.m_z[0]; a.amap[1] = w.m_z[1];
+    set_w(a, ly.g2, 256);
+    a.n_seg = 1;
+    a.seg[0] = Segment{0, 0, 0, C / kBlockK, 0};
+    a.epi.bias = ly.g2_bias.as<float>();
+    a.epi.f32_a = w.xres.as<float>();
+    a.epi.f32_b = w.skip.as<float>();
+    a.epi.out_hi = w.xa_hi.as<__nv_bfloat16>(); a.epi.out_lo = lo ? w.xa_lo.as<__nv_bfloat16>() : nullptr;
+    a.epi.out2_hi = w.s_hi.as<__nv_bfloat16>(); a.epi.out2_lo = lo ? w.s_lo.as<__nv_bfloat16>() : nullptr;
+    a.epi.dvec = (l + 1 < L) ? lut_t + static_cast<size_t>(l + 1) * C : nullptr;
+    a.epi.out_pitch = C;
+    a.epi.flags = (l == 0 ? 1 : 0) | (l == L - 1 ? 2 : 0);
+    a.epi.c0 = 1.0f / std::sqrt(static_cast<float>(L));
+    return a;
+}
+
+// Average duration of one hot kernel, measured with CUDA events on `st`: `reps` back-to-back launches cycling through
+// the layers (so weights change from launch to launch as in a real step).  which: 0 = gate GEMM, 1 = residual/skip GEMM.
+float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t st) {
+    B200_CHECK(which == 0 || which == 1, "unknown kernel id");
+    B200_CHECK(reps > 0, "reps must be positive");
+    B200_CUDA(cudaSetDevice(device));
+    Workspace& w = workspace(B, T);
+    const int L = cfg.residual_layers;
+    cudaEvent_t e0, e1;
+    B200_CUDA(cudaEventCreate(&e0));
+    B200_CUDA(cudaEventCreate(&e1));
+    auto run = [&](int n) {
+        for (int i = 0; i < n; ++i) {
+            const int l = i % L;
+            if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st);
+            else launch_conv_gemm(256, terms, EPI_RES_SKIP, resskip_args(w, l == 0 ? 1 : l, lut.as<float>()), st);
+            ++launches, ++g_launch_count;
+        }
+    };
+    run(3);
+    B200_CUDA(cudaEventRecord(e0, st));
+    run(reps);
+    B200_CUDA(cudaEventRecord(e1, st));
+    B200_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms / static_cast<float>(reps);
+}
+
 // One DiffNet evaluation at diffusion step t (net.py:107-130) followed by `tail`:
 //   tail == 0: posterior update of xt (p_sample), tail == 1: write eps to ws.eps
 void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail,
@@ -324,41 +398,10 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         ++launches, ++g_launch_count;
     }
     for (int l = 0; l < L; ++l) {
-        Layer& ly = layers[l];
-        {   // dilated conv(x + d) + conditioner projection -> sigmoid*tanh gate (net.py:67-74)
-            ConvGemmArgs a{};
-            set_geometry(a, B, T, 2 * C, 256);
-            a.amap[0] = w.m_xa[0]; a.amap[1] = w.m_xa[1];
-            a.amap[2] = w.m_cond[0]; a.amap[3] = w.m_cond[1];
-            set_w(a, ly.g1, 256);
-            a.n_seg = 4;
-            for (int tap = 0; tap < 3; ++tap) a.seg[tap] = Segment{0, (tap - 1) * ly.dilation, 0, C / kBlockK, tap * C};
-            a.seg[3] = Segment{1, 0, 0, H / kBlockK, 3 * C};
-            a.epi.bias = ly.g1_bias.as<float>();
-            a.epi.out_hi = w.z_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.z_lo);
-            a.epi.out_pitch = C;
-            launch_conv_gemm(256, terms, EPI_GATE, a, st);
-            ++launches, ++g_launch_count;
-        }
-        {   // output projection -> residual / skip (net.py:76-78), skip sum (net.py:126)
-            ConvGemmArgs a{};
-            set_geometry(a, B, T, 2 * C, 256);
-            a.amap[0] = w.m_z[0]; a.amap[1] = w.m_z[1];
-            set_w(a, ly.g2, 256);
-            a.n_seg = 1;
-            a.seg[0] = Segment{0, 0, 0, C / kBlockK, 0};
-            a.epi.bias = ly.g2_bias.as<float>();
-            a.epi.f32_a = w.xres.as<float>();
-            a.epi.f32_b = w.skip.as<float>();
-            a.epi.out_hi = w.xa_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.xa_lo);
-            a.epi.out2_hi = w.s_hi.as<__nv_bfloat16>(); a.epi.out2_lo = nz(w.s_lo);
-            a.epi.dvec = (l + 1 < L) ? lut_t + static_cast<size_t>(l + 1) * C : nullptr;
-            a.epi.out_pitch = C;
-            a.epi.flags = (l == 0 ? 1 : 0) | (l == L - 1 ? 2 : 0);
-            a.epi.c0 = 1.0f / std::sqrt(static_cast<float>(L));
-            launch_conv_gemm(256, terms, EPI_RES_SKIP, a, st);
-            ++launches, ++g_launch_count;
-        }
+        launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st);
+        ++launches, ++g_launch_count;
+        launch_conv_gemm(256, terms, EPI_RES_SKIP, resskip_args(w, l, lut_t), st);
+        ++launches, ++g_launch_count;
     }
     {   // skip_projection + ReLU (net.py:127-128)
         ConvGemmArgs a{};

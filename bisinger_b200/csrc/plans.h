@@ -21,6 +21,7 @@ public:
     void sample(const float* cond, const float* fs2_mel, const float* start_noise, const float* step_noise,
                 unsigned long long seed, const int64_t* mel2ph, int B, int T, float* mel_out, float* x_final, cudaStream_t st);
     void denoise(const float* spec, int t, const float* cond, int B, int T, float* eps_out, cudaStream_t st);
+    float time_kernel(int which, int B, int T, int reps, cudaStream_t st);
 
     bsg_diffnet_config cfg;
     int device;
@@ -39,6 +40,8 @@ private:
         float sqrt_ac, sqrt_1mac, c0, c1, c2, c3, sigma;
     };
     Workspace& workspace(int B, int T);
+    ConvGemmArgs gate_args(Workspace& w, int l);
+    ConvGemmArgs resskip_args(Workspace& w, int l, const float* lut_t);
     void enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail, cudaStream_t st);
 
     std::vector<Layer> layers;

@@ -160,6 +160,12 @@ class DiffusionPlan:
                                                   _lib.current_stream_ptr(self.device)))
         return out
 
+    def time_kernel(self, which: int, B: int, T: int, reps: int = 40) -> float:
+        """Average ms per launch of one hot kernel (0 = gate GEMM, 1 = residual/skip GEMM), CUDA events on the current stream."""
+        ms = C.c_float()
+        _lib.check(_lib.lib().bsg_diffusion_time_kernel(self._h, which, B, T, reps, C.byref(ms), _lib.current_stream_ptr(self.device)))
+        return float(ms.value)
+
     def sample(self, cond_btH, fs2_mel=None, start_noise=None, step_noise=None, seed: int = 0, mel2ph=None,
                return_x: bool = False):
         """cond_btH [B,T,H]; fs2_mel [B,T,M] or None (Gaussian start); start_noise [B,1,M,T]; step_noise [K,B,1,M,T]

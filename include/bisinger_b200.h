@@ -106,6 +106,13 @@ int bsg_diffusion_sample(bsg_diffusion_plan* plan, const float* cond, const floa
 int bsg_diffnet_forward(bsg_diffusion_plan* plan, const float* spec, int t, const float* cond, int B, int T,
                         float* eps_out, void* stream);
 
+/* Measurement hook for bench.py's roofline line: average duration (ms, CUDA events on `stream`) of `reps` back-to-back
+ * launches of one hot kernel at batch shape (B, T), cycling through the residual layers.
+ *   which = 0: dilated-conv + conditioner GEMM with the sigmoid*tanh gate epilogue (net.py:67-74)
+ *   which = 1: output-projection GEMM with the residual / skip epilogue (net.py:76-78)
+ * The kernels run on the plan's workspace (whatever the last sample left there); results are discarded.       */
+int bsg_diffusion_time_kernel(bsg_diffusion_plan* plan, int which, int B, int T, int reps, float* avg_ms, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * HiFi-GAN / NSF generator
  * ------------------------------------------------------------------------------------------------ */

@@ -1,0 +1,75 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/bisinger_b200.h declares; the host
+wrappers mirror the reference's parameter names; no CPU fallback exists."""
+import os
+import re
+
+import pytest
+import torch
+
+import synth
+from bisinger_b200 import _lib
+from bisinger_b200.diffusion import B200DiffNet, B200GaussianDiffusion
+from bisinger_b200.vocoder import B200HifiGanGenerator
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+
+
+def test_header_symbols_exported():
+    _ensure_built()
+    hdr = open(os.path.join(ROOT, "include", "bisinger_b200.h")).read()
+    declared = set(re.findall(r"\b(bsg_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.bsg_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    _ensure_built()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    net = B200DiffNet(80)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 80, 8), torch.zeros(1, dtype=torch.long), torch.zeros(1, 256, 8))
+
+
+def test_diffnet_state_dict_names_match_reference_layout():
+    sd = synth.diffnet_state(1)
+    net = B200DiffNet(80)
+    missing = net.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert list(net.state_dict().keys()) == list(sd.keys())          # registration order == blob order
+    assert net.flat_weights().numel() == 15086416
+
+
+def test_hifigan_state_dict_names():
+    gen = B200HifiGanGenerator(synth.HIFIGAN_CONFIG)
+    keys = list(gen.state_dict().keys())
+    assert "conv_pre.weight_g" in keys and "ups.0.weight_v" in keys and "resblocks.11.convs2.2.weight_g" in keys
+    assert len(keys) == 244                                          # SURVEY.md §9.1 (weight-normed)
+    w_before = gen.flat_weights()
+    gen.remove_weight_norm()
+    assert len(gen.state_dict()) == 166
+    assert torch.allclose(w_before, gen.flat_weights(), atol=1e-6)   # folding == remove_weight_norm
+    gen.load_folded_state_dict(synth.hifigan_state(2), strict=True)
+    assert gen.flat_weights().numel() == 13673867
+
+
+def test_gaussian_diffusion_buffers():
+    import svs_oracle as O
+    net = B200DiffNet(80)
+    gd = B200GaussianDiffusion(None, 80, net, timesteps=100, K_step=100, betas=O.linear_beta_schedule(100, 0.06),
+                               spec_min=synth.SPEC_MIN, spec_max=synth.SPEC_MAX)
+    ref = O.schedule_buffers(O.linear_beta_schedule(100, 0.06))
+    for k, v in ref.items():
+        assert torch.equal(getattr(gd, k), v), k
+    assert gd.spec_min.shape == (1, 1, 80)
+    with pytest.raises(NotImplementedError):
+        gd(torch.zeros(1, 4, dtype=torch.long), infer=False)

@@ -1,0 +1,110 @@
+"""CPU tests: the oracle restatement (oracle/svs_oracle.py) against the golden vectors written by the executed
+reference (oracle/make_golden.py) and -- when /root/reference is present -- against the live reference modules."""
+import numpy as np
+import pytest
+import torch
+
+import svs_oracle as O
+import synth
+from make_golden import DIFF_CASES, EPS_CASES, K_STEP, MAX_BETA, VOC_CASES
+
+torch.set_num_threads(8)
+
+
+@pytest.fixture(scope="module")
+def sd_diff():
+    return synth.diffnet_state(1234)
+
+
+@pytest.fixture(scope="module")
+def sd_voc():
+    return synth.hifigan_state(4321)
+
+
+def test_schedule_buffers_bit_exact(golden):
+    s = O.schedule_buffers(O.linear_beta_schedule(K_STEP, MAX_BETA))
+    for k in ("betas", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+              "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped"):
+        assert np.array_equal(s[k].numpy(), golden["sched." + k]), k
+
+
+def test_schedule_known_answers():
+    # SURVEY.md §9.2 (probe of the reference, timesteps=100, linear, max_beta=0.06)
+    s = O.schedule_buffers(O.linear_beta_schedule(100, 0.06))
+    assert abs(s["sqrt_recip_alphas_cumprod"][99].item() - 4.635046) < 1e-5
+    assert abs(s["sqrt_recipm1_alphas_cumprod"][50].item() - 1.09157) < 1e-5
+    assert abs(s["posterior_mean_coef1"][1].item() - 0.875817) < 1e-6
+    assert abs(s["posterior_log_variance_clipped"][0].item() - (-46.051701)) < 1e-4
+    assert s["posterior_mean_coef2"][0].item() == 0.0
+
+
+@pytest.mark.parametrize("i", range(len(EPS_CASES)))
+def test_diffnet_forward_vs_golden(golden, sd_diff, i):
+    c = EPS_CASES[i]
+    inp = synth.kernel_inputs(c["seed"], c["B"], c["T"], 1)
+    with torch.no_grad():
+        eps = O.diffnet_forward(sd_diff, inp["start_noise"], torch.full((c["B"],), c["t"]), inp["cond"].transpose(1, 2))
+    # identical arithmetic up to the order of the skip summation (the reference stacks then sums, net.py:126)
+    assert np.abs(eps.numpy() - golden[f"eps.{i}"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("i", range(len(DIFF_CASES)))
+def test_sampler_vs_golden(golden, sd_diff, i):
+    c = DIFF_CASES[i]
+    inp = synth.kernel_inputs(c["seed"], c["B"], c["T"], c["K"])
+    sched = O.schedule_buffers(O.linear_beta_schedule(K_STEP, MAX_BETA))
+    smin, smax = torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX)
+    with torch.no_grad():
+        mel, x0, _ = O.diffusion_infer(sd_diff, sched, smin, smax, inp["cond"], K_STEP, inp["step_noise"], inp["fs2_mel"],
+                                       inp["start_noise"], return_trace=True)
+    assert np.abs(mel.numpy() - golden[f"mel.{i}"]).max() < 1e-4
+    assert np.abs(x0.numpy() - golden[f"x0.{i}"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("i", range(len(VOC_CASES)))
+def test_vocoder_vs_golden(golden, sd_voc, i):
+    c = VOC_CASES[i]
+    inp = synth.vocoder_inputs(c["seed"], c["B"], c["T"])
+    with torch.no_grad():
+        wav, har = O.hifigan_forward(sd_voc, synth.HIFIGAN_CONFIG, inp["mel"], inp["f0"], inp["rand_ini"], inp["src_noise"],
+                                     return_source=True)
+        wav2 = O.hifigan_forward(sd_voc, synth.HIFIGAN_CONFIG, inp["mel"], None)
+    assert np.abs(har.numpy() - golden[f"har.{i}"]).max() < 1e-6
+    assert np.abs(wav.numpy() - golden[f"wav.{i}"]).max() < 1e-5
+    assert np.abs(wav2.numpy() - golden[f"wav_nof0.{i}"]).max() < 1e-5
+
+
+def test_zero_init_trap_documented(sd_diff):
+    """The reference zero-initialises DiffNet.output_projection.weight (net.py:105): eps would then be independent of the
+    input and any parity test vacuous.  The synthetic factory must NOT reproduce that."""
+    assert float(sd_diff["output_projection.weight"].abs().max()) > 0
+
+
+def test_operand_rounding_model_orders(sd_diff):
+    """bf16 operand rounding must be much worse than the bf16x3 split -- guards the emulation used by the
+    GPU tests to separate precision effects from bugs."""
+    inp = synth.kernel_inputs(5, 1, 64, 1)
+    t = torch.full((1,), 37)
+    with torch.no_grad():
+        ref = O.diffnet_forward(sd_diff, inp["start_noise"], t, inp["cond"].transpose(1, 2))
+        bf = O.diffnet_forward(sd_diff, inp["start_noise"], t, inp["cond"].transpose(1, 2), operand="bf16")
+    e = float((bf - ref).abs().max())
+    assert 1e-3 < e < 0.2
+
+
+reference_present = __import__("ref_shim").available()
+
+
+@pytest.mark.skipif(not reference_present, reason="/root/reference not mounted (GPU box)")
+def test_live_reference_matches_oracle(sd_diff):
+    """Build container only: run the unmodified reference DiffNet on fresh inputs and compare with the restatement."""
+    import ref_shim
+    ns = ref_shim.load()
+    net = ns.DiffNet(80)
+    net.load_state_dict(sd_diff, strict=True)
+    inp = synth.kernel_inputs(99, 2, 70, 1)
+    t = torch.full((2,), 63)
+    with torch.no_grad():
+        a = net(inp["start_noise"], t, inp["cond"].transpose(1, 2))
+        b = O.diffnet_forward(sd_diff, inp["start_noise"], t, inp["cond"].transpose(1, 2))
+    assert float((a - b).abs().max()) < 2e-5

@@ -198,7 +198,20 @@ def stage_vbench():
               "launches", (_lib.launch_count() - n0) // 3, "mem GB %.1f" % (torch.cuda.mem_get_info()[1] / 1e9 - torch.cuda.mem_get_info()[0] / 1e9))
 
 
-STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench, "vocoder": stage_vocoder, "vbench": stage_vbench}
+def stage_proftarget():
+    """Target for ncu: a few launches of the two DiffNet layer kernels at the cfg3 shape."""
+    import torch
+    sd, sched, plan, inp, O, synth = _diff_setup(1, 8, 100, os.environ.get("BSG_PREC", "bf16x3"))
+    B, T = 32, 1875
+    g = torch.Generator().manual_seed(1)
+    cond = torch.randn(B, T, 256, generator=g).cuda()
+    fs2 = (torch.rand(B, T, 80, generator=g) * 5 - 6).cuda()
+    plan.sample(cond, fs2, None, None, seed=1)
+    torch.cuda.synchronize()
+    print("gate ms", plan.time_kernel(0, B, T, 6), "resskip ms", plan.time_kernel(1, B, T, 6))
+
+
+STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench, "vocoder": stage_vocoder, "vbench": stage_vbench, "proftarget": stage_proftarget}
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--run":
