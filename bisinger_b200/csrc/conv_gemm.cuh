@@ -14,8 +14,10 @@
 // and each k-block issues A_hi*W_hi + A_lo*W_hi + A_hi*W_lo into the same fp32 accumulator (~16
 // mantissa bits).  The 100-step sampler needs it to stay within the 1e-2 mel tolerance.
 //
-// Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer (one thread),
-// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).
+// Warp roles (320 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer (one thread),
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; the two warps of a quadrant split the tile's columns --
+// a single warp per scheduler was instruction-latency bound, profiles/r01_b).  Before working on tile i every
+// epilogue warp L2-prefetches the fp32 operands it will read-modify-write for tile i+1 (residual stream / skip sum).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -28,8 +30,8 @@ namespace b200 {
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kMaxSeg = 12;
-constexpr int kGemmThreads = 192;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kGemmThreads = 32 * (2 + 8);   // producer, MMA, 8 epilogue warps
+constexpr int kSmemBudget = 196 * 1024;
 
 struct Segment {
     int a_src;      // index of the A tensor-map pair (hi = 2*a_src, lo = 2*a_src + 1)
@@ -126,40 +128,8 @@ __device__ __forceinline__ float fast_tanh(float x) {
 }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-// store 32 floats as bf16 hi (and lo) rows: 64 B each, 16-byte vector stores
-__device__ __forceinline__ void store_split32(const float (&v)[32], __nv_bfloat16* hi_row, __nv_bfloat16* lo_row) {
-    uint32_t ph[16], pl[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        float h0, h1;
-        __nv_bfloat16 bh0, bl0, bh1, bl1;
-        split_bf16(v[2 * i], h0, bh0, bl0);
-        split_bf16(v[2 * i + 1], h1, bh1, bl1);
-        ph[i] = static_cast<uint32_t>(__bfloat16_as_ushort(bh0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bh1)) << 16);
-        pl[i] = static_cast<uint32_t>(__bfloat16_as_ushort(bl0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bl1)) << 16);
-    }
-    uint4* dh = reinterpret_cast<uint4*>(hi_row);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dh[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-    if (lo_row != nullptr) {
-        uint4* dl = reinterpret_cast<uint4*>(lo_row);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dl[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
-    }
-}
-__device__ __forceinline__ void load_f32x32(const float* p, float (&v)[32]) {
-    const float4* s = reinterpret_cast<const float4*>(p);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float4 q = s[i];
-        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-    }
-}
-__device__ __forceinline__ void store_f32x32(float* p, const float (&v)[32]) {
-    float4* d = reinterpret_cast<float4*>(p);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
+
+// ---- accumulator access -----------------------------------------------------------------------
 __device__ __forceinline__ void ld_acc32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after any divergent store path
@@ -177,6 +147,60 @@ __device__ __forceinline__ void ld_acc16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- coalescing transpose ---------------------------------------------------------------------
+// tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).  Row-per-thread global accesses
+// touch 32 different 128-byte lines per instruction, which made the epilogue LSU-bound (profiles/r01_a).  Each
+// warp therefore bounces its 32x32 fp32 chunk (16 rows at a time) through a private shared-memory tile (row pitch
+// 36 floats: conflict-free for the float4 row writes and for the float2 reads below) and continues in a transposed
+// ownership: lane l holds, for rp = 0..15, the two columns cc = 2*(l & 15), cc+1 of row 2*rp + (l >> 4).
+// A warp instruction then covers two full 128-byte row segments -> fully coalesced loads and stores.
+constexpr int kStagePitch = 36;
+constexpr int kStageFloatsPerWarp = 16 * kStagePitch;
+constexpr int kEpiWarps = 8;          // two column groups x four TMEM lane quadrants
+
+struct LanePos {
+    int r0;   // 0 / 1: which row of each row pair this lane owns
+    int cc;   // first of the two columns (within the 32-column chunk) this lane owns
+};
+__device__ __forceinline__ LanePos lane_pos(int lane) { return LanePos{lane >> 4, (lane & 15) * 2}; }
+
+__device__ __forceinline__ void chunk_transpose(float* stage, int lane, const float (&v)[32], float2 (&o)[16]) {
+    const LanePos lp = lane_pos(lane);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (lp.r0 == half) {
+            float4* w = reinterpret_cast<float4*>(stage + (lane & 15) * kStagePitch);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int rp = 0; rp < 8; ++rp)
+            o[half * 8 + rp] = *reinterpret_cast<const float2*>(stage + (2 * rp + lp.r0) * kStagePitch + lp.cc);
+        __syncwarp();
+    }
+}
+// load one accumulator chunk (32 rows x 32 columns starting at column c) in transposed ownership
+__device__ __forceinline__ void ld_chunk_t(uint32_t tacc, int c, float* stage, int lane, float2 (&o)[16]) {
+    float v[32];
+    ld_acc32(tacc + c, v);
+    chunk_transpose(stage, lane, v, o);
+}
+// bf16 hi/lo split of two neighbouring values, packed for 4-byte stores
+__device__ __forceinline__ void st_split2(float2 y, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(y.x, y.y);
+    const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+    *reinterpret_cast<uint32_t*>(hi) = hu;
+    if (lo != nullptr) {
+        const float hx = __uint_as_float(hu << 16), hy = __uint_as_float(hu & 0xffff0000u);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(y.x - hx, y.y - hy);
+        *reinterpret_cast<uint32_t*>(lo) = *reinterpret_cast<const uint32_t*>(&l);
+    }
+}
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+
 // BIAS_ACT flags (HiFi-GAN epilogue)
 enum : int {
     BA_ADD_RES = 1,      // y += aux0[row][n]            (ResBlock1 residual, hifigan.py:60)
@@ -187,112 +211,153 @@ enum : int {
     BA_ACT_FROM_B = 32,  // the bf16 activation is taken from the accumulated f32_b value instead of y
 };
 
-template <int N_TILE, int EPI>
-__device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t tacc, int b, int t, int n_tile) {
+// b: batch index, t_warp: first row (within the batch) of this warp's 32 accumulator lanes, grp: column group of the
+// warp (0/1: two warps share a TMEM lane quadrant and split the tile's columns), stage: the warp's transpose tile.
+// FULL: all 32 rows of the warp are inside the batch (no row predicates).  Rows t >= L are never stored.
+template <int N_TILE, int EPI, bool FULL>
+__device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t tacc, int b, int t_warp, int n_tile, int grp,
+                                             float* stage, int lane) {
     const EpiParams& e = args.epi;
-    const bool row_ok = t < args.L;
-    const long long row = static_cast<long long>(b) * args.L + t;
+    const LanePos lp = lane_pos(lane);
+    const long long row_w = static_cast<long long>(b) * args.L + t_warp;   // global row of the warp's lane 0
+    const int rows_left = args.L - t_warp - lp.r0;                          // row pair rp is valid iff 2*rp < rows_left
+#define B200_ROW_OK(rp) (FULL || 2 * (rp) < rows_left)
+    // column range of this warp
+    constexpr int kSplit = (N_TILE % 64 == 0) ? 2 : 1;
+    constexpr int kColsPerGrp = N_TILE / kSplit;
+    if (kSplit == 1 && grp != 0) return;
+    const int c_begin = grp * kColsPerGrp;
+    (void)rows_left; (void)c_begin; (void)row_w; (void)lp;
 
     if constexpr (EPI == EPI_F32) {
 #pragma unroll 1
-        for (int c = 0; c < N_TILE; c += 32) {
-            float v[32];
-            ld_acc32(tacc + c, v);
-            if (row_ok) {
-                const int n = n_tile * N_TILE + c;
+        for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
+            float2 o[16];
+            ld_chunk_t(tacc, c, stage, lane, o);
+            const int n = n_tile * N_TILE + c + lp.cc;
+            const float2 bias = ldg2(e.bias + n);
+            float* p = e.f32_a + (row_w + lp.r0) * e.out_pitch + n;
+            const long long st = 2LL * e.out_pitch;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __ldg(e.bias + n + i);
-                store_f32x32(e.f32_a + row * e.out_pitch + n, v);
-            }
+            for (int rp = 0; rp < 16; ++rp)
+                if (B200_ROW_OK(rp)) st2(p + rp * st, make_float2(o[rp].x + bias.x, o[rp].y + bias.y));
         }
     } else if constexpr (EPI == EPI_INPROJ) {
 #pragma unroll 1
-        for (int c = 0; c < N_TILE; c += 32) {
-            float v[32];
-            ld_acc32(tacc + c, v);
-            if (row_ok) {
-                const int n = n_tile * N_TILE + c;
+        for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
+            float2 o[16];
+            ld_chunk_t(tacc, c, stage, lane, o);
+            const int n = n_tile * N_TILE + c + lp.cc;
+            const float2 bias = ldg2(e.bias + n), d = ldg2(e.dvec + n);
+            const long long off0 = (row_w + lp.r0) * e.out_pitch + n, st = 2LL * e.out_pitch;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(e.bias + n + i), 0.0f);
-                store_f32x32(e.f32_a + row * e.out_pitch + n, v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __ldg(e.dvec + n + i);
-                store_split32(v, e.out_hi + row * e.out_pitch + n, e.out_lo ? e.out_lo + row * e.out_pitch + n : nullptr);
+            for (int rp = 0; rp < 16; ++rp) {
+                if (B200_ROW_OK(rp)) {
+                    const long long off = off0 + rp * st;
+                    const float2 x = make_float2(fmaxf(o[rp].x + bias.x, 0.0f), fmaxf(o[rp].y + bias.y, 0.0f));
+                    st2(e.f32_a + off, x);
+                    st_split2(make_float2(x.x + d.x, x.y + d.y), e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr);
+                }
             }
         }
     } else if constexpr (EPI == EPI_GATE) {
         // tile columns [0, N_TILE/2) = gate pre-activations, [N_TILE/2, N_TILE) = filter pre-activations of
         // the same N_TILE/2 channels (weight rows permuted by the packer).
         constexpr int HALF = N_TILE / 2;
+        static_assert(HALF % 64 == 0, "gate epilogue splits HALF over two warp groups");
 #pragma unroll 1
-        for (int c = 0; c < HALF; c += 32) {
-            float g[32], f[32];
-            ld_acc32(tacc + c, g);
-            ld_acc32(tacc + HALF + c, f);
-            if (row_ok) {
-                const int nb = n_tile * N_TILE + c;   // bias index of gate col c ; filter bias at +HALF
-                const int ch = n_tile * HALF + c;     // output channel
+        for (int c = grp * (HALF / 2); c < (grp + 1) * (HALF / 2); c += 32) {
+            float2 g[16], f[16];
+            ld_chunk_t(tacc, c, stage, lane, g);
+            ld_chunk_t(tacc, HALF + c, stage, lane, f);
+            const int nb = n_tile * N_TILE + c + lp.cc;   // bias index of the gate columns ; filter bias at +HALF
+            const int ch = n_tile * HALF + c + lp.cc;     // output channel
+            const float2 bg = ldg2(e.bias + nb), bf = ldg2(e.bias + nb + HALF);
+            const long long off0 = (row_w + lp.r0) * e.out_pitch + ch, st = 2LL * e.out_pitch;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float gg = g[i] + __ldg(e.bias + nb + i);
-                    const float ff = f[i] + __ldg(e.bias + nb + HALF + i);
-                    g[i] = fast_sigmoid(gg) * fast_tanh(ff);
+            for (int rp = 0; rp < 16; ++rp) {
+                if (B200_ROW_OK(rp)) {
+                    const float2 z = make_float2(fast_sigmoid(g[rp].x + bg.x) * fast_tanh(f[rp].x + bf.x),
+                                                 fast_sigmoid(g[rp].y + bg.y) * fast_tanh(f[rp].y + bf.y));
+                    st_split2(z, e.out_hi + off0 + rp * st, e.out_lo ? e.out_lo + off0 + rp * st : nullptr);
                 }
-                store_split32(g, e.out_hi + row * e.out_pitch + ch, e.out_lo ? e.out_lo + row * e.out_pitch + ch : nullptr);
             }
         }
     } else if constexpr (EPI == EPI_RES_SKIP) {
         static_assert(N_TILE == 256, "residual/skip split assumes 256 channels per tile");
+        const float rs2 = 0.70710678118654752440f;
+        const long long st = 2LL * e.out_pitch;
+        if (n_tile == 0) {
+            // x <- (x + residual) / sqrt(2)  (net.py:78) ; next layer's conv input = x + d_{l+1}  (net.py:69)
 #pragma unroll 1
-        for (int c = 0; c < N_TILE; c += 32) {
-            float v[32];
-            ld_acc32(tacc + c, v);
-            if (!row_ok) continue;
-            const int n = n_tile * N_TILE + c;
+            for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
+                const int cl = c + lp.cc;
+                const long long off0 = (row_w + lp.r0) * e.out_pitch + cl;
+                float2 x[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(e.bias + n + i);
-            if (n_tile == 0) {
-                float* xr = e.f32_a + row * e.out_pitch + c;
-                float x[32];
-                load_f32x32(xr, x);
+                for (int rp = 0; rp < 16; ++rp)
+                    if (B200_ROW_OK(rp)) x[rp] = ld2(e.f32_a + off0 + rp * st);
+                float2 o[16];
+                ld_chunk_t(tacc, c, stage, lane, o);
+                const float2 bias = ldg2(e.bias + cl);
+                float2 d = make_float2(0.f, 0.f);
+                if (e.dvec != nullptr) d = ldg2(e.dvec + cl);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = (x[i] + v[i]) * 0.70710678118654752440f;
-                store_f32x32(xr, v);
-                if (e.dvec != nullptr) {   // not needed after the last layer
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += __ldg(e.dvec + c + i);
-                    store_split32(v, e.out_hi + row * e.out_pitch + c, e.out_lo ? e.out_lo + row * e.out_pitch + c : nullptr);
+                for (int rp = 0; rp < 16; ++rp) {
+                    if (B200_ROW_OK(rp)) {
+                        const long long off = off0 + rp * st;
+                        const float2 y = make_float2((x[rp].x + o[rp].x + bias.x) * rs2, (x[rp].y + o[rp].y + bias.y) * rs2);
+                        st2(e.f32_a + off, y);
+                        if (e.dvec != nullptr)   // not needed after the last layer
+                            st_split2(make_float2(y.x + d.x, y.y + d.y), e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr);
+                    }
                 }
-            } else {
-                float* sk = e.f32_b + row * e.out_pitch + c;
-                if (!(e.flags & 1)) {
-                    float s[32];
-                    load_f32x32(sk, s);
+            }
+        } else {
+            // skip accumulation (net.py:78,126); the last layer hands sum/sqrt(L) to the head GEMM as bf16 operand
+#pragma unroll 1
+            for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
+                const int cl = c + lp.cc;
+                const long long off0 = (row_w + lp.r0) * e.out_pitch + cl;
+                float2 sk[16];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += s[i];
+                for (int rp = 0; rp < 16; ++rp) {
+                    sk[rp] = make_float2(0.f, 0.f);
+                    if (!(e.flags & 1) && B200_ROW_OK(rp)) sk[rp] = ld2(e.f32_b + off0 + rp * st);
                 }
-                if (e.flags & 2) {   // last layer: hand sum/sqrt(L) to the head GEMM as bf16 operand
+                float2 o[16];
+                ld_chunk_t(tacc, c, stage, lane, o);
+                const float2 bias = ldg2(e.bias + N_TILE + cl);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= e.c0;
-                    store_split32(v, e.out2_hi + row * e.out_pitch + c, e.out2_lo ? e.out2_lo + row * e.out_pitch + c : nullptr);
-                } else {
-                    store_f32x32(sk, v);
+                for (int rp = 0; rp < 16; ++rp) {
+                    if (B200_ROW_OK(rp)) {
+                        const long long off = off0 + rp * st;
+                        const float2 y = make_float2(sk[rp].x + o[rp].x + bias.x, sk[rp].y + o[rp].y + bias.y);
+                        if (e.flags & 2) st_split2(make_float2(y.x * e.c0, y.y * e.c0), e.out2_hi + off, e.out2_lo ? e.out2_lo + off : nullptr);
+                        else st2(e.f32_b + off, y);
+                    }
                 }
             }
         }
     } else if constexpr (EPI == EPI_RELU_BF16) {
 #pragma unroll 1
-        for (int c = 0; c < N_TILE; c += 32) {
-            float v[32];
-            ld_acc32(tacc + c, v);
-            if (row_ok) {
-                const int n = n_tile * N_TILE + c;
+        for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
+            float2 o[16];
+            ld_chunk_t(tacc, c, stage, lane, o);
+            const int n = n_tile * N_TILE + c + lp.cc;
+            const float2 bias = ldg2(e.bias + n);
+            const long long off0 = (row_w + lp.r0) * e.out_pitch + n, st = 2LL * e.out_pitch;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(e.bias + n + i), 0.0f);
-                store_split32(v, e.out_hi + row * e.out_pitch + n, e.out_lo ? e.out_lo + row * e.out_pitch + n : nullptr);
-            }
+            for (int rp = 0; rp < 16; ++rp)
+                if (B200_ROW_OK(rp))
+                    st_split2(make_float2(fmaxf(o[rp].x + bias.x, 0.0f), fmaxf(o[rp].y + bias.y, 0.0f)), e.out_hi + off0 + rp * st,
+                              e.out_lo ? e.out_lo + off0 + rp * st : nullptr);
         }
     } else if constexpr (EPI == EPI_POSTERIOR) {
+        // row-per-thread ownership: row t_warp + lane (only warp group 0 gets here: kSplit == 1)
+        const int t = t_warp + lane;
+        const bool row_ok = FULL || t < args.L;
+        const long long row = row_w + lane;
         // N_TILE == mel bins (80).  x_t lives in the reference layout [B][M][T] (T contiguous): lanes hold
         // consecutive t, so the per-channel accesses below are coalesced.
         static_assert(N_TILE % 16 == 0 && N_TILE <= 96, "posterior epilogue expects <= 96 mel bins");
@@ -372,45 +437,79 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
             }
         }
     } else if constexpr (EPI == EPI_BIAS_ACT) {
+        const long long st = 2LL * e.out_pitch, sta = 2LL * e.act_pitch;
 #pragma unroll 1
-        for (int c = 0; c < N_TILE; c += 32) {
-            float v[32];
-            ld_acc32(tacc + c, v);
-            if (!row_ok) continue;
-            const int n = n_tile * N_TILE + c;            // bias / logical channel index
-            const long long o = row * e.out_pitch + e.out_col0 + n;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(e.bias + n + i);
+        for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
+            const int n = n_tile * N_TILE + c + lp.cc;     // bias / logical channel index
+            const long long o32 = (row_w + lp.r0) * e.out_pitch + e.out_col0 + n;
+            const long long o16 = (row_w + lp.r0) * e.act_pitch + n;
+            float2 r[16], s[16];
             if (e.flags & BA_ADD_RES) {
-                float r[32];
-                load_f32x32(e.aux0 + o, r);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += r[i];
+                for (int rp = 0; rp < 16; ++rp)
+                    if (B200_ROW_OK(rp)) r[rp] = ld2(e.aux0 + o32 + rp * st);
             }
-            if (e.flags & BA_WRITE_F32) store_f32x32(e.f32_a + o, v);
-            if (e.flags & BA_ACCUM_F32B) {
-                float s[32];
-                if (e.flags & BA_ACCUM_INIT) {
+            if ((e.flags & BA_ACCUM_F32B) && !(e.flags & BA_ACCUM_INIT)) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) s[i] = v[i] * e.c0;
-                } else {
-                    load_f32x32(e.f32_b + o, s);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) s[i] += v[i] * e.c0;
-                }
-                store_f32x32(e.f32_b + o, s);
-                if (e.flags & BA_ACT_FROM_B) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = s[i];
-                }
+                for (int rp = 0; rp < 16; ++rp)
+                    if (B200_ROW_OK(rp)) s[rp] = ld2(e.f32_b + o32 + rp * st);
             }
-            if (e.flags & BA_WRITE_ACT) {
+            float2 o[16];
+            ld_chunk_t(tacc, c, stage, lane, o);
+            const float2 bias = ldg2(e.bias + n);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.0f ? v[i] : v[i] * e.c1;
-                const long long oa = row * e.act_pitch + n;
-                store_split32(v, e.out_hi + oa, e.out_lo ? e.out_lo + oa : nullptr);
+            for (int rp = 0; rp < 16; ++rp) {
+                if (B200_ROW_OK(rp)) {
+                    float2 y = make_float2(o[rp].x + bias.x, o[rp].y + bias.y);
+                    if (e.flags & BA_ADD_RES) { y.x += r[rp].x; y.y += r[rp].y; }
+                    if (e.flags & BA_WRITE_F32) st2(e.f32_a + o32 + rp * st, y);
+                    if (e.flags & BA_ACCUM_F32B) {
+                        float2 a = make_float2(y.x * e.c0, y.y * e.c0);
+                        if (!(e.flags & BA_ACCUM_INIT)) { a.x += s[rp].x; a.y += s[rp].y; }
+                        st2(e.f32_b + o32 + rp * st, a);
+                        if (e.flags & BA_ACT_FROM_B) y = a;
+                    }
+                    if (e.flags & BA_WRITE_ACT) {
+                        y.x = y.x > 0.0f ? y.x : y.x * e.c1;
+                        y.y = y.y > 0.0f ? y.y : y.y * e.c1;
+                        st_split2(y, e.out_hi + o16 + rp * sta, e.out_lo ? e.out_lo + o16 + rp * sta : nullptr);
+                    }
+                }
             }
         }
+    }
+#undef B200_ROW_OK
+}
+
+// L2 prefetch of the fp32 tiles the epilogue of `tile` will read (this warp's 32 rows x its column group).
+template <int N_TILE, int EPI>
+__device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int tile, int quad, int grp, int lane) {
+    const EpiParams& e = args.epi;
+    const int n_tile = tile % args.n_tiles_n;
+    const int m = tile / args.n_tiles_n;
+    const int b = m / args.tiles_per_batch;
+    const int t0 = (m % args.tiles_per_batch) * kTileM + quad * 32;
+    constexpr int kSplit = (N_TILE % 64 == 0) ? 2 : 1;
+    if (kSplit == 1 && grp != 0) return;
+    constexpr int kCols = N_TILE / kSplit;
+    constexpr int kLinesPerRow = (kCols * 4 + 127) / 128;
+    const float* src0 = nullptr;
+    const float* src1 = nullptr;
+    int col = grp * kCols;
+    if constexpr (EPI == EPI_RES_SKIP) {
+        src0 = n_tile == 0 ? e.f32_a : ((e.flags & 1) ? nullptr : e.f32_b);
+    } else {
+        col += e.out_col0 + n_tile * N_TILE;
+        if (e.flags & BA_ADD_RES) src0 = e.aux0;
+        if ((e.flags & BA_ACCUM_F32B) && !(e.flags & BA_ACCUM_INIT)) src1 = e.f32_b;
+    }
+    const int rows = min(32, args.L - t0);
+    const long long row0 = static_cast<long long>(b) * args.L + t0;
+    for (int idx = lane; idx < rows * kLinesPerRow; idx += 32) {
+        const int r = idx / kLinesPerRow, ln = idx % kLinesPerRow;
+        const long long off = (row0 + r) * e.out_pitch + col + ln * 32;
+        if (src0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src0 + off));
+        if (src1) asm volatile("prefetch.global.L2 [%0];" ::"l"(src1 + off));
     }
 }
 
@@ -425,7 +524,8 @@ struct GemmSmem {
     static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kBarBytes = 256;
-    static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 for manual alignment
+    static constexpr int kXposeBytes = kEpiWarps * kStageFloatsPerWarp * 4;   // one 16x36 fp32 transpose tile per epilogue warp
+    static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kXposeBytes + 1024;  // +1024 for manual alignment
     static_assert(kStages >= 2, "need at least a double-buffered pipeline");
     static_assert(kBBytes % 1024 == 0, "B tile must keep 1024-byte swizzle alignment");
 };
@@ -449,13 +549,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     uint64_t* tfull_bar = bars + 2 * S::kStages;
     uint64_t* tempty_bar = bars + 2 * S::kStages + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 4);
+    float* xpose = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + S::kBarBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 32) {
         for (int s = 0; s < S::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -533,7 +634,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             }
             umma_commit(&tfull_bar[acc]);             // accumulator complete -> epilogue
         }
-    } else if (warp >= 2) {
+    } else if (warp >= 2 && warp < 2 + kEpiWarps) {
         // ================= Epilogue warps =================
         const int quad = warp & 3;
         int it = 0;
@@ -542,16 +643,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             const int n_tile = tile % args.n_tiles_n;
             const int m = tile / args.n_tiles_n;
             const int b = m / args.tiles_per_batch;
-            const int t = (m % args.tiles_per_batch) * kTileM + quad * 32 + lane;
+            const int t_warp = (m % args.tiles_per_batch) * kTileM + quad * 32;
             mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * N_TILE;
-            run_epilogue<N_TILE, EPI>(args, tacc, b, t, n_tile);
+            float* stage = xpose + (warp - 2) * kStageFloatsPerWarp;
+            const int grp = (warp - 2) >> 2;
+            if constexpr (EPI == EPI_RES_SKIP || EPI == EPI_BIAS_ACT) {
+                const int nt = tile + gridDim.x;
+                if (nt < args.num_tiles) prefetch_rmw_tile<N_TILE, EPI>(args, nt, quad, grp, lane);
+            }
+            if (args.L - t_warp >= 32) run_epilogue<N_TILE, EPI, true>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
+            else run_epilogue<N_TILE, EPI, false>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
     }
+
 
     tc_fence_before();
     __syncthreads();

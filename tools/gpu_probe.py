@@ -199,16 +199,11 @@ def stage_vbench():
 
 
 def stage_proftarget():
-    """Target for ncu: a few launches of the two DiffNet layer kernels at the cfg3 shape."""
+    """Target for ncu: a few launches of one DiffNet layer kernel (BSG_WHICH = 0 gate / 1 residual-skip) at the cfg3 shape."""
     import torch
     sd, sched, plan, inp, O, synth = _diff_setup(1, 8, 100, os.environ.get("BSG_PREC", "bf16x3"))
-    B, T = 32, 1875
-    g = torch.Generator().manual_seed(1)
-    cond = torch.randn(B, T, 256, generator=g).cuda()
-    fs2 = (torch.rand(B, T, 80, generator=g) * 5 - 6).cuda()
-    plan.sample(cond, fs2, None, None, seed=1)
-    torch.cuda.synchronize()
-    print("gate ms", plan.time_kernel(0, B, T, 6), "resskip ms", plan.time_kernel(1, B, T, 6))
+    which = int(os.environ.get("BSG_WHICH", "1"))
+    print("kernel", which, "ms", plan.time_kernel(which, 32, 1875, 4))
 
 
 STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench, "vocoder": stage_vocoder, "vbench": stage_vbench, "proftarget": stage_proftarget}
