@@ -205,6 +205,14 @@ def run_ours(args):
             "peak_source": peaks["source"] + ", of measured",
             "share_of_step": round(20 * K_STEP * k_ms / (ms / args.steps), 3),
         }
+        r_ms = gd.plan.time_kernel(1, B, T, reps)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream); mel_t = gd.sample(cond_d, mel_d, seed=99); e1.record(stream)
+        gen(mel_t.transpose(1, 2).contiguous(), f0_d, seed=99); e2.record(stream)
+        torch.cuda.synchronize(dev)
+        line["breakdown_ms"] = {"sampler": round(e0.elapsed_time(e1), 2), "vocoder": round(e1.elapsed_time(e2), 2),
+                                "gate_gemm_launch": round(k_ms, 4), "resskip_gemm_launch": round(r_ms, 4),
+                                "layer_gemms_share_of_sampler": round(20 * K_STEP * (k_ms + r_ms) / e0.elapsed_time(e1), 3)}
         line["pipeline_algorithmic_tflops"] = round((FLOPS_DIFFNET_FRAME_STEP * K_STEP + FLOPS_HIFIGAN_FRAME) * B * T * world * args.steps / (ms * 1e-3) / 1e12, 1)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(steps=1, warmup=1)

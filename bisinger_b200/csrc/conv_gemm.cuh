@@ -118,6 +118,14 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, uint32_t
     return (w & 1) ? n.y : n.x;
 }
 
+// four standard normals from one Philox call (counter = idx4)
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32_t step, uint64_t idx4) {
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(idx4), static_cast<uint32_t>(idx4 >> 32), step, 0x5eed4u),
+                                  make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Epilogue helpers
 // ---------------------------------------------------------------------------------------------
@@ -386,19 +394,27 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
         } else if (row_ok) {
             float* xt = e.f32_a + (static_cast<long long>(b) * M) * args.L + t;
             const float* nz = e.aux0 ? e.aux0 + (static_cast<long long>(b) * M) * args.L + t : nullptr;
+            const unsigned long long seed = (nz == nullptr && e.c4 != 0.0f) ? __ldg(e.seed_ptr) : 0ull;
 #pragma unroll
-            for (int c = 0; c < N_TILE; ++c) {
-                const float eps = xnew[c] + __ldg(e.bias + c);
-                const float x = xt[static_cast<long long>(c) * args.L];
-                float x0 = e.c0 * x - e.c1 * eps;                       // predict_start_from_noise (:134-138)
-                x0 = fminf(fmaxf(x0, -1.0f), 1.0f);                      // clamp_ (:153-154)
-                float mean = e.c2 * x0 + e.c3 * x;                       // q_posterior (:140-147)
-                float z;
-                if (nz != nullptr) z = nz[static_cast<long long>(c) * args.L];
-                else z = philox_normal(__ldg(e.seed_ptr), e.step, (static_cast<uint64_t>(b) * M + c) * args.L + t);
-                const float xn = mean + e.c4 * z;                        // (:166), c4 = 0 at t == 0
-                xt[static_cast<long long>(c) * args.L] = xn;
-                xnew[c] = xn;
+            for (int c4 = 0; c4 < N_TILE; c4 += 4) {
+                // one Philox4x32-10 call yields the four normals of channels c4..c4+3 at this (b, t)
+                float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (nz == nullptr && e.c4 != 0.0f)   // the noise of the t == 0 step is multiplied by zero (:165): skip drawing it
+                    z4 = philox_normal4(seed, e.step, (static_cast<uint64_t>(b) * (M / 4) + c4 / 4) * args.L + t);
+                const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = c4 + i;
+                    const float eps = xnew[c] + __ldg(e.bias + c);
+                    const float x = xt[static_cast<long long>(c) * args.L];
+                    float x0 = e.c0 * x - e.c1 * eps;                       // predict_start_from_noise (:134-138)
+                    x0 = fminf(fmaxf(x0, -1.0f), 1.0f);                      // clamp_ (:153-154)
+                    const float mean = e.c2 * x0 + e.c3 * x;                 // q_posterior (:140-147)
+                    const float z = nz != nullptr ? nz[static_cast<long long>(c) * args.L] : zz[i];
+                    const float xn = mean + e.c4 * z;                        // (:166), c4 = 0 at t == 0
+                    xt[static_cast<long long>(c) * args.L] = xn;
+                    xnew[c] = xn;
+                }
             }
             // bf16 operand copy [B][T][M] for the next step's input projection
             if (e.out_hi != nullptr) {
