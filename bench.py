@@ -26,7 +26,10 @@ SR, HOP, MEL, HID = 24000, 128, 80, 256
 K_STEP, MAX_BETA = 100, 0.06
 BATCH, FRAMES = 32, 1875                      # cfg3: 32 phrases x 10 s
 FLOPS_DIFFNET_FRAME_STEP = 26_427_392         # SURVEY.md §8d (2*MAC, what the reference computes)
-FLOPS_GATE_GEMM_FRAME = 2 * (3 * 256 + 256) * 512   # dilated conv k=3 256->512 + conditioner 1x1 256->512 per frame per layer
+FLOPS_GATE_GEMM_FRAME = 2 * (3 * 256) * 512           # dilated conv k=3 256->512 per frame per layer (the step-invariant
+#   conditioner 1x1 is hoisted out of the K loop and evaluated once per batch: SURVEY.md §8d allows exactly this)
+FLOPS_COND_ONCE_FRAME = 20 * 2 * 256 * 512            # 5 242 880 per frame, once
+FLOPS_DIFFNET_FRAME_STEP_HOISTED = FLOPS_DIFFNET_FRAME_STEP - FLOPS_COND_ONCE_FRAME   # 21 184 512
 FLOPS_HIFIGAN_FRAME = 375_734_272
 METRIC = "audio_seconds_per_second"
 UNIT = "audio-s/s"
@@ -198,7 +201,7 @@ def run_ours(args):
         gate_flops = FLOPS_GATE_GEMM_FRAME * B * T
         achieved = gate_flops / (k_ms * 1e-3) / 1e12
         line["roofline"] = {
-            "bound": "tensor", "kernel": "conv_gemm_kernel<256,%d,EPI_GATE> (dilated conv + conditioner GEMM, gate epilogue)" % (3 if args.precision == "bf16x3" else 1),
+            "bound": "tensor", "kernel": "conv_gemm_kernel<256,%d,EPI_GATE> (dilated-conv GEMM k=3 256->512, conditioner add + sigmoid*tanh gate epilogue)" % (3 if args.precision == "bf16x3" else 1),
             "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops"], 4),
             "traffic": None, "avg_launch_ms": round(k_ms, 4), "algorithmic_flops_per_launch": gate_flops,
             "issued_mma_flops_per_algorithmic_flop": 3 if args.precision == "bf16x3" else 1,
@@ -213,7 +216,7 @@ def run_ours(args):
         line["breakdown_ms"] = {"sampler": round(e0.elapsed_time(e1), 2), "vocoder": round(e1.elapsed_time(e2), 2),
                                 "gate_gemm_launch": round(k_ms, 4), "resskip_gemm_launch": round(r_ms, 4),
                                 "layer_gemms_share_of_sampler": round(20 * K_STEP * (k_ms + r_ms) / e0.elapsed_time(e1), 3)}
-        line["pipeline_algorithmic_tflops"] = round((FLOPS_DIFFNET_FRAME_STEP * K_STEP + FLOPS_HIFIGAN_FRAME) * B * T * world * args.steps / (ms * 1e-3) / 1e12, 1)
+        line["pipeline_algorithmic_tflops"] = round((FLOPS_DIFFNET_FRAME_STEP_HOISTED * K_STEP + FLOPS_COND_ONCE_FRAME + FLOPS_HIFIGAN_FRAME) * B * T * world * args.steps / (ms * 1e-3) / 1e12, 1)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(steps=1, warmup=1)
         print(json.dumps(line), flush=True)

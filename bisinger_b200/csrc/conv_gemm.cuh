@@ -275,18 +275,27 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
         static_assert(HALF % 64 == 0, "gate epilogue splits HALF over two warp groups");
 #pragma unroll 1
         for (int c = grp * (HALF / 2); c < (grp + 1) * (HALF / 2); c += 32) {
-            float2 g[16], f[16];
-            ld_chunk_t(tacc, c, stage, lane, g);
-            ld_chunk_t(tacc, HALF + c, stage, lane, f);
-            const int nb = n_tile * N_TILE + c + lp.cc;   // bias index of the gate columns ; filter bias at +HALF
+            const int nb = n_tile * N_TILE + c + lp.cc;   // packed column of the gate pre-activation ; filter at +HALF
             const int ch = n_tile * HALF + c + lp.cc;     // output channel
-            const float2 bg = ldg2(e.bias + nb), bf = ldg2(e.bias + nb + HALF);
+            // aux0 = precomputed conditioner projection + biases, f32 [rows][2*HALF*n_tiles] in the packed column order
+            const long long cp0 = (row_w + lp.r0) * (2LL * e.out_pitch) + nb, cst = 4LL * e.out_pitch;
+            float2 g[16], f[16], cp[16];
+#pragma unroll
+            for (int rp = 0; rp < 16; ++rp)
+                if (B200_ROW_OK(rp)) cp[rp] = ld2(e.aux0 + cp0 + rp * cst);
+            ld_chunk_t(tacc, c, stage, lane, g);
+#pragma unroll
+            for (int rp = 0; rp < 16; ++rp) { g[rp].x += cp[rp].x; g[rp].y += cp[rp].y; }
+#pragma unroll
+            for (int rp = 0; rp < 16; ++rp)
+                if (B200_ROW_OK(rp)) cp[rp] = ld2(e.aux0 + cp0 + HALF + rp * cst);
+            ld_chunk_t(tacc, HALF + c, stage, lane, f);
             const long long off0 = (row_w + lp.r0) * e.out_pitch + ch, st = 2LL * e.out_pitch;
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp) {
                 if (B200_ROW_OK(rp)) {
-                    const float2 z = make_float2(fast_sigmoid(g[rp].x + bg.x) * fast_tanh(f[rp].x + bf.x),
-                                                 fast_sigmoid(g[rp].y + bg.y) * fast_tanh(f[rp].y + bf.y));
+                    const float2 z = make_float2(fast_sigmoid(g[rp].x) * fast_tanh(f[rp].x + cp[rp].x),
+                                                 fast_sigmoid(g[rp].y) * fast_tanh(f[rp].y + cp[rp].y));
                     st_split2(z, e.out_hi + off0 + rp * st, e.out_lo ? e.out_lo + off0 + rp * st : nullptr);
                 }
             }
@@ -521,6 +530,16 @@ __device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int 
     }
     const int rows = min(32, args.L - t0);
     const long long row0 = static_cast<long long>(b) * args.L + t0;
+    if constexpr (EPI == EPI_GATE) {
+        // conditioner projection tile: this group's 64 gate columns and 64 filter columns (2 x 256 B per row)
+        constexpr int HALF = N_TILE / 2;
+        for (int idx = lane; idx < rows * 4; idx += 32) {
+            const int r = idx >> 2, q = idx & 3;
+            const long long off = (row0 + r) * (2LL * e.out_pitch) + n_tile * N_TILE + grp * (HALF / 2) + (q >> 1) * HALF + (q & 1) * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(e.aux0 + off));
+        }
+        return;
+    }
     for (int idx = lane; idx < rows * kLinesPerRow; idx += 32) {
         const int r = idx / kLinesPerRow, ln = idx % kLinesPerRow;
         const long long off = (row0 + r) * e.out_pitch + col + ln * 32;
@@ -665,7 +684,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * N_TILE;
             float* stage = xpose + (warp - 2) * kStageFloatsPerWarp;
             const int grp = (warp - 2) >> 2;
-            if constexpr (EPI == EPI_RES_SKIP || EPI == EPI_BIAS_ACT) {
+            if constexpr (EPI == EPI_RES_SKIP || EPI == EPI_BIAS_ACT || EPI == EPI_GATE) {
                 const int nt = tile + gridDim.x;
                 if (nt < args.num_tiles) prefetch_rmw_tile<N_TILE, EPI>(args, nt, quad, grp, lane);
             }

@@ -128,6 +128,7 @@ __global__ void init_x_kernel(int mode, const float* __restrict__ fs2_mel, const
 // ---------------------------------------------------------------------------------------------
 struct DiffusionPlan::Workspace {
     int B = 0, T = 0;
+    DevBuf cp;   // f32 [L][rows][2C]: conditioner projection + biases of every layer (step-invariant)
     DevBuf xt, xin_hi, xin_lo, cond_hi, cond_lo, xres, xa_hi, xa_lo, z_hi, z_lo, skip, s_hi, s_lo, h_hi, h_lo, mel, mel2ph, eps;
     CUtensorMap m_xin[2], m_cond[2], m_xa[2], m_z[2], m_s[2], m_h[2];
     cudaGraphExec_t graph = nullptr;
@@ -185,8 +186,10 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
         // G1 weights: [2C rows][K = 3*C (taps) + H (cond)], rows permuted so that every 256-row N tile holds the
         // gate rows of 128 channels followed by the filter rows of the same channels (gate = first half of the
         // conv output, filter = second half: net.py:73).
-        const int K1 = 3 * C + H;
-        std::vector<float> g1(static_cast<size_t>(2 * C) * K1), gb(2 * C);
+        // The conditioner projection is step-invariant: it is evaluated once per utterance batch (precompute_cond) and
+        // added in the gate epilogue, so the per-step gate GEMM only carries the three dilated taps (K = 3*C).
+        const int K1 = 3 * C;
+        std::vector<float> g1(static_cast<size_t>(2 * C) * K1), gc(static_cast<size_t>(2 * C) * H), gb(2 * C);
         for (int tile = 0; tile < 2; ++tile)
             for (int part = 0; part < 2; ++part)
                 for (int j = 0; j < 128; ++j) {
@@ -195,10 +198,11 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
                     float* row = &g1[static_cast<size_t>(dst) * K1];
                     for (int tap = 0; tap < 3; ++tap)
                         for (int ci = 0; ci < C; ++ci) row[tap * C + ci] = wdil[(static_cast<size_t>(src) * C + ci) * 3 + tap];
-                    for (int ci = 0; ci < H; ++ci) row[3 * C + ci] = wc[static_cast<size_t>(src) * H + ci];
+                    for (int ci = 0; ci < H; ++ci) gc[static_cast<size_t>(dst) * H + ci] = wc[static_cast<size_t>(src) * H + ci];
                     gb[dst] = bdil[src] + bc[src];
                 }
         layers[l].g1.pack(g1, 2 * C, K1);
+        layers[l].gc.pack(gc, 2 * C, H);
         upload(layers[l].g1_bias, gb);
         layers[l].g2.pack(wo, 2 * C, C);
         upload(layers[l].g2_bias, bo);
@@ -243,7 +247,7 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
 
     // set the dynamic-smem attribute of every instantiation outside of any stream capture
     ConvGemmArgs none{};
-    for (int epi : {EPI_INPROJ, EPI_GATE, EPI_RES_SKIP, EPI_RELU_BF16}) launch_conv_gemm(256, terms, epi, none, nullptr);
+    for (int epi : {EPI_F32, EPI_INPROJ, EPI_GATE, EPI_RES_SKIP, EPI_RELU_BF16}) launch_conv_gemm(256, terms, epi, none, nullptr);
     launch_conv_gemm(80, terms, EPI_POSTERIOR, none, nullptr);
 }
 
@@ -273,6 +277,7 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
     w->h_hi.alloc(rows * C * 2);
     w->mel.alloc(rows * M * 4);
     w->mel2ph.alloc(rows * 8);
+    w->cp.alloc(static_cast<size_t>(cfg.residual_layers) * rows * 2 * C * 4);
     if (lo) {
         w->xin_lo.alloc(rows * M * 2);
         w->cond_lo.alloc(rows * H * 2);
@@ -299,19 +304,37 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
 static void set_w(ConvGemmArgs& a, PackedW& w, int n_tile) { w.maps(n_tile, a.wmap[0], a.wmap[1]); }
 
 
-// dilated conv(x + d) + conditioner projection -> sigmoid*tanh gate (net.py:67-74)
+// cp[l] = conditioner_projection_l(cond) + its bias + the dilated conv's bias (net.py:68,71), all layers, once per call
+void DiffusionPlan::precompute_cond(Workspace& w, cudaStream_t st) {
+    const int H = cfg.hidden_size, C = cfg.residual_channels, L = cfg.residual_layers;
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = layers[l];
+        ConvGemmArgs a{};
+        set_geometry(a, w.B, w.T, 2 * C, 256);
+        a.amap[0] = w.m_cond[0]; a.amap[1] = w.m_cond[1];
+        set_w(a, ly.gc, 256);
+        a.n_seg = 1;
+        a.seg[0] = Segment{0, 0, 0, H / kBlockK, 0};
+        a.epi.bias = ly.g1_bias.as<float>();
+        a.epi.f32_a = w.cp.as<float>() + static_cast<size_t>(l) * w.B * w.T * 2 * C;
+        a.epi.out_pitch = 2 * C;
+        launch_conv_gemm(256, terms, EPI_F32, a, st);
+        ++launches, ++g_launch_count;
+    }
+}
+
+// dilated conv(x + d) [+ precomputed conditioner projection] -> sigmoid*tanh gate (net.py:67-74)
 ConvGemmArgs DiffusionPlan::gate_args(Workspace& w, int l) {
     const int H = cfg.hidden_size, C = cfg.residual_channels;
     Layer& ly = layers[l];
     ConvGemmArgs a{};
     set_geometry(a, w.B, w.T, 2 * C, 256);
     a.amap[0] = w.m_xa[0]; a.amap[1] = w.m_xa[1];
-    a.amap[2] = w.m_cond[0]; a.amap[3] = w.m_cond[1];
     set_w(a, ly.g1, 256);
-    a.n_seg = 4;
+    a.n_seg = 3;
     for (int tap = 0; tap < 3; ++tap) a.seg[tap] = Segment{0, (tap - 1) * ly.dilation, 0, C / kBlockK, tap * C};
-    a.seg[3] = Segment{1, 0, 0, H / kBlockK, 3 * C};
-    a.epi.bias = ly.g1_bias.as<float>();
+    a.epi.aux0 = w.cp.as<float>() + static_cast<size_t>(l) * w.B * w.T * 2 * C;   // + conditioner projection + biases
+    (void)H;
     a.epi.out_hi = w.z_hi.as<__nv_bfloat16>();
     a.epi.out_lo = terms == 3 ? w.z_lo.as<__nv_bfloat16>() : nullptr;
     a.epi.out_pitch = C;
@@ -464,6 +487,7 @@ void DiffusionPlan::sample(const float* cond, const float* fs2_mel, const float*
         split_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256 + 1), 256, 0, st>>>(cond, w.cond_hi.as<__nv_bfloat16>(),
                                                                                     lo ? w.cond_lo.as<__nv_bfloat16>() : nullptr, n);
         ++launches, ++g_launch_count;
+        precompute_cond(w, st);
         const int mode = fs2_mel ? 0 : 1;
         init_x_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(
             mode, fs2_mel, start_noise, d_spec_min.as<float>(), d_spec_max.as<float>(), sched[K - 1].sqrt_ac, sched[K - 1].sqrt_1mac,
@@ -531,6 +555,7 @@ void DiffusionPlan::denoise(const float* spec, int t, const float* cond, int B, 
                                                                              lo ? w.xin_lo.as<__nv_bfloat16>() : nullptr);
     launches += 2, g_launch_count += 2;
     B200_CUDA(cudaGetLastError());
+    precompute_cond(w, st);
     enqueue_step(w, t, 0, nullptr, false, false, 1, st);
     B200_CUDA(cudaMemcpyAsync(eps_out, w.eps.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
 }

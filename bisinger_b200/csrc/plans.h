@@ -32,7 +32,7 @@ public:
 private:
     struct Workspace;
     struct Layer {
-        PackedW g1, g2;
+        PackedW g1, g2, gc;   // dilated conv taps, output projection, conditioner projection
         DevBuf g1_bias, g2_bias;
         int dilation = 1;
     };
@@ -40,6 +40,7 @@ private:
         float sqrt_ac, sqrt_1mac, c0, c1, c2, c3, sigma;
     };
     Workspace& workspace(int B, int T);
+    void precompute_cond(Workspace& w, cudaStream_t st);
     ConvGemmArgs gate_args(Workspace& w, int l);
     ConvGemmArgs resskip_args(Workspace& w, int l, const float* lut_t);
     void enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail, cudaStream_t st);
