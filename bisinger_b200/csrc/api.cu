@@ -103,7 +103,7 @@ int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias
     using namespace b200;
     return guarded([&] {
         B200_CHECK(a_dev && w_host && bias_host && shifts && out_dev, "null argument");
-        B200_CHECK(Cin % 8 == 0 && N % n_tile == 0 && ntaps >= 1 && ntaps <= kMaxSeg, "bad shape");
+        B200_CHECK(Cin % 8 == 0 && N % n_tile == 0 && ntaps >= 1 && ntaps <= kMaxTaps, "bad shape");
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         const int terms = precision == BSG_PRECISION_BF16X3 ? 3 : 1;
         const size_t rows = static_cast<size_t>(B) * L;
@@ -132,11 +132,10 @@ int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias
         pw.pack(wp, N, ntaps * Cpad);
         ConvGemmArgs a{};
         set_geometry(a, B, L, N, n_tile);
-        a.amap[0] = make_act_tmap(d_ah.p, B, L, Cin);
-        a.amap[1] = make_act_tmap(d_al.p, B, L, Cin);
+        const int rows_box = set_taps(a, 0, 0, n_kb, shifts, ntaps, Cpad);
+        a.amap[0] = make_act_tmap(d_ah.p, B, L, Cin, 0, rows_box);
+        a.amap[1] = make_act_tmap(d_al.p, B, L, Cin, 0, rows_box);
         pw.maps(n_tile, a.wmap[0], a.wmap[1]);
-        a.n_seg = ntaps;
-        for (int tp = 0; tp < ntaps; ++tp) a.seg[tp] = Segment{0, shifts[tp], 0, n_kb, tp * Cpad};
         a.epi.bias = d_bias.as<float>();
         a.epi.f32_a = out_dev;
         a.epi.out_pitch = N;

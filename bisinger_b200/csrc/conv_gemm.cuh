@@ -2,10 +2,14 @@
 //
 // One kernel template serves every 1-D convolution on the hot path.  Activations are stored
 // channels-last ([B][L][C] bf16), so a convolution tap is a *row shift* of the A operand:
-//     Y[b, t, n] = sum_seg sum_c  A_seg[b, t + shift_seg, c] * W[n, wcol_seg + c]
-// A tiles (128 rows x 64 channels) are fetched by 3-D TMA with the shifted row coordinate; rows that
-// fall outside [0, L) are zero-filled by the TMA unit, which is exactly the reference's zero padding
-// (nn.Conv1d padding=dilation, usr/diff/net.py:61; get_padding, modules/hifigan/hifigan.py:26-27).
+//     Y[b, t, n] = sum_tap sum_c  A[b, t + shift_tap, c] * W[n, wcol_tap + c]
+// For every 64-channel k-block ONE halo tile of A (rows t0+min_shift .. t0+127+max_shift, <= 192 rows) is fetched
+// by 3-D TMA; rows that fall outside [0, L) are zero-filled by the TMA unit, which is exactly the reference's zero
+// padding (nn.Conv1d padding=dilation, usr/diff/net.py:61; get_padding, modules/hifigan/hifigan.py:26-27).  The taps
+// then read that tile through UMMA descriptors whose start address is advanced by shift*128 B: the SWIZZLE_128B
+// pattern is a function of the absolute shared-memory address, so a descriptor may start on any row of a swizzle
+// atom (verified on B200 with csrc/experiments.cu, profiles/r01_c).  A k=11 convolution therefore moves its
+// activations from L2 to shared memory once instead of eleven times.
 // Weights are packed K-major ([N][Ktot] bf16) and fetched by 2-D TMA.  tcgen05.mma (M=128, N=N_TILE,
 // K=16) accumulates in TMEM (fp32); two accumulator buffers let the epilogue of tile i overlap the
 // MMAs of tile i+1.
@@ -29,16 +33,20 @@ namespace b200 {
 
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kMaxSeg = 12;
+constexpr int kMaxTaps = 11;
 constexpr int kGemmThreads = 32 * (2 + 8);   // producer, MMA, 8 epilogue warps
-constexpr int kSmemBudget = 196 * 1024;
+constexpr int kSmemBudget = 200 * 1024;
 
-struct Segment {
-    int a_src;      // index of the A tensor-map pair (hi = 2*a_src, lo = 2*a_src + 1)
-    int row_shift;  // tap offset in rows (may be negative)
-    int a_col0;     // first channel of A used by this segment
-    int n_kb;       // number of 64-channel k-blocks
-    int w_col0;     // first K column of the packed weight matrix
+// The taps of one convolution: all read the same A source / channel range, each with its own row shift and its own
+// K-column block of the packed weight matrix.
+struct TapSet {
+    int a_src;               // index of the A tensor-map pair (hi = 2*a_src, lo = 2*a_src + 1)
+    int a_col0;              // first channel of A
+    int n_kb;                // number of 64-channel k-blocks
+    int row_shift;           // row shift of the halo tile's first row (= smallest tap shift, may be negative)
+    int n_taps;
+    int row_off[kMaxTaps];   // tap shift - row_shift  (>= 0): row of the halo tile where the tap's 128 rows start
+    int w_col0[kMaxTaps];    // first K column of the tap in the packed weight matrix
 };
 
 // Epilogue selector
@@ -75,15 +83,15 @@ struct EpiParams {
 };
 
 struct ConvGemmArgs {
-    CUtensorMap amap[6];   // A sources: (hi, lo) pairs
+    CUtensorMap amap[4];   // A sources: (hi, lo) pairs, box = 64 channels x a_rows rows
     CUtensorMap wmap[2];   // packed weights hi / lo
     int B, L;              // batches, rows per batch
     int tiles_per_batch;   // ceil(L / 128)
     int n_tiles_n;         // N tiles per row tile
     int num_tiles;
     int w_row0;            // first weight row of this launch
-    int n_seg;
-    Segment seg[kMaxSeg];
+    int a_rows;            // rows of the A halo box (multiple of 8, 128 + max_shift - min_shift rounded up)
+    TapSet taps;
     EpiParams epi;
 };
 
@@ -553,16 +561,22 @@ __device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int 
 // ---------------------------------------------------------------------------------------------
 template <int N_TILE, int TERMS>
 struct GemmSmem {
-    static constexpr int kABytes = kTileM * kBlockK * 2;
-    static constexpr int kBBytes = N_TILE * kBlockK * 2;
-    static constexpr int kStageBytes = (TERMS == 3 ? 2 : 1) * (kABytes + kBBytes);
-    static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
-    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kASlotRows = TERMS == 3 ? 144 : 192;                       // halo tile capacity
+    static constexpr int kAPartBytes = kASlotRows * kBlockK * 2;                    // one of hi / lo
+    static constexpr int kBPartBytes = N_TILE * kBlockK * 2;
+    static constexpr int kASlotBytes = (TERMS == 3 ? 2 : 1) * kAPartBytes;
+    static constexpr int kBSlotBytes = (TERMS == 3 ? 2 : 1) * kBPartBytes;
+    static constexpr int kAStages = TERMS == 3 ? 2 : 3;
+    static constexpr int kBStagesRaw = (kSmemBudget - kAStages * kASlotBytes) / kBSlotBytes;
+    static constexpr int kBStages = kBStagesRaw > 6 ? 6 : kBStagesRaw;
+    static constexpr int kOperandBytes = kAStages * kASlotBytes + kBStages * kBSlotBytes;
     static constexpr int kBarBytes = 256;
     static constexpr int kXposeBytes = kEpiWarps * kStageFloatsPerWarp * 4;   // one 16x36 fp32 transpose tile per epilogue warp
-    static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kXposeBytes + 1024;  // +1024 for manual alignment
-    static_assert(kStages >= 2, "need at least a double-buffered pipeline");
-    static_assert(kBBytes % 1024 == 0, "B tile must keep 1024-byte swizzle alignment");
+    static constexpr int kTotal = kOperandBytes + kBarBytes + kXposeBytes + 1024;  // +1024 for manual alignment
+    static_assert(kBStages >= 2, "need at least a double-buffered weight ring");
+    static_assert(kAPartBytes % 1024 == 0 && kBPartBytes % 1024 == 0, "tiles must keep 1024-byte swizzle alignment");
+    static_assert((2 * kAStages + 2 * kBStages + 4) * 8 + 8 <= kBarBytes, "barrier area too small");
+    static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
 __host__ __device__ constexpr int tmem_cols_for(int n) {
@@ -578,19 +592,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
-    uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + S::kStages;
-    uint64_t* tfull_bar = bars + 2 * S::kStages;
-    uint64_t* tempty_bar = bars + 2 * S::kStages + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 4);
-    float* xpose = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + S::kBarBytes);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + S::kAStages * S::kASlotBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOperandBytes);
+    uint64_t* afull_bar = bars;
+    uint64_t* aempty_bar = afull_bar + S::kAStages;
+    uint64_t* bfull_bar = aempty_bar + S::kAStages;
+    uint64_t* bempty_bar = bfull_bar + S::kBStages;
+    uint64_t* tfull_bar = bempty_bar + S::kBStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* xpose = reinterpret_cast<float*>(smem + S::kOperandBytes + S::kBarBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 32) {
-        for (int s = 0; s < S::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < S::kAStages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); }
+        for (int s = 0; s < S::kBStages; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
         fence_barrier_init();
     }
@@ -603,39 +622,44 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_seg = args.n_seg;
+    const TapSet& ts = args.taps;
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
-        int stage = 0;
-        uint32_t phase = 0;
+        const uint32_t a_bytes = static_cast<uint32_t>(args.a_rows) * kBlockK * 2 * (TERMS == 3 ? 2 : 1);
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
         for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
             const int n_tile = tile % args.n_tiles_n;
             const int m = tile / args.n_tiles_n;
             const int b = m / args.tiles_per_batch;
             const int t0 = (m % args.tiles_per_batch) * kTileM;
             const int wrow = args.w_row0 + n_tile * N_TILE;
-            for (int s = 0; s < n_seg; ++s) {
-                const Segment sg = args.seg[s];
-                for (int kb = 0; kb < sg.n_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* st = smem + stage * S::kStageBytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-                    tma_load_3d(st, &args.amap[2 * sg.a_src], &full_bar[stage], sg.a_col0 + kb * kBlockK, t0 + sg.row_shift, b);
-                    if (TERMS == 3)
-                        tma_load_3d(st + S::kABytes, &args.amap[2 * sg.a_src + 1], &full_bar[stage], sg.a_col0 + kb * kBlockK,
-                                    t0 + sg.row_shift, b);
-                    uint8_t* sb = st + (TERMS == 3 ? 2 : 1) * S::kABytes;
-                    tma_load_2d(sb, &args.wmap[0], &full_bar[stage], sg.w_col0 + kb * kBlockK, wrow);
-                    if (TERMS == 3) tma_load_2d(sb + S::kBBytes, &args.wmap[1], &full_bar[stage], sg.w_col0 + kb * kBlockK, wrow);
-                    if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+            for (int kb = 0; kb < ts.n_kb; ++kb) {
+                // one halo tile of activations per 64-channel k-block ...
+                mbar_wait(&aempty_bar[as], aph ^ 1);
+                uint8_t* sa = smem_a + as * S::kASlotBytes;
+                mbar_arrive_expect_tx(&afull_bar[as], a_bytes);
+                tma_load_3d(sa, &args.amap[2 * ts.a_src], &afull_bar[as], ts.a_col0 + kb * kBlockK, t0 + ts.row_shift, b);
+                if (TERMS == 3)
+                    tma_load_3d(sa + S::kAPartBytes, &args.amap[2 * ts.a_src + 1], &afull_bar[as], ts.a_col0 + kb * kBlockK,
+                                t0 + ts.row_shift, b);
+                if (++as == S::kAStages) { as = 0; aph ^= 1; }
+                // ... and one weight tile per tap
+                for (int tp = 0; tp < ts.n_taps; ++tp) {
+                    mbar_wait(&bempty_bar[bs], bph ^ 1);
+                    uint8_t* sb = smem_b + bs * S::kBSlotBytes;
+                    mbar_arrive_expect_tx(&bfull_bar[bs], S::kBSlotBytes);
+                    tma_load_2d(sb, &args.wmap[0], &bfull_bar[bs], ts.w_col0[tp] + kb * kBlockK, wrow);
+                    if (TERMS == 3) tma_load_2d(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], ts.w_col0[tp] + kb * kBlockK, wrow);
+                    if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
                 }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer (single thread) =================
-        int stage = 0;
-        uint32_t phase = 0;
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -643,15 +667,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             tc_fence_after();
             const uint32_t tacc = tmem_base + acc * N_TILE;
             uint32_t accumulate = 0;
-            for (int s = 0; s < n_seg; ++s) {
-                const int n_kb = args.seg[s].n_kb;
-                for (int kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+            for (int kb = 0; kb < ts.n_kb; ++kb) {
+                mbar_wait(&afull_bar[as], aph);
+                tc_fence_after();
+                const uint32_t a_slot = smem_u32(smem_a + as * S::kASlotBytes);
+                for (int tp = 0; tp < ts.n_taps; ++tp) {
+                    mbar_wait(&bfull_bar[bs], bph);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + stage * S::kStageBytes);
-                    const uint32_t a_lo = a_hi + S::kABytes;
-                    const uint32_t b_hi = a_hi + (TERMS == 3 ? 2 : 1) * S::kABytes;
-                    const uint32_t b_lo = b_hi + S::kBBytes;
+                    const uint32_t a_hi = a_slot + ts.row_off[tp] * (kBlockK * 2);   // tap = row offset into the halo tile
+                    const uint32_t a_lo = a_hi + S::kAPartBytes;
+                    const uint32_t b_hi = smem_u32(smem_b + bs * S::kBSlotBytes);
+                    const uint32_t b_lo = b_hi + S::kBPartBytes;
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         const uint64_t da = umma_smem_desc<128>(a_hi + k * 32);
@@ -663,11 +689,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                             umma_f16(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
                         }
                     }
-                    umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-                    if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+                    umma_commit(&bempty_bar[bs]);   // frees the weight slot when these MMAs retire
+                    if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
                 }
+                umma_commit(&aempty_bar[as]);       // frees the halo tile after its last tap
+                if (++as == S::kAStages) { as = 0; aph ^= 1; }
             }
-            umma_commit(&tfull_bar[acc]);             // accumulator complete -> epilogue
+            umma_commit(&tfull_bar[acc]);           // accumulator complete -> epilogue
         }
     } else if (warp >= 2 && warp < 2 + kEpiWarps) {
         // ================= Epilogue warps =================

@@ -126,6 +126,8 @@ __global__ void init_x_kernel(int mode, const float* __restrict__ fs2_mel, const
 // ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
+static const int kOneTap[1] = {0};
+static constexpr int kXaBoxRows = 144;   // 128 + 2 * max dilation (8)
 struct DiffusionPlan::Workspace {
     int B = 0, T = 0;
     DevBuf cp;   // f32 [L][rows][2C]: conditioner projection + biases of every layer (step-invariant)
@@ -156,6 +158,7 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     B200_CHECK(C == 256 && H == 256, "this build is specialised for residual_channels == hidden_size == 256");
     B200_CHECK(M == 80, "this build is specialised for 80 mel bins");
     B200_CHECK(L >= 1 && c.k_step >= 1 && c.k_step <= c.timesteps, "bad layer/step counts");
+    B200_CHECK(c.dilation_cycle >= 1 && (1 << (c.dilation_cycle - 1)) * 2 + kTileM <= kXaBoxRows, "dilation cycle too long for the halo tile");
     B200_CHECK(c.precision == BSG_PRECISION_BF16 || c.precision == BSG_PRECISION_BF16X3, "bad precision");
     terms = c.precision == BSG_PRECISION_BF16X3 ? 3 : 1;
     const size_t expect = static_cast<size_t>(C) * M + C + 4 * C * C + 4 * C + 4 * C * C + C +
@@ -286,13 +289,13 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
         w->s_lo.alloc(rows * C * 2);
         w->h_lo.alloc(rows * C * 2);
     }
-    auto mk = [&](CUtensorMap (&m)[2], const DevBuf& hi, const DevBuf& lo_, int ch) {
-        m[0] = make_act_tmap(hi.p, B, T, ch);
-        m[1] = lo ? make_act_tmap(lo_.p, B, T, ch) : m[0];
+    auto mk = [&](CUtensorMap (&m)[2], const DevBuf& hi, const DevBuf& lo_, int ch, int box_rows = kTileM) {
+        m[0] = make_act_tmap(hi.p, B, T, ch, 0, box_rows);
+        m[1] = lo ? make_act_tmap(lo_.p, B, T, ch, 0, box_rows) : m[0];
     };
     mk(w->m_xin, w->xin_hi, w->xin_lo, M);
     mk(w->m_cond, w->cond_hi, w->cond_lo, H);
-    mk(w->m_xa, w->xa_hi, w->xa_lo, C);
+    mk(w->m_xa, w->xa_hi, w->xa_lo, C, kXaBoxRows);   // halo tile of the dilated conv (3 taps, dilation <= 8)
     mk(w->m_z, w->z_hi, w->z_lo, C);
     mk(w->m_s, w->s_hi, w->s_lo, C);
     mk(w->m_h, w->h_hi, w->h_lo, C);
@@ -313,8 +316,7 @@ void DiffusionPlan::precompute_cond(Workspace& w, cudaStream_t st) {
         set_geometry(a, w.B, w.T, 2 * C, 256);
         a.amap[0] = w.m_cond[0]; a.amap[1] = w.m_cond[1];
         set_w(a, ly.gc, 256);
-        a.n_seg = 1;
-        a.seg[0] = Segment{0, 0, 0, H / kBlockK, 0};
+        set_taps(a, 0, 0, H / kBlockK, kOneTap, 1, 0);
         a.epi.bias = ly.g1_bias.as<float>();
         a.epi.f32_a = w.cp.as<float>() + static_cast<size_t>(l) * w.B * w.T * 2 * C;
         a.epi.out_pitch = 2 * C;
@@ -331,8 +333,9 @@ ConvGemmArgs DiffusionPlan::gate_args(Workspace& w, int l) {
     set_geometry(a, w.B, w.T, 2 * C, 256);
     a.amap[0] = w.m_xa[0]; a.amap[1] = w.m_xa[1];
     set_w(a, ly.g1, 256);
-    a.n_seg = 3;
-    for (int tap = 0; tap < 3; ++tap) a.seg[tap] = Segment{0, (tap - 1) * ly.dilation, 0, C / kBlockK, tap * C};
+    const int shifts[3] = {-ly.dilation, 0, ly.dilation};
+    set_taps(a, 0, 0, C / kBlockK, shifts, 3, C);
+    a.a_rows = kXaBoxRows;   // the xa tensor maps are encoded once with the box of the largest dilation
     a.epi.aux0 = w.cp.as<float>() + static_cast<size_t>(l) * w.B * w.T * 2 * C;   // + conditioner projection + biases
     (void)H;
     a.epi.out_hi = w.z_hi.as<__nv_bfloat16>();
@@ -350,8 +353,7 @@ ConvGemmArgs DiffusionPlan::resskip_args(Workspace& w, int l, const float* lut_t
     set_geometry(a, w.B, w.T, 2 * C, 256);
     a.amap[0] = w.m_z[0]; a.amap[1] = w.m_z[1];
     set_w(a, ly.g2, 256);
-    a.n_seg = 1;
-    a.seg[0] = Segment{0, 0, 0, C / kBlockK, 0};
+    set_taps(a, 0, 0, C / kBlockK, kOneTap, 1, 0);
     a.epi.bias = ly.g2_bias.as<float>();
     a.epi.f32_a = w.xres.as<float>();
     a.epi.f32_b = w.skip.as<float>();
@@ -410,8 +412,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         set_geometry(a, B, T, C, 256);
         a.amap[0] = w.m_xin[0]; a.amap[1] = w.m_xin[1];
         set_w(a, inproj, 256);
-        a.n_seg = 1;
-        a.seg[0] = Segment{0, 0, 0, (M + kBlockK - 1) / kBlockK, 0};
+        set_taps(a, 0, 0, (M + kBlockK - 1) / kBlockK, kOneTap, 1, 0);
         a.epi.bias = inproj_bias.as<float>();
         a.epi.f32_a = w.xres.as<float>();
         a.epi.out_hi = w.xa_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.xa_lo);
@@ -431,8 +432,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         set_geometry(a, B, T, C, 256);
         a.amap[0] = w.m_s[0]; a.amap[1] = w.m_s[1];
         set_w(a, skipproj, 256);
-        a.n_seg = 1;
-        a.seg[0] = Segment{0, 0, 0, C / kBlockK, 0};
+        set_taps(a, 0, 0, C / kBlockK, kOneTap, 1, 0);
         a.epi.bias = skipproj_bias.as<float>();
         a.epi.out_hi = w.h_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.h_lo);
         a.epi.out_pitch = C;
@@ -444,8 +444,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         set_geometry(a, B, T, M, 80);
         a.amap[0] = w.m_h[0]; a.amap[1] = w.m_h[1];
         set_w(a, outproj, 80);
-        a.n_seg = 1;
-        a.seg[0] = Segment{0, 0, 0, C / kBlockK, 0};
+        set_taps(a, 0, 0, C / kBlockK, kOneTap, 1, 0);
         a.epi.bias = outproj_bias.as<float>();
         if (tail == 1) {
             a.epi.f32_a = w.eps.as<float>();

@@ -54,6 +54,7 @@ void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
     static int sms = 0;
     if (sms == 0) sms = device_sm_count();
     if (args.num_tiles <= 0) return;
+    B200_CHECK(args.a_rows >= kTileM && args.a_rows <= S::kASlotRows && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
     const int grid = args.num_tiles < sms ? args.num_tiles : sms;
     kern<<<grid, kGemmThreads, S::kTotal, stream>>>(args);
     B200_CUDA(cudaGetLastError());

@@ -238,7 +238,7 @@ HifiganPlan::HifiganPlan(const bsg_hifigan_config& c, const float* w, size_t n_w
                 const int kk = d * s.rate + ph + pad;
                 if (kk >= 0 && kk < s.ksize) deltas.push_back(d);
             }
-            B200_CHECK(!deltas.empty() && static_cast<int>(deltas.size()) <= kMaxSeg, "unsupported transposed-conv geometry");
+            B200_CHECK(!deltas.empty() && static_cast<int>(deltas.size()) <= kMaxTaps, "unsupported transposed-conv geometry");
             const int nt = static_cast<int>(deltas.size());
             std::vector<float> wk(static_cast<size_t>(s.cout) * s.cin * nt);   // as a [Cout][Cin][nt] conv
             for (int o = 0; o < s.cout; ++o)
@@ -270,7 +270,7 @@ HifiganPlan::HifiganPlan(const bsg_hifigan_config& c, const float* w, size_t n_w
         s.convs2.resize(c.num_kernels * c.num_dilations);
         for (int j = 0; j < c.num_kernels; ++j) {
             const int k = c.resblock_kernel_sizes[j];
-            B200_CHECK(k % 2 == 1 && k <= kMaxSeg, "resblock kernel size must be odd and <= 11");
+            B200_CHECK(k % 2 == 1 && k <= kMaxTaps, "resblock kernel size must be odd and <= 11");
             for (int m = 0; m < c.num_dilations; ++m) {
                 need(static_cast<size_t>(C) * C * k + C);
                 auto wt = take(p, static_cast<size_t>(C) * C * k);
@@ -380,12 +380,11 @@ void HifiganPlan::forward(const float* mel, const float* f0, const float* rand_i
         ConvGemmArgs a{};
         const int nt = ntile_for(cv.cout);
         set_geometry(a, B, Lrows, cv.cout, nt);
-        a.amap[0] = make_act_tmap(a_ptr, B, Lrows, cv.cin, a_pitch);
+        const int cp = ((cv.cin + kBlockK - 1) / kBlockK) * kBlockK;
+        const int rows_box = set_taps(a, 0, 0, cp / kBlockK, shifts.data(), static_cast<int>(shifts.size()), cp);
+        a.amap[0] = make_act_tmap(a_ptr, B, Lrows, cv.cin, a_pitch, rows_box);
         a.amap[1] = a.amap[0];
         cv.w.maps(nt, a.wmap[0], a.wmap[1]);
-        const int cp = ((cv.cin + kBlockK - 1) / kBlockK) * kBlockK;
-        a.n_seg = static_cast<int>(shifts.size());
-        for (int j = 0; j < a.n_seg; ++j) a.seg[j] = Segment{0, shifts[j], 0, cp / kBlockK, j * cp};
         a.epi = epi;
         a.epi.bias = cv.bias.as<float>();
         launch_conv_gemm(nt, 1, EPI_BIAS_ACT, a, st);

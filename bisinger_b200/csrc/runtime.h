@@ -92,12 +92,12 @@ EncodeTiledFn get_encode_tiled();
 // bf16 tensor, dims given innermost-first; strides (bytes) for dims 1..rank-1; SWIZZLE_128B, zero OOB fill.
 CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
-// activations [B][L][C] (channels-last), box = 64 channels x 128 rows
-inline CUtensorMap make_act_tmap(const void* base, int B, int L, int C, int row_pitch_elems = 0) {
+// activations [B][L][C] (channels-last), box = 64 channels x box_rows rows (the halo tile of one k-block)
+inline CUtensorMap make_act_tmap(const void* base, int B, int L, int C, int row_pitch_elems = 0, int box_rows = kTileM) {
     if (row_pitch_elems == 0) row_pitch_elems = C;
     const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
     const uint64_t strides[2] = {static_cast<uint64_t>(row_pitch_elems) * 2, static_cast<uint64_t>(row_pitch_elems) * 2 * L};
-    const uint32_t box[3] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(kTileM), 1};
+    const uint32_t box[3] = {static_cast<uint32_t>(kBlockK), static_cast<uint32_t>(box_rows), 1};
     return make_tmap_bf16(base, 3, dims, strides, box);
 }
 // packed weights [N][K] (K-major), box = 64 x n_tile
@@ -123,6 +123,23 @@ inline void set_geometry(ConvGemmArgs& a, int B, int L, int n_total, int n_tile)
     a.num_tiles = B * a.tiles_per_batch * a.n_tiles_n;
     a.w_row0 = 0;
 }
+
+// Fills args.taps / args.a_rows for a convolution whose tap j reads rows shifted by shifts[j] and K columns
+// [j * w_tap_stride, ...) of the packed weights.  Returns the rows the A halo box must have.
+inline int set_taps(ConvGemmArgs& a, int a_src, int a_col0, int n_kb, const int* shifts, int n_taps, int w_tap_stride) {
+    B200_CHECK(n_taps >= 1 && n_taps <= kMaxTaps, "too many taps");
+    int lo = shifts[0], hi = shifts[0];
+    for (int j = 1; j < n_taps; ++j) { lo = shifts[j] < lo ? shifts[j] : lo; hi = shifts[j] > hi ? shifts[j] : hi; }
+    a.taps.a_src = a_src;
+    a.taps.a_col0 = a_col0;
+    a.taps.n_kb = n_kb;
+    a.taps.row_shift = lo;
+    a.taps.n_taps = n_taps;
+    for (int j = 0; j < n_taps; ++j) { a.taps.row_off[j] = shifts[j] - lo; a.taps.w_col0[j] = j * w_tap_stride; }
+    a.a_rows = ((kTileM + hi - lo) + 7) / 8 * 8;
+    return a.a_rows;
+}
+inline int halo_rows(int span) { return ((kTileM + span) + 7) / 8 * 8; }
 
 // Packed bf16 (hi, lo) weight matrix on the device
 struct PackedW {
