@@ -180,19 +180,28 @@ struct LanePos {
 };
 __device__ __forceinline__ LanePos lane_pos(int lane) { return LanePos{lane >> 4, (lane & 15) * 2}; }
 
+__device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float2 lds64(uint32_t saddr) {
+    float2 r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(saddr) : "memory");
+    return r;
+}
 __device__ __forceinline__ void chunk_transpose(float* stage, int lane, const float (&v)[32], float2 (&o)[16]) {
     const LanePos lp = lane_pos(lane);
+    const uint32_t sbase = smem_u32(stage);   // explicit shared-space accesses (generic LD/ST showed up as stall_lg)
+    const uint32_t wr = sbase + (lane & 15) * (kStagePitch * 4);
+    const uint32_t rd = sbase + (lp.r0 * kStagePitch + lp.cc) * 4;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         if (lp.r0 == half) {
-            float4* w = reinterpret_cast<float4*>(stage + (lane & 15) * kStagePitch);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) sts128(wr + j * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         __syncwarp();
 #pragma unroll
-        for (int rp = 0; rp < 8; ++rp)
-            o[half * 8 + rp] = *reinterpret_cast<const float2*>(stage + (2 * rp + lp.r0) * kStagePitch + lp.cc);
+        for (int rp = 0; rp < 8; ++rp) o[half * 8 + rp] = lds64(rd + rp * (2 * kStagePitch * 4));
         __syncwarp();
     }
 }
@@ -314,14 +323,26 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
         const long long st = 2LL * e.out_pitch;
         if (n_tile == 0) {
             // x <- (x + residual) / sqrt(2)  (net.py:78) ; next layer's conv input = x + d_{l+1}  (net.py:69)
+            // software pipeline: the residual rows of chunk c+1 are in flight while chunk c is processed
+            float2 xn[16];
+            {
+                const long long off0 = (row_w + lp.r0) * e.out_pitch + c_begin + lp.cc;
+#pragma unroll
+                for (int rp = 0; rp < 16; ++rp)
+                    if (B200_ROW_OK(rp)) xn[rp] = ld2(e.f32_a + off0 + rp * st);
+            }
 #pragma unroll 1
             for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
                 const int cl = c + lp.cc;
                 const long long off0 = (row_w + lp.r0) * e.out_pitch + cl;
                 float2 x[16];
 #pragma unroll
-                for (int rp = 0; rp < 16; ++rp)
-                    if (B200_ROW_OK(rp)) x[rp] = ld2(e.f32_a + off0 + rp * st);
+                for (int rp = 0; rp < 16; ++rp) x[rp] = xn[rp];
+                if (c + 32 < c_begin + kColsPerGrp) {
+#pragma unroll
+                    for (int rp = 0; rp < 16; ++rp)
+                        if (B200_ROW_OK(rp)) xn[rp] = ld2(e.f32_a + off0 + 32 + rp * st);
+                }
                 float2 o[16];
                 ld_chunk_t(tacc, c, stage, lane, o);
                 const float2 bias = ldg2(e.bias + cl);
@@ -340,15 +361,27 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
             }
         } else {
             // skip accumulation (net.py:78,126); the last layer hands sum/sqrt(L) to the head GEMM as bf16 operand
+            const bool first = (e.flags & 1) != 0;
+            float2 sn[16];
+#pragma unroll
+            for (int rp = 0; rp < 16; ++rp) sn[rp] = make_float2(0.f, 0.f);
+            if (!first) {
+                const long long off0 = (row_w + lp.r0) * e.out_pitch + c_begin + lp.cc;
+#pragma unroll
+                for (int rp = 0; rp < 16; ++rp)
+                    if (B200_ROW_OK(rp)) sn[rp] = ld2(e.f32_b + off0 + rp * st);
+            }
 #pragma unroll 1
             for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
                 const int cl = c + lp.cc;
                 const long long off0 = (row_w + lp.r0) * e.out_pitch + cl;
                 float2 sk[16];
 #pragma unroll
-                for (int rp = 0; rp < 16; ++rp) {
-                    sk[rp] = make_float2(0.f, 0.f);
-                    if (!(e.flags & 1) && B200_ROW_OK(rp)) sk[rp] = ld2(e.f32_b + off0 + rp * st);
+                for (int rp = 0; rp < 16; ++rp) sk[rp] = sn[rp];
+                if (!first && c + 32 < c_begin + kColsPerGrp) {
+#pragma unroll
+                    for (int rp = 0; rp < 16; ++rp)
+                        if (B200_ROW_OK(rp)) sn[rp] = ld2(e.f32_b + off0 + 32 + rp * st);
                 }
                 float2 o[16];
                 ld_chunk_t(tacc, c, stage, lane, o);
