@@ -54,8 +54,8 @@ enum : int {
     EPI_F32 = 0,        // out_f32[row][n] = acc + bias[n]                       (unit tests)
     EPI_INPROJ = 1,     // relu(acc+bias) -> xres f32 ; (+dvec) -> xa hi/lo      (net.py:116-118)
     EPI_GATE = 2,       // sigmoid(g+bg) * tanh(f+bf) -> z hi/lo                 (net.py:71-74)
-    EPI_RES_SKIP = 3,   // n_tile 0: x=(x+r+b)/sqrt2 ; n_tile 1: skip += s+b     (net.py:76-78,126)
-    EPI_RELU_BF16 = 4,  // relu(acc+bias) -> hi/lo                               (net.py:127-128)
+    EPI_RES_SKIP = 3,   // x=(x+r+b)/sqrt2 -> xres f32, split(x + d_next) -> xa  (net.py:76-78; skip half: see EPI_RELU_BF16)
+    EPI_RELU_BF16 = 4,  // (acc+bias)*c0 [ReLU] -> hi/lo                         (net.py:126-128)
     EPI_POSTERIOR = 5,  // eps=acc+bias -> DDPM posterior update of x_t          (shallow_diffusion_tts.py:149-166)
     EPI_BIAS_ACT = 6,   // HiFi-GAN: y = acc+bias (+res) ; writes f32 and/or lrelu(y) bf16
 };
@@ -294,8 +294,9 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
         for (int c = grp * (HALF / 2); c < (grp + 1) * (HALF / 2); c += 32) {
             const int nb = n_tile * N_TILE + c + lp.cc;   // packed column of the gate pre-activation ; filter at +HALF
             const int ch = n_tile * HALF + c + lp.cc;     // output channel
-            // aux0 = precomputed conditioner projection + biases, f32 [rows][2*HALF*n_tiles] in the packed column order
-            const long long cp0 = (row_w + lp.r0) * (2LL * e.out_pitch) + nb, cst = 4LL * e.out_pitch;
+            // aux0 = precomputed conditioner projection + biases, f32 [rows][out_pitch] in the packed column order;
+            // z goes to out_hi/out_lo [rows][act_pitch] at column out_col0 + channel (the all-layer z matrix)
+            const long long cp0 = (row_w + lp.r0) * static_cast<long long>(e.out_pitch) + nb, cst = 2LL * e.out_pitch;
             float2 g[16], f[16], cp[16];
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp)
@@ -307,7 +308,7 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
             for (int rp = 0; rp < 16; ++rp)
                 if (B200_ROW_OK(rp)) cp[rp] = ld2(e.aux0 + cp0 + HALF + rp * cst);
             ld_chunk_t(tacc, HALF + c, stage, lane, f);
-            const long long off0 = (row_w + lp.r0) * e.out_pitch + ch, st = 2LL * e.out_pitch;
+            const long long off0 = (row_w + lp.r0) * static_cast<long long>(e.act_pitch) + e.out_col0 + ch, st = 2LL * e.act_pitch;
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp) {
                 if (B200_ROW_OK(rp)) {
@@ -318,86 +319,50 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
             }
         }
     } else if constexpr (EPI == EPI_RES_SKIP) {
-        static_assert(N_TILE == 256, "residual/skip split assumes 256 channels per tile");
+        // residual half of the output projection: x <- (x + r + b) / sqrt(2)  (net.py:76-78); also writes the next
+        // layer's conv input split(x + d_{l+1}) (net.py:69).  The skip half is not computed per layer: the skip sum is one
+        // K = L*C GEMM over all gated activations at the end of the step (DiffusionPlan::enqueue_step).
         const float rs2 = 0.70710678118654752440f;
         const long long st = 2LL * e.out_pitch;
-        if (n_tile == 0) {
-            // x <- (x + residual) / sqrt(2)  (net.py:78) ; next layer's conv input = x + d_{l+1}  (net.py:69)
-            // software pipeline: the residual rows of chunk c+1 are in flight while chunk c is processed
-            float2 xn[16];
-            {
-                const long long off0 = (row_w + lp.r0) * e.out_pitch + c_begin + lp.cc;
+        const int c0g = n_tile * N_TILE;
+        // software pipeline: the residual rows of chunk c+1 are in flight while chunk c is processed
+        float2 xn[16];
+        {
+            const long long off0 = (row_w + lp.r0) * e.out_pitch + c0g + c_begin + lp.cc;
+#pragma unroll
+            for (int rp = 0; rp < 16; ++rp)
+                if (B200_ROW_OK(rp)) xn[rp] = ld2(e.f32_a + off0 + rp * st);
+        }
+#pragma unroll 1
+        for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
+            const int cl = c0g + c + lp.cc;
+            const long long off0 = (row_w + lp.r0) * e.out_pitch + cl;
+            float2 x[16];
+#pragma unroll
+            for (int rp = 0; rp < 16; ++rp) x[rp] = xn[rp];
+            if (c + 32 < c_begin + kColsPerGrp) {
 #pragma unroll
                 for (int rp = 0; rp < 16; ++rp)
-                    if (B200_ROW_OK(rp)) xn[rp] = ld2(e.f32_a + off0 + rp * st);
+                    if (B200_ROW_OK(rp)) xn[rp] = ld2(e.f32_a + off0 + 32 + rp * st);
             }
-#pragma unroll 1
-            for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
-                const int cl = c + lp.cc;
-                const long long off0 = (row_w + lp.r0) * e.out_pitch + cl;
-                float2 x[16];
+            float2 o[16];
+            ld_chunk_t(tacc, c, stage, lane, o);
+            const float2 bias = ldg2(e.bias + cl);
+            float2 d = make_float2(0.f, 0.f);
+            if (e.dvec != nullptr) d = ldg2(e.dvec + cl);
 #pragma unroll
-                for (int rp = 0; rp < 16; ++rp) x[rp] = xn[rp];
-                if (c + 32 < c_begin + kColsPerGrp) {
-#pragma unroll
-                    for (int rp = 0; rp < 16; ++rp)
-                        if (B200_ROW_OK(rp)) xn[rp] = ld2(e.f32_a + off0 + 32 + rp * st);
-                }
-                float2 o[16];
-                ld_chunk_t(tacc, c, stage, lane, o);
-                const float2 bias = ldg2(e.bias + cl);
-                float2 d = make_float2(0.f, 0.f);
-                if (e.dvec != nullptr) d = ldg2(e.dvec + cl);
-#pragma unroll
-                for (int rp = 0; rp < 16; ++rp) {
-                    if (B200_ROW_OK(rp)) {
-                        const long long off = off0 + rp * st;
-                        const float2 y = make_float2((x[rp].x + o[rp].x + bias.x) * rs2, (x[rp].y + o[rp].y + bias.y) * rs2);
-                        st2(e.f32_a + off, y);
-                        if (e.dvec != nullptr)   // not needed after the last layer
-                            st_split2(make_float2(y.x + d.x, y.y + d.y), e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr);
-                    }
-                }
-            }
-        } else {
-            // skip accumulation (net.py:78,126); the last layer hands sum/sqrt(L) to the head GEMM as bf16 operand
-            const bool first = (e.flags & 1) != 0;
-            float2 sn[16];
-#pragma unroll
-            for (int rp = 0; rp < 16; ++rp) sn[rp] = make_float2(0.f, 0.f);
-            if (!first) {
-                const long long off0 = (row_w + lp.r0) * e.out_pitch + c_begin + lp.cc;
-#pragma unroll
-                for (int rp = 0; rp < 16; ++rp)
-                    if (B200_ROW_OK(rp)) sn[rp] = ld2(e.f32_b + off0 + rp * st);
-            }
-#pragma unroll 1
-            for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
-                const int cl = c + lp.cc;
-                const long long off0 = (row_w + lp.r0) * e.out_pitch + cl;
-                float2 sk[16];
-#pragma unroll
-                for (int rp = 0; rp < 16; ++rp) sk[rp] = sn[rp];
-                if (!first && c + 32 < c_begin + kColsPerGrp) {
-#pragma unroll
-                    for (int rp = 0; rp < 16; ++rp)
-                        if (B200_ROW_OK(rp)) sn[rp] = ld2(e.f32_b + off0 + 32 + rp * st);
-                }
-                float2 o[16];
-                ld_chunk_t(tacc, c, stage, lane, o);
-                const float2 bias = ldg2(e.bias + N_TILE + cl);
-#pragma unroll
-                for (int rp = 0; rp < 16; ++rp) {
-                    if (B200_ROW_OK(rp)) {
-                        const long long off = off0 + rp * st;
-                        const float2 y = make_float2(sk[rp].x + o[rp].x + bias.x, sk[rp].y + o[rp].y + bias.y);
-                        if (e.flags & 2) st_split2(make_float2(y.x * e.c0, y.y * e.c0), e.out2_hi + off, e.out2_lo ? e.out2_lo + off : nullptr);
-                        else st2(e.f32_b + off, y);
-                    }
+            for (int rp = 0; rp < 16; ++rp) {
+                if (B200_ROW_OK(rp)) {
+                    const long long off = off0 + rp * st;
+                    const float2 y = make_float2((x[rp].x + o[rp].x + bias.x) * rs2, (x[rp].y + o[rp].y + bias.y) * rs2);
+                    st2(e.f32_a + off, y);
+                    if (e.dvec != nullptr)   // not needed after the last layer
+                        st_split2(make_float2(y.x + d.x, y.y + d.y), e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr);
                 }
             }
         }
     } else if constexpr (EPI == EPI_RELU_BF16) {
+        // y = (acc + bias) * c0, ReLU unless flags & 1  -> bf16 hi/lo      (skip sum / sqrt(L): net.py:126 ; skip_projection + ReLU: :127-128)
 #pragma unroll 1
         for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
             float2 o[16];
@@ -405,11 +370,12 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
             const int n = n_tile * N_TILE + c + lp.cc;
             const float2 bias = ldg2(e.bias + n);
             const long long off0 = (row_w + lp.r0) * e.out_pitch + n, st = 2LL * e.out_pitch;
+            const float lo_clamp = (e.flags & 1) ? -3.0e38f : 0.0f;
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp)
                 if (B200_ROW_OK(rp))
-                    st_split2(make_float2(fmaxf(o[rp].x + bias.x, 0.0f), fmaxf(o[rp].y + bias.y, 0.0f)), e.out_hi + off0 + rp * st,
-                              e.out_lo ? e.out_lo + off0 + rp * st : nullptr);
+                    st_split2(make_float2(fmaxf((o[rp].x + bias.x) * e.c0, lo_clamp), fmaxf((o[rp].y + bias.y) * e.c0, lo_clamp)),
+                              e.out_hi + off0 + rp * st, e.out_lo ? e.out_lo + off0 + rp * st : nullptr);
         }
     } else if constexpr (EPI == EPI_POSTERIOR) {
         // row-per-thread ownership: row t_warp + lane (only warp group 0 gets here: kSplit == 1)
@@ -563,7 +529,8 @@ __device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int 
     const float* src1 = nullptr;
     int col = grp * kCols;
     if constexpr (EPI == EPI_RES_SKIP) {
-        src0 = n_tile == 0 ? e.f32_a : ((e.flags & 1) ? nullptr : e.f32_b);
+        src0 = e.f32_a;
+        col += n_tile * N_TILE;
     } else {
         col += e.out_col0 + n_tile * N_TILE;
         if (e.flags & BA_ADD_RES) src0 = e.aux0;
@@ -576,7 +543,7 @@ __device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int 
         constexpr int HALF = N_TILE / 2;
         for (int idx = lane; idx < rows * 4; idx += 32) {
             const int r = idx >> 2, q = idx & 3;
-            const long long off = (row0 + r) * (2LL * e.out_pitch) + n_tile * N_TILE + grp * (HALF / 2) + (q >> 1) * HALF + (q & 1) * 32;
+            const long long off = (row0 + r) * static_cast<long long>(e.out_pitch) + n_tile * N_TILE + grp * (HALF / 2) + (q >> 1) * HALF + (q & 1) * 32;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(e.aux0 + off));
         }
         return;

@@ -10,10 +10,11 @@
 //   cond    bf16 [rows][H]      hi/lo copy of decoder_inp (step-invariant)
 //   xres    f32  [rows][C]      residual stream x
 //   xa      bf16 [rows][C]      hi/lo of (x + d_l): the zero-padded input of layer l's dilated conv
-//   z       bf16 [rows][C]      hi/lo of the gated activation
-//   skip    f32  [rows][C]      running sum of skip connections
+//   z       bf16 [rows][L*C]    hi/lo of the gated activations of ALL layers of the current step (layer l = columns
+//                               [l*C, (l+1)*C)): A operand of layer l's output projection and, at the end of the step, of
+//                               ONE K = L*C GEMM that produces the skip sum (instead of an fp32 read-modify-write per layer)
 //   s, h    bf16 [rows][C]      head operands: sum(skip)/sqrt(L) and relu(skip_projection)
-// Per step: 1 + 2L + 2 launches of conv_gemm_kernel; all K steps are captured in one CUDA graph when the
+// Per step: 1 + 2L + 3 launches of conv_gemm_kernel; all K steps are captured in one CUDA graph when the
 // noise is generated on the device.
 #include <cmath>
 #include <map>
@@ -128,10 +129,11 @@ __global__ void init_x_kernel(int mode, const float* __restrict__ fs2_mel, const
 // ---------------------------------------------------------------------------------------------
 static const int kOneTap[1] = {0};
 static constexpr int kXaBoxRows = 144;   // 128 + 2 * max dilation (8)
+static constexpr int kResTile = 128;     // N tile of the residual / skip-sum GEMMs (N = 256): 2x the tiles -> better wave balance
 struct DiffusionPlan::Workspace {
     int B = 0, T = 0;
     DevBuf cp;   // f32 [L][rows][2C]: conditioner projection + biases of every layer (step-invariant)
-    DevBuf xt, xin_hi, xin_lo, cond_hi, cond_lo, xres, xa_hi, xa_lo, z_hi, z_lo, skip, s_hi, s_lo, h_hi, h_lo, mel, mel2ph, eps;
+    DevBuf xt, xin_hi, xin_lo, cond_hi, cond_lo, xres, xa_hi, xa_lo, z_hi, z_lo, s_hi, s_lo, h_hi, h_lo, mel, mel2ph, eps;
     CUtensorMap m_xin[2], m_cond[2], m_xa[2], m_z[2], m_s[2], m_h[2];
     cudaGraphExec_t graph = nullptr;
     bool graph_has_mask = false;
@@ -174,6 +176,7 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     auto w2 = take(p, 4 * C * C);
     auto b2 = take(p, C);
     std::vector<float> wd_all, bd_all;
+    std::vector<float> skip_w(static_cast<size_t>(C) * L * C), skip_b(C, 0.0f);   // skip halves of all layers, K-concatenated
     layers.resize(L);
     for (int l = 0; l < L; ++l) {
         auto wdil = take(p, static_cast<size_t>(2 * C) * C * 3);   // [2C][C][3]
@@ -207,8 +210,13 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
         layers[l].g1.pack(g1, 2 * C, K1);
         layers[l].gc.pack(gc, 2 * C, H);
         upload(layers[l].g1_bias, gb);
-        layers[l].g2.pack(wo, 2 * C, C);
-        upload(layers[l].g2_bias, bo);
+        // output projection: first half of the output channels = residual, second half = skip (net.py:77)
+        layers[l].g2.pack(std::vector<float>(wo.begin(), wo.begin() + static_cast<size_t>(C) * C), C, C);
+        upload(layers[l].g2_bias, std::vector<float>(bo.begin(), bo.begin() + C));
+        for (int o = 0; o < C; ++o) {
+            for (int ci = 0; ci < C; ++ci) skip_w[static_cast<size_t>(o) * L * C + static_cast<size_t>(l) * C + ci] = wo[static_cast<size_t>(C + o) * C + ci];
+            skip_b[o] += bo[C + o];
+        }
         layers[l].dilation = 1 << (l % c.dilation_cycle);
     }
     auto w_skip = take(p, static_cast<size_t>(C) * C);
@@ -217,6 +225,8 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     auto b_out = take(p, M);
     inproj.pack(w_in, C, M);
     upload(inproj_bias, b_in);
+    skipall.pack(skip_w, C, L * C);
+    upload(skipall_bias, skip_b);
     skipproj.pack(w_skip, C, C);
     upload(skipproj_bias, b_skip);
     outproj.pack(w_out, M, C);
@@ -252,6 +262,8 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     ConvGemmArgs none{};
     for (int epi : {EPI_F32, EPI_INPROJ, EPI_GATE, EPI_RES_SKIP, EPI_RELU_BF16}) launch_conv_gemm(256, terms, epi, none, nullptr);
     launch_conv_gemm(80, terms, EPI_POSTERIOR, none, nullptr);
+    launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, none, nullptr);
+    launch_conv_gemm(kResTile, terms, EPI_RELU_BF16, none, nullptr);
 }
 
 DiffusionPlan::~DiffusionPlan() = default;
@@ -274,8 +286,7 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
     w->cond_hi.alloc(rows * H * 2);
     w->xres.alloc(rows * C * 4);
     w->xa_hi.alloc(rows * C * 2);
-    w->z_hi.alloc(rows * C * 2);
-    w->skip.alloc(rows * C * 4);
+    w->z_hi.alloc(rows * cfg.residual_layers * C * 2);
     w->s_hi.alloc(rows * C * 2);
     w->h_hi.alloc(rows * C * 2);
     w->mel.alloc(rows * M * 4);
@@ -285,7 +296,7 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
         w->xin_lo.alloc(rows * M * 2);
         w->cond_lo.alloc(rows * H * 2);
         w->xa_lo.alloc(rows * C * 2);
-        w->z_lo.alloc(rows * C * 2);
+        w->z_lo.alloc(rows * cfg.residual_layers * C * 2);
         w->s_lo.alloc(rows * C * 2);
         w->h_lo.alloc(rows * C * 2);
     }
@@ -296,7 +307,7 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
     mk(w->m_xin, w->xin_hi, w->xin_lo, M);
     mk(w->m_cond, w->cond_hi, w->cond_lo, H);
     mk(w->m_xa, w->xa_hi, w->xa_lo, C, kXaBoxRows);   // halo tile of the dilated conv (3 taps, dilation <= 8)
-    mk(w->m_z, w->z_hi, w->z_lo, C);
+    mk(w->m_z, w->z_hi, w->z_lo, cfg.residual_layers * C);
     mk(w->m_s, w->s_hi, w->s_lo, C);
     mk(w->m_h, w->h_hi, w->h_lo, C);
     auto& ref = *w;
@@ -340,29 +351,27 @@ ConvGemmArgs DiffusionPlan::gate_args(Workspace& w, int l) {
     (void)H;
     a.epi.out_hi = w.z_hi.as<__nv_bfloat16>();
     a.epi.out_lo = terms == 3 ? w.z_lo.as<__nv_bfloat16>() : nullptr;
-    a.epi.out_pitch = C;
+    a.epi.out_pitch = 2 * C;                         // pitch of the conditioner-projection rows (aux0)
+    a.epi.act_pitch = cfg.residual_layers * C;       // pitch of the all-layer z matrix
+    a.epi.out_col0 = l * C;
     return a;
 }
 
-// output projection -> residual / skip (net.py:76-78), skip sum (net.py:126)
+// residual half of the output projection (net.py:76-78): x <- (x + W_res z + b) / sqrt(2), xa <- split(x + d_{l+1})
 ConvGemmArgs DiffusionPlan::resskip_args(Workspace& w, int l, const float* lut_t) {
     const int C = cfg.residual_channels, L = cfg.residual_layers;
     Layer& ly = layers[l];
     const bool lo = terms == 3;
     ConvGemmArgs a{};
-    set_geometry(a, w.B, w.T, 2 * C, 256);
+    set_geometry(a, w.B, w.T, C, kResTile);
     a.amap[0] = w.m_z[0]; a.amap[1] = w.m_z[1];
-    set_w(a, ly.g2, 256);
-    set_taps(a, 0, 0, C / kBlockK, kOneTap, 1, 0);
+    set_w(a, ly.g2, kResTile);
+    set_taps(a, 0, l * C, C / kBlockK, kOneTap, 1, 0);
     a.epi.bias = ly.g2_bias.as<float>();
     a.epi.f32_a = w.xres.as<float>();
-    a.epi.f32_b = w.skip.as<float>();
     a.epi.out_hi = w.xa_hi.as<__nv_bfloat16>(); a.epi.out_lo = lo ? w.xa_lo.as<__nv_bfloat16>() : nullptr;
-    a.epi.out2_hi = w.s_hi.as<__nv_bfloat16>(); a.epi.out2_lo = lo ? w.s_lo.as<__nv_bfloat16>() : nullptr;
     a.epi.dvec = (l + 1 < L) ? lut_t + static_cast<size_t>(l + 1) * C : nullptr;
     a.epi.out_pitch = C;
-    a.epi.flags = (l == 0 ? 1 : 0) | (l == L - 1 ? 2 : 0);
-    a.epi.c0 = 1.0f / std::sqrt(static_cast<float>(L));
     return a;
 }
 
@@ -381,7 +390,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
         for (int i = 0; i < n; ++i) {
             const int l = i % L;
             if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st);
-            else launch_conv_gemm(256, terms, EPI_RES_SKIP, resskip_args(w, l == 0 ? 1 : l, lut.as<float>()), st);
+            else launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
             ++launches, ++g_launch_count;
         }
     };
@@ -424,7 +433,21 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
     for (int l = 0; l < L; ++l) {
         launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st);
         ++launches, ++g_launch_count;
-        launch_conv_gemm(256, terms, EPI_RES_SKIP, resskip_args(w, l, lut_t), st);
+        launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut_t), st);
+        ++launches, ++g_launch_count;
+    }
+    {   // skip sum: sum_l (W_skip,l z_l + b_skip,l) / sqrt(L)  (net.py:77-78,126) as one K = L*C GEMM over the step's z matrix
+        ConvGemmArgs a{};
+        set_geometry(a, B, T, C, kResTile);
+        a.amap[0] = w.m_z[0]; a.amap[1] = w.m_z[1];
+        set_w(a, skipall, kResTile);
+        set_taps(a, 0, 0, L * C / kBlockK, kOneTap, 1, 0);
+        a.epi.bias = skipall_bias.as<float>();
+        a.epi.out_hi = w.s_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.s_lo);
+        a.epi.out_pitch = C;
+        a.epi.flags = 1;                                        // no ReLU
+        a.epi.c0 = 1.0f / std::sqrt(static_cast<float>(L));
+        launch_conv_gemm(kResTile, terms, EPI_RELU_BF16, a, st);
         ++launches, ++g_launch_count;
     }
     {   // skip_projection + ReLU (net.py:127-128)
@@ -436,6 +459,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         a.epi.bias = skipproj_bias.as<float>();
         a.epi.out_hi = w.h_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.h_lo);
         a.epi.out_pitch = C;
+        a.epi.c0 = 1.0f;
         launch_conv_gemm(256, terms, EPI_RELU_BF16, a, st);
         ++launches, ++g_launch_count;
     }

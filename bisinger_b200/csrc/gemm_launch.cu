@@ -72,8 +72,8 @@ void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, 
     // DiffNet
     B200_CASE(256, 1, EPI_INPROJ) B200_CASE(256, 3, EPI_INPROJ)
     B200_CASE(256, 1, EPI_GATE) B200_CASE(256, 3, EPI_GATE)
-    B200_CASE(256, 1, EPI_RES_SKIP) B200_CASE(256, 3, EPI_RES_SKIP)
-    B200_CASE(256, 1, EPI_RELU_BF16) B200_CASE(256, 3, EPI_RELU_BF16)
+    B200_CASE(256, 1, EPI_RES_SKIP) B200_CASE(256, 3, EPI_RES_SKIP) B200_CASE(128, 1, EPI_RES_SKIP) B200_CASE(128, 3, EPI_RES_SKIP)
+    B200_CASE(256, 1, EPI_RELU_BF16) B200_CASE(256, 3, EPI_RELU_BF16) B200_CASE(128, 1, EPI_RELU_BF16) B200_CASE(128, 3, EPI_RELU_BF16)
     B200_CASE(80, 1, EPI_POSTERIOR) B200_CASE(80, 3, EPI_POSTERIOR)
     // HiFi-GAN
     B200_CASE(256, 1, EPI_BIAS_ACT) B200_CASE(128, 1, EPI_BIAS_ACT) B200_CASE(64, 1, EPI_BIAS_ACT) B200_CASE(32, 1, EPI_BIAS_ACT)

@@ -46,8 +46,8 @@ private:
     void enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail, cudaStream_t st);
 
     std::vector<Layer> layers;
-    PackedW inproj, skipproj, outproj;
-    DevBuf inproj_bias, skipproj_bias, outproj_bias;
+    PackedW inproj, skipproj, outproj, skipall;   // skipall: skip halves of all output projections, [C][L*C]
+    DevBuf inproj_bias, skipproj_bias, outproj_bias, skipall_bias;
     DevBuf lut, d_spec_min, d_spec_max, d_seed;
     std::vector<StepCoef> sched;
     std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
