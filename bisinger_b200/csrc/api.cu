@@ -105,7 +105,8 @@ int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias
         B200_CHECK(a_dev && w_host && bias_host && shifts && out_dev, "null argument");
         B200_CHECK(Cin % 8 == 0 && N % n_tile == 0 && ntaps >= 1 && ntaps <= kMaxTaps, "bad shape");
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        const int terms = precision == BSG_PRECISION_BF16X3 ? 3 : 1;
+        const bool pair = (precision & 0x100) != 0;   // test hook: run the 2-CTA (cta_group::2) variant of the kernel
+        const int terms = (precision & 0xff) == BSG_PRECISION_BF16X3 ? 3 : 1;
         const size_t rows = static_cast<size_t>(B) * L;
         // activations -> bf16 hi/lo (same split kernel the plans use is file-local; do it on the host here)
         std::vector<float> a_host(rows * Cin);
@@ -131,15 +132,15 @@ int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias
         PackedW pw;
         pw.pack(wp, N, ntaps * Cpad);
         ConvGemmArgs a{};
-        set_geometry(a, B, L, N, n_tile);
+        set_geometry(a, B, L, N, n_tile, pair);
         const int rows_box = set_taps(a, 0, 0, n_kb, shifts, ntaps, Cpad);
         a.amap[0] = make_act_tmap(d_ah.p, B, L, Cin, 0, rows_box);
         a.amap[1] = make_act_tmap(d_al.p, B, L, Cin, 0, rows_box);
-        pw.maps(n_tile, a.wmap[0], a.wmap[1]);
+        pw.maps(pair ? n_tile / 2 : n_tile, a.wmap[0], a.wmap[1]);
         a.epi.bias = d_bias.as<float>();
         a.epi.f32_a = out_dev;
         a.epi.out_pitch = N;
-        launch_conv_gemm(n_tile, terms, EPI_F32, a, st);
+        launch_conv_gemm(n_tile, terms, EPI_F32, a, st, pair);
         ++g_launch_count;
         B200_CUDA(cudaStreamSynchronize(st));
     });

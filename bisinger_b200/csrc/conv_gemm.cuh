@@ -515,12 +515,12 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
 
 // L2 prefetch of the fp32 tiles the epilogue of `tile` will read (this warp's 32 rows x its column group).
 template <int N_TILE, int EPI>
-__device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int tile, int quad, int grp, int lane) {
+__device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int tile, int tile_rows, int row_in_tile, int grp, int lane) {
     const EpiParams& e = args.epi;
     const int n_tile = tile % args.n_tiles_n;
     const int m = tile / args.n_tiles_n;
     const int b = m / args.tiles_per_batch;
-    const int t0 = (m % args.tiles_per_batch) * kTileM + quad * 32;
+    const int t0 = (m % args.tiles_per_batch) * tile_rows + row_in_tile;
     constexpr int kSplit = (N_TILE % 64 == 0) ? 2 : 1;
     if (kSplit == 1 && grp != 0) return;
     constexpr int kCols = N_TILE / kSplit;
@@ -559,11 +559,11 @@ __device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int 
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
-template <int N_TILE, int TERMS>
+template <int N_TILE, int TERMS, bool PAIR = false>
 struct GemmSmem {
     static constexpr int kASlotRows = TERMS == 3 ? 144 : 192;                       // halo tile capacity
     static constexpr int kAPartBytes = kASlotRows * kBlockK * 2;                    // one of hi / lo
-    static constexpr int kBPartBytes = N_TILE * kBlockK * 2;
+    static constexpr int kBPartBytes = (PAIR ? N_TILE / 2 : N_TILE) * kBlockK * 2;       // PAIR: each CTA stages half of the N columns
     static constexpr int kASlotBytes = (TERMS == 3 ? 2 : 1) * kAPartBytes;
     static constexpr int kBSlotBytes = (TERMS == 3 ? 2 : 1) * kBPartBytes;
     static constexpr int kAStages = TERMS == 3 ? 2 : 3;
@@ -583,12 +583,18 @@ __host__ __device__ constexpr int tmem_cols_for(int n) {
     return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512)));
 }
 
-template <int N_TILE, int TERMS, int EPI>
+// PAIR = true: the kernel is launched in clusters of two CTAs that cooperate on 256-row tiles with
+// tcgen05.mma.cta_group::2: CTA rank r stages rows [128r, 128r+128) of A and columns [r*N/2, (r+1)*N/2) of the
+// weights, the leader CTA (rank 0) issues every MMA (M = 256) and each CTA's TMEM receives the accumulators of its own
+// 128 rows.  Per MMA every SM reads 8 KB of shared memory instead of 12 KB, which is what a single CTA could not
+// sustain next to the TMA fill (profiles/r01_d: 1-CTA SS-mode MMAs were shared-memory-bandwidth bound).
+template <int N_TILE, int TERMS, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs args) {
-    using S = GemmSmem<N_TILE, TERMS>;
+    using S = GemmSmem<N_TILE, TERMS, PAIR>;
     static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128");
     constexpr int kTmemCols = tmem_cols_for(2 * N_TILE);
-    constexpr uint32_t kIdesc = umma_idesc_bf16(kTileM, N_TILE);
+    constexpr uint32_t kIdesc = umma_idesc_bf16(PAIR ? 2 * kTileM : kTileM, N_TILE);
+    constexpr int kTileRows = PAIR ? 2 * kTileM : kTileM;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -606,62 +612,79 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;           // 0 = leader
+    const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int n_workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
     if (threadIdx.x == 32) {
         for (int s = 0; s < S::kAStages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); }
         for (int s = 0; s < S::kBStages; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * kEpiWarps : kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 0) {
-        tmem_alloc(tmem_slot, kTmemCols);
-        tmem_relinquish();
+        if constexpr (PAIR) { tmem_alloc_pair(tmem_slot, kTmemCols); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const TapSet& ts = args.taps;
 
     if (warp == 0 && lane == 0) {
-        // ================= TMA producer =================
-        const uint32_t a_bytes = static_cast<uint32_t>(args.a_rows) * kBlockK * 2 * (TERMS == 3 ? 2 : 1);
+        // ================= TMA producer (one per CTA) =================
+        const uint32_t a_bytes = static_cast<uint32_t>(args.a_rows) * kBlockK * 2 * (TERMS == 3 ? 2 : 1) * (PAIR ? 2 : 1);
+        const uint32_t b_bytes = S::kBSlotBytes * (PAIR ? 2 : 1);
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
-        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+        for (int tile = worker; tile < args.num_tiles; tile += n_workers) {
             const int n_tile = tile % args.n_tiles_n;
             const int m = tile / args.n_tiles_n;
             const int b = m / args.tiles_per_batch;
-            const int t0 = (m % args.tiles_per_batch) * kTileM;
-            const int wrow = args.w_row0 + n_tile * N_TILE;
+            const int t0 = (m % args.tiles_per_batch) * kTileRows + rank * kTileM;
+            const int wrow = args.w_row0 + n_tile * N_TILE + rank * (N_TILE / 2);
             for (int kb = 0; kb < ts.n_kb; ++kb) {
                 // one halo tile of activations per 64-channel k-block ...
                 mbar_wait(&aempty_bar[as], aph ^ 1);
                 uint8_t* sa = smem_a + as * S::kASlotBytes;
-                mbar_arrive_expect_tx(&afull_bar[as], a_bytes);
-                tma_load_3d(sa, &args.amap[2 * ts.a_src], &afull_bar[as], ts.a_col0 + kb * kBlockK, t0 + ts.row_shift, b);
-                if (TERMS == 3)
-                    tma_load_3d(sa + S::kAPartBytes, &args.amap[2 * ts.a_src + 1], &afull_bar[as], ts.a_col0 + kb * kBlockK,
-                                t0 + ts.row_shift, b);
+                const int ac = ts.a_col0 + kb * kBlockK, ar = t0 + ts.row_shift;
+                if constexpr (PAIR) {
+                    // both CTAs' bytes are credited to the leader's barrier; only the leader arms it
+                    if (rank == 0) mbar_arrive_expect_tx(&afull_bar[as], a_bytes);
+                    tma_load_3d_pair(sa, &args.amap[2 * ts.a_src], &afull_bar[as], ac, ar, b);
+                    if (TERMS == 3) tma_load_3d_pair(sa + S::kAPartBytes, &args.amap[2 * ts.a_src + 1], &afull_bar[as], ac, ar, b);
+                } else {
+                    mbar_arrive_expect_tx(&afull_bar[as], a_bytes);
+                    tma_load_3d(sa, &args.amap[2 * ts.a_src], &afull_bar[as], ac, ar, b);
+                    if (TERMS == 3) tma_load_3d(sa + S::kAPartBytes, &args.amap[2 * ts.a_src + 1], &afull_bar[as], ac, ar, b);
+                }
                 if (++as == S::kAStages) { as = 0; aph ^= 1; }
                 // ... and one weight tile per tap
                 for (int tp = 0; tp < ts.n_taps; ++tp) {
                     mbar_wait(&bempty_bar[bs], bph ^ 1);
                     uint8_t* sb = smem_b + bs * S::kBSlotBytes;
-                    mbar_arrive_expect_tx(&bfull_bar[bs], S::kBSlotBytes);
-                    tma_load_2d(sb, &args.wmap[0], &bfull_bar[bs], ts.w_col0[tp] + kb * kBlockK, wrow);
-                    if (TERMS == 3) tma_load_2d(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], ts.w_col0[tp] + kb * kBlockK, wrow);
+                    const int wc = ts.w_col0[tp] + kb * kBlockK;
+                    if constexpr (PAIR) {
+                        if (rank == 0) mbar_arrive_expect_tx(&bfull_bar[bs], b_bytes);
+                        tma_load_2d_pair(sb, &args.wmap[0], &bfull_bar[bs], wc, wrow);
+                        if (TERMS == 3) tma_load_2d_pair(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
+                    } else {
+                        mbar_arrive_expect_tx(&bfull_bar[bs], b_bytes);
+                        tma_load_2d(sb, &args.wmap[0], &bfull_bar[bs], wc, wrow);
+                        if (TERMS == 3) tma_load_2d(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
+                    }
                     if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ================= MMA issuer (single thread) =================
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ================= MMA issuer (single thread; leader CTA only in PAIR mode) =================
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = worker; tile < args.num_tiles; tile += n_workers, ++it) {
             const int acc = it & 1;
             mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -682,54 +705,69 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         const uint64_t da = umma_smem_desc<128>(a_hi + k * 32);
                         const uint64_t db = umma_smem_desc<128>(b_hi + k * 32);
-                        umma_f16(tacc, da, db, kIdesc, accumulate);
-                        accumulate = 1;
-                        if (TERMS == 3) {
-                            umma_f16(tacc, umma_smem_desc<128>(a_lo + k * 32), db, kIdesc, 1);
-                            umma_f16(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
+                        if constexpr (PAIR) {
+                            umma_f16_pair(tacc, da, db, kIdesc, accumulate);
+                            if (TERMS == 3) {
+                                umma_f16_pair(tacc, umma_smem_desc<128>(a_lo + k * 32), db, kIdesc, 1);
+                                umma_f16_pair(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
+                            }
+                        } else {
+                            umma_f16(tacc, da, db, kIdesc, accumulate);
+                            if (TERMS == 3) {
+                                umma_f16(tacc, umma_smem_desc<128>(a_lo + k * 32), db, kIdesc, 1);
+                                umma_f16(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
+                            }
                         }
+                        accumulate = 1;
                     }
-                    umma_commit(&bempty_bar[bs]);   // frees the weight slot when these MMAs retire
+                    // free the weight slot (in both CTAs) when these MMAs retire
+                    if constexpr (PAIR) umma_commit_pair(&bempty_bar[bs]); else umma_commit(&bempty_bar[bs]);
                     if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
                 }
-                umma_commit(&aempty_bar[as]);       // frees the halo tile after its last tap
+                // free the halo tile after its last tap
+                if constexpr (PAIR) umma_commit_pair(&aempty_bar[as]); else umma_commit(&aempty_bar[as]);
                 if (++as == S::kAStages) { as = 0; aph ^= 1; }
             }
-            umma_commit(&tfull_bar[acc]);           // accumulator complete -> epilogue
+            // accumulator complete -> epilogue (of both CTAs)
+            if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
         }
     } else if (warp >= 2 && warp < 2 + kEpiWarps) {
         // ================= Epilogue warps =================
         const int quad = warp & 3;
         int it = 0;
-        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++it) {
+        // PAIR: the accumulator-free barrier lives in the leader CTA (its MMA thread waits on it)
+        const uint32_t tempty_remote0 = PAIR ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0;
+        for (int tile = worker; tile < args.num_tiles; tile += n_workers, ++it) {
             const int acc = it & 1;
             const int n_tile = tile % args.n_tiles_n;
             const int m = tile / args.n_tiles_n;
             const int b = m / args.tiles_per_batch;
-            const int t_warp = (m % args.tiles_per_batch) * kTileM + quad * 32;
+            const int t_warp = (m % args.tiles_per_batch) * kTileRows + rank * kTileM + quad * 32;
             mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * N_TILE;
             float* stage = xpose + (warp - 2) * kStageFloatsPerWarp;
             const int grp = (warp - 2) >> 2;
             if constexpr (EPI == EPI_RES_SKIP || EPI == EPI_BIAS_ACT || EPI == EPI_GATE) {
-                const int nt = tile + gridDim.x;
-                if (nt < args.num_tiles) prefetch_rmw_tile<N_TILE, EPI>(args, nt, quad, grp, lane);
+                const int nt = tile + n_workers;
+                if (nt < args.num_tiles) prefetch_rmw_tile<N_TILE, EPI>(args, nt, kTileRows, rank * kTileM + quad * 32, grp, lane);
             }
             if (args.L - t_warp >= 32) run_epilogue<N_TILE, EPI, true>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
             else run_epilogue<N_TILE, EPI, false>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_remote(tempty_remote0 + acc * 8);
+                else mbar_arrive(&tempty_bar[acc]);
+            }
         }
     }
 
-
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: no CTA may exit while its peer can still signal it
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 

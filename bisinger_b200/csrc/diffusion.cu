@@ -17,6 +17,7 @@
 // Per step: 1 + 2L + 3 launches of conv_gemm_kernel; all K steps are captured in one CUDA graph when the
 // noise is generated on the device.
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <memory>
 
@@ -129,6 +130,7 @@ __global__ void init_x_kernel(int mode, const float* __restrict__ fs2_mel, const
 // ---------------------------------------------------------------------------------------------
 static const int kOneTap[1] = {0};
 static constexpr int kXaBoxRows = 144;   // 128 + 2 * max dilation (8)
+static constexpr int kSkipTilePair = 256; // N tile of the skip-sum GEMM when run on 2-CTA tiles
 static constexpr int kResTile = 128;     // N tile of the residual / skip-sum GEMMs (N = 256): 2x the tiles -> better wave balance
 struct DiffusionPlan::Workspace {
     int B = 0, T = 0;
@@ -264,6 +266,9 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     launch_conv_gemm(80, terms, EPI_POSTERIOR, none, nullptr);
     launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, none, nullptr);
     launch_conv_gemm(kResTile, terms, EPI_RELU_BF16, none, nullptr);
+    if (const char* np = std::getenv("BSG_NO_PAIR")) use_pair = !(np[0] == '1');
+    launch_conv_gemm(256, terms, EPI_GATE, none, nullptr, true);
+    launch_conv_gemm(kSkipTilePair, terms, EPI_RELU_BF16, none, nullptr, true);
 }
 
 DiffusionPlan::~DiffusionPlan() = default;
@@ -341,9 +346,9 @@ ConvGemmArgs DiffusionPlan::gate_args(Workspace& w, int l) {
     const int H = cfg.hidden_size, C = cfg.residual_channels;
     Layer& ly = layers[l];
     ConvGemmArgs a{};
-    set_geometry(a, w.B, w.T, 2 * C, 256);
+    set_geometry(a, w.B, w.T, 2 * C, 256, use_pair);
     a.amap[0] = w.m_xa[0]; a.amap[1] = w.m_xa[1];
-    set_w(a, ly.g1, 256);
+    set_w(a, ly.g1, use_pair ? 128 : 256);   // 2-CTA tiles: each CTA stages half of the 256 weight rows
     const int shifts[3] = {-ly.dilation, 0, ly.dilation};
     set_taps(a, 0, 0, C / kBlockK, shifts, 3, C);
     a.a_rows = kXaBoxRows;   // the xa tensor maps are encoded once with the box of the largest dilation
@@ -389,7 +394,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
     auto run = [&](int n) {
         for (int i = 0; i < n; ++i) {
             const int l = i % L;
-            if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st);
+            if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, use_pair);
             else launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
             ++launches, ++g_launch_count;
         }
@@ -431,23 +436,24 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         ++launches, ++g_launch_count;
     }
     for (int l = 0; l < L; ++l) {
-        launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st);
+        launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, use_pair);
         ++launches, ++g_launch_count;
         launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut_t), st);
         ++launches, ++g_launch_count;
     }
     {   // skip sum: sum_l (W_skip,l z_l + b_skip,l) / sqrt(L)  (net.py:77-78,126) as one K = L*C GEMM over the step's z matrix
         ConvGemmArgs a{};
-        set_geometry(a, B, T, C, kResTile);
+        const int nt = use_pair ? kSkipTilePair : kResTile;
+        set_geometry(a, B, T, C, nt, use_pair);
         a.amap[0] = w.m_z[0]; a.amap[1] = w.m_z[1];
-        set_w(a, skipall, kResTile);
+        set_w(a, skipall, use_pair ? nt / 2 : nt);
         set_taps(a, 0, 0, L * C / kBlockK, kOneTap, 1, 0);
         a.epi.bias = skipall_bias.as<float>();
         a.epi.out_hi = w.s_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.s_lo);
         a.epi.out_pitch = C;
         a.epi.flags = 1;                                        // no ReLU
         a.epi.c0 = 1.0f / std::sqrt(static_cast<float>(L));
-        launch_conv_gemm(kResTile, terms, EPI_RELU_BF16, a, st);
+        launch_conv_gemm(nt, terms, EPI_RELU_BF16, a, st, use_pair);
         ++launches, ++g_launch_count;
     }
     {   // skip_projection + ReLU (net.py:127-128)

@@ -43,10 +43,10 @@ int device_sm_count() {
 
 namespace {
 
-template <int N_TILE, int TERMS, int EPI>
+template <int N_TILE, int TERMS, int EPI, bool PAIR>
 void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
-    using S = GemmSmem<N_TILE, TERMS>;
-    auto kern = conv_gemm_kernel<N_TILE, TERMS, EPI>;
+    using S = GemmSmem<N_TILE, TERMS, PAIR>;
+    auto kern = conv_gemm_kernel<N_TILE, TERMS, EPI, PAIR>;
     static std::once_flag once;   // per instantiation
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal); });
@@ -55,30 +55,52 @@ void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
     if (sms == 0) sms = device_sm_count();
     if (args.num_tiles <= 0) return;
     B200_CHECK(args.a_rows >= kTileM && args.a_rows <= S::kASlotRows && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
-    const int grid = args.num_tiles < sms ? args.num_tiles : sms;
-    kern<<<grid, kGemmThreads, S::kTotal, stream>>>(args);
+    if (!PAIR) {
+        const int grid = args.num_tiles < sms ? args.num_tiles : sms;
+        kern<<<grid, kGemmThreads, S::kTotal, stream>>>(args);
+    } else {
+        const int pairs = sms / 2;
+        const int grid = 2 * (args.num_tiles < pairs ? args.num_tiles : pairs);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = S::kTotal;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        B200_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+    }
     B200_CUDA(cudaGetLastError());
 }
 
 }  // namespace
 
 #define B200_CASE(NT, TM, EP) \
-    if (n_tile == NT && terms == TM && epi == EP) return launch_inst<NT, TM, EP>(args, stream);
+    if (!pair && n_tile == NT && terms == TM && epi == EP) return launch_inst<NT, TM, EP, false>(args, stream);
+#define B200_PAIR(NT, TM, EP) \
+    if (pair && n_tile == NT && terms == TM && epi == EP) return launch_inst<NT, TM, EP, true>(args, stream);
 
-void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream) {
+void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream, bool pair) {
     // unit-test GEMMs
     B200_CASE(256, 1, EPI_F32) B200_CASE(256, 3, EPI_F32) B200_CASE(128, 1, EPI_F32) B200_CASE(128, 3, EPI_F32)
     B200_CASE(64, 1, EPI_F32) B200_CASE(32, 1, EPI_F32)
+    B200_PAIR(256, 1, EPI_F32) B200_PAIR(256, 3, EPI_F32) B200_PAIR(128, 3, EPI_F32)
     // DiffNet
     B200_CASE(256, 1, EPI_INPROJ) B200_CASE(256, 3, EPI_INPROJ)
-    B200_CASE(256, 1, EPI_GATE) B200_CASE(256, 3, EPI_GATE)
+    B200_CASE(256, 1, EPI_GATE) B200_CASE(256, 3, EPI_GATE) B200_PAIR(256, 1, EPI_GATE) B200_PAIR(256, 3, EPI_GATE)
     B200_CASE(256, 1, EPI_RES_SKIP) B200_CASE(256, 3, EPI_RES_SKIP) B200_CASE(128, 1, EPI_RES_SKIP) B200_CASE(128, 3, EPI_RES_SKIP)
     B200_CASE(256, 1, EPI_RELU_BF16) B200_CASE(256, 3, EPI_RELU_BF16) B200_CASE(128, 1, EPI_RELU_BF16) B200_CASE(128, 3, EPI_RELU_BF16)
+    B200_PAIR(256, 1, EPI_RELU_BF16) B200_PAIR(256, 3, EPI_RELU_BF16) B200_PAIR(128, 1, EPI_RELU_BF16) B200_PAIR(128, 3, EPI_RELU_BF16)
     B200_CASE(80, 1, EPI_POSTERIOR) B200_CASE(80, 3, EPI_POSTERIOR)
     // HiFi-GAN
     B200_CASE(256, 1, EPI_BIAS_ACT) B200_CASE(128, 1, EPI_BIAS_ACT) B200_CASE(64, 1, EPI_BIAS_ACT) B200_CASE(32, 1, EPI_BIAS_ACT)
     throw Error("conv_gemm: no instantiation for n_tile=" + std::to_string(n_tile) + " terms=" + std::to_string(terms) +
-                " epi=" + std::to_string(epi));
+                " epi=" + std::to_string(epi) + (pair ? " (pair)" : ""));
 }
 
 }  // namespace b200

@@ -27,6 +27,7 @@ public:
     int device;
     int terms = 1;
     bool use_graphs = true;
+    bool use_pair = true;    // 2-CTA (cta_group::2) tiles for the tensor-bound GEMMs (gate GEMM, skip-sum GEMM)
     unsigned long long launches = 0;
 
 private:

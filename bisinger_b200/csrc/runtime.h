@@ -112,13 +112,15 @@ inline CUtensorMap make_w_tmap(const void* base, int N, int K, int n_tile, int r
 int device_sm_count();
 
 // Launch one instantiation of conv_gemm_kernel (defined in gemm_launch.cu)
-void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream);
+// pair = true: 2-CTA clusters on 256-row tiles (tcgen05 cta_group::2); the weight tensor map box must then be n_tile/2 rows
+void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream, bool pair = false);
 
 // fills the tile-geometry fields of args from (B, L, N_total, n_tile)
-inline void set_geometry(ConvGemmArgs& a, int B, int L, int n_total, int n_tile) {
+inline void set_geometry(ConvGemmArgs& a, int B, int L, int n_total, int n_tile, bool pair = false) {
     a.B = B;
     a.L = L;
-    a.tiles_per_batch = (L + kTileM - 1) / kTileM;
+    const int rows = pair ? 2 * kTileM : kTileM;
+    a.tiles_per_batch = (L + rows - 1) / rows;
     a.n_tiles_n = n_total / n_tile;
     a.num_tiles = B * a.tiles_per_batch * a.n_tiles_n;
     a.w_row0 = 0;

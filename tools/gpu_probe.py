@@ -206,7 +206,40 @@ def stage_proftarget():
     print("kernel", which, "ms", plan.time_kernel(which, 32, 1875, 4))
 
 
-STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench, "vocoder": stage_vocoder, "vbench": stage_vbench, "proftarget": stage_proftarget}
+def stage_pairtest():
+    """2-CTA (cta_group::2) variant of the conv kernel through the self-test entry (precision | 0x100)."""
+    import ctypes as C, torch
+    from bisinger_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(0)
+    cases = [
+        (1, 256, 64, 256, [0], 256, 0), (1, 256, 256, 256, [0], 256, 0), (2, 300, 256, 512, [-2, 0, 2], 256, 0),
+        (2, 300, 256, 512, [-8, 0, 8], 256, 1), (1, 1875, 256, 256, [0], 128, 1), (3, 77, 256, 256, [-1, 0, 1], 256, 1),
+        (4, 1000, 512, 256, [0], 128, 1),
+    ]
+    for (B, Lr, Cin, N, shifts, n_tile, prec) in cases:
+        a = torch.randn(B, Lr, Cin, device="cuda")
+        w = torch.randn(N, len(shifts), Cin) / (Cin * len(shifts)) ** 0.5
+        bias = torch.randn(N)
+        out = torch.full((B, Lr, N), float("nan"), device="cuda")
+        sh = (C.c_int * len(shifts))(*shifts)
+        st = L.bsg_selftest_conv(_lib.dev_ptr(a), _lib.fptr(w.contiguous()), _lib.fptr(bias), B, Lr, Cin, N, len(shifts), sh, n_tile, prec | 0x100,
+                                 _lib.dev_ptr(out), None)
+        if st != 0:
+            print("PAIR CASE", (B, Lr, Cin, N, shifts, n_tile, prec), "ERROR", L.bsg_last_error().decode()); continue
+        torch.cuda.synchronize()
+        ar, wr = (a.bfloat16().float(), w.bfloat16().float()) if prec == 0 else (a, w)
+        ref = conv_ref(ar, wr.cuda(), bias.cuda(), shifts)
+        err = (out.double() - ref).abs()
+        print("PAIR CASE", (B, Lr, Cin, N, shifts, n_tile, prec), "max_err %.3e" % err.max().item(), "nan", int(torch.isnan(out).sum().item()))
+        if not (err.max().item() < 1e-2):
+            e = err[0]
+            rows = e.amax(dim=1); cols = e.amax(dim=0)
+            print("   bad rows (b=0):", [i for i in range(min(Lr, 600)) if rows[i] > 1e-2][:24], "... count", int((rows > 1e-2).sum()))
+            print("   bad cols:", [i for i in range(N) if cols[i] > 1e-2][:24], "... count", int((cols > 1e-2).sum()))
+
+
+STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench, "vocoder": stage_vocoder, "vbench": stage_vbench, "proftarget": stage_proftarget, "pairtest": stage_pairtest}
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--run":
