@@ -84,78 +84,105 @@ __global__ void nsf_source_kernel(const float* __restrict__ f0, const double* __
 }
 
 // x += layer_norm_C( relu( noise_conv(har) ) ); a = lrelu(x)     hifigan.py:155-160
-// noise_conv: Conv1d(1 -> C, kernel ksz, stride s, padding pad).  blockDim = 256 = (256/C) rows x C channels.
-__global__ void noise_branch_kernel(const float* __restrict__ har, const float* __restrict__ w, const float* __restrict__ bias, int B,
-                                    long long Lout, long long Lhar, int C, int ksz, int stride, int pad, int has_source,
-                                    float* __restrict__ x, __nv_bfloat16* __restrict__ act, int act_pitch) {
-    extern __shared__ float sm[];
-    const int rows_per_block = blockDim.x / C;
-    float* red = sm;                                  // [blockDim/32] partial sums
-    const int c = threadIdx.x % C, rl = threadIdx.x / C;
-    const int warps_per_row = C / 32;
-    const long long row = static_cast<long long>(blockIdx.x) * rows_per_block + rl;
-    const bool ok = row < static_cast<long long>(B) * Lout;
-    float v = 0.0f;
-    if (ok && has_source) {
-        const int b = static_cast<int>(row / Lout);
-        const long long l = row % Lout;
-        float acc = bias[c];
-        for (int k = 0; k < ksz; ++k) {
-            const long long hl = l * stride - pad + k;
-            if (hl >= 0 && hl < Lhar) acc = fmaf(w[c * ksz + k], har[static_cast<long long>(b) * Lhar + hl], acc);
-        }
-        v = fmaxf(acc, 0.0f);
-    }
-    float out = 0.0f;
+// noise_conv: Conv1d(1 -> C, kernel ksz, stride s, padding pad).  One warp per output row (grid-stride): lane owns
+// channels lane, lane+32, ...; the conv weights sit in shared memory as [k][c] (conflict-free), the <= 32 source
+// samples of the row's window are held one per lane and broadcast with shuffles; LayerNorm statistics by warp
+// shuffles (two-pass, as F.layer_norm); x is read-modified-written with 128-byte coalesced accesses.
+template <int CPL>   // channels per lane = C / 32
+__global__ void __launch_bounds__(256) noise_branch_kernel(const float* __restrict__ har, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, int B, long long Lout, long long Lhar, int ksz,
+                                                           int stride, int pad, int has_source, float* __restrict__ x,
+                                                           __nv_bfloat16* __restrict__ act, int act_pitch) {
+    constexpr int C = CPL * 32;
+    extern __shared__ float wsm[];   // [ksz][C] then bias [C]
     if (has_source) {
-        // two-pass mean / variance over the C channels of a row (F.layer_norm, eps 1e-5, no affine)
-        float s = v;
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-        __syncthreads();
-        float mean = 0.0f;
-        for (int i = 0; i < warps_per_row; ++i) mean += red[rl * warps_per_row + i];
-        mean /= static_cast<float>(C);
-        __syncthreads();
-        const float d = v - mean;
-        float q = d * d;
-        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
-        __syncthreads();
-        float var = 0.0f;
-        for (int i = 0; i < warps_per_row; ++i) var += red[rl * warps_per_row + i];
-        var /= static_cast<float>(C);
-        out = d * rsqrtf(var + 1e-5f);
+        for (int i = threadIdx.x; i < ksz * C; i += blockDim.x) wsm[(i % ksz) * C + i / ksz] = w[i];   // w is [C][ksz]
+        for (int i = threadIdx.x; i < C; i += blockDim.x) wsm[ksz * C + i] = bias[i];
     }
-    if (ok) {
-        const float xv = x[row * C + c] + out;
-        x[row * C + c] = xv;
-        act[row * act_pitch + c] = __float2bfloat16_rn(xv > 0.0f ? xv : xv * kLrelu);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp_g = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const long long rows = static_cast<long long>(B) * Lout;
+    for (long long row = warp_g; row < rows; row += n_warps) {
+        float v[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) v[j] = 0.0f;
+        if (has_source) {
+            const int b = static_cast<int>(row / Lout);
+            const long long l = row % Lout;
+            const long long h0 = l * stride - pad;
+            float hs = 0.0f;
+            if (lane < ksz) {
+                const long long hl = h0 + lane;
+                if (hl >= 0 && hl < Lhar) hs = har[static_cast<long long>(b) * Lhar + hl];
+            }
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) v[j] = wsm[ksz * C + lane + 32 * j];
+            for (int k = 0; k < ksz; ++k) {
+                const float hk = __shfl_sync(0xffffffffu, hs, k);
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) v[j] = fmaf(wsm[k * C + lane + 32 * j], hk, v[j]);
+            }
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) { v[j] = fmaxf(v[j], 0.0f); sum += v[j]; }
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum / static_cast<float>(C);
+            float q = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) { v[j] -= mean; q += v[j] * v[j]; }
+            for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            const float rstd = rsqrtf(q / static_cast<float>(C) + 1e-5f);
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) v[j] *= rstd;
+        }
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const int c = lane + 32 * j;
+            const float xv = x[row * C + c] + v[j];
+            x[row * C + c] = xv;
+            act[row * act_pitch + c] = __float2bfloat16_rn(xv > 0.0f ? xv : xv * kLrelu);
+        }
     }
 }
 
-// wav = tanh( conv_post( lrelu(x, 0.01) ) )   hifigan.py:169-171 ; conv_post: Conv1d(C -> 1, k, padding (k-1)/2)
-__global__ void conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B,
-                                 long long L, int C, int ksz, float* __restrict__ wav) {
-    extern __shared__ float wsm[];   // [ksz][C]
-    for (int i = threadIdx.x; i < ksz * C; i += blockDim.x) wsm[i] = w[i];
-    __syncthreads();
-    const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (g >= static_cast<long long>(B) * L) return;
-    const long long l = g % L;
+// wav = tanh( conv_post( lrelu(x, 0.01) ) )   hifigan.py:169-171 ; conv_post: Conv1d(C -> 1, k, padding (k-1)/2), C == 32.
+// A block stages blockDim + k - 1 rows of lrelu(x) in shared memory (pitch 33: conflict-free) with coalesced loads.
+__global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, int B, long long L, int ksz,
+                                                        float* __restrict__ wav) {
+    constexpr int C = 32, P = 33;
+    extern __shared__ float sm[];
+    float* wsm = sm;                  // [ksz][C]
+    float* xs = sm + ksz * C;         // [blockDim + ksz - 1][P]
     const int half = (ksz - 1) / 2;
+    for (int i = threadIdx.x; i < ksz * C; i += blockDim.x) wsm[i] = w[i];
+    const long long g0 = static_cast<long long>(blockIdx.x) * blockDim.x;   // first output sample (flattened b*L + l) of this block
+    const long long total = static_cast<long long>(B) * L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int nrows = blockDim.x + ksz - 1;
+    for (int r = warp; r < nrows; r += nwarp) {
+        const long long g = g0 + r - half;          // flattened source row
+        float v = 0.0f;
+        if (g >= 0 && g < total) {
+            v = x[g * C + lane];
+            v = v > 0.0f ? v : v * 0.01f;
+        }
+        xs[r * P + lane] = v;
+    }
+    __syncthreads();
+    const long long g = g0 + threadIdx.x;
+    if (g >= total) return;
+    const long long l = g % L;
     float acc = bias[0];
     for (int k = 0; k < ksz; ++k) {
         const long long ll = l + k - half;
-        if (ll < 0 || ll >= L) continue;
-        const float4* xr = reinterpret_cast<const float4*>(x + (g + k - half) * C);
-        for (int c4 = 0; c4 < C / 4; ++c4) {
-            const float4 q = xr[c4];
-            const float* ww = wsm + k * C + c4 * 4;
-            const float a0 = q.x > 0.f ? q.x : q.x * 0.01f, a1 = q.y > 0.f ? q.y : q.y * 0.01f;
-            const float a2 = q.z > 0.f ? q.z : q.z * 0.01f, a3 = q.w > 0.f ? q.w : q.w * 0.01f;
-            acc = fmaf(ww[0], a0, acc); acc = fmaf(ww[1], a1, acc); acc = fmaf(ww[2], a2, acc); acc = fmaf(ww[3], a3, acc);
-        }
+        if (ll < 0 || ll >= L) continue;              // zero padding at the ends of every batch item
+        const float* xr = xs + (threadIdx.x + k) * P;
+        const float* ww = wsm + k * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc = fmaf(ww[c], xr[c], acc);
     }
     wav[g] = tanhf(acc);
 }
@@ -428,11 +455,24 @@ void HifiganPlan::forward(const float* mel, const float* f0, const float* rand_i
         __nv_bfloat16* Tb = w.Tb.as<__nv_bfloat16>();
         // ---- harmonic-source branch + lrelu (hifigan.py:155-160, ResBlock1's first leaky_relu :56)
         {
-            const int threads = 256;
-            const int rpb = threads / C;
-            noise_branch_kernel<<<static_cast<unsigned>((rows + rpb - 1) / rpb), threads, (threads / 32) * sizeof(float), st>>>(
-                w.har.as<float>(), has_src ? s.noise_w.as<float>() : nullptr, has_src ? s.noise_b.as<float>() : nullptr, B, Lout,
-                static_cast<long long>(T) * hop, C, s.noise_k, s.noise_stride, s.noise_pad, has_src ? 1 : 0, w.X0.as<float>(), A0, Cp);
+            B200_CHECK(s.noise_k <= 32, "noise branch kernel holds the source window in one warp (kernel size <= 32)");
+            const int blocks = device_sm_count() * 8;
+            const size_t sm_bytes = (static_cast<size_t>(s.noise_k) * C + C) * sizeof(float);
+            const float* nw = has_src ? s.noise_w.as<float>() : nullptr;
+            const float* nb = has_src ? s.noise_b.as<float>() : nullptr;
+            const long long Lhar = static_cast<long long>(T) * hop;
+#define B200_NOISE(CPL)                                                                                                              \
+    noise_branch_kernel<CPL><<<blocks, 256, sm_bytes, st>>>(w.har.as<float>(), nw, nb, B, Lout, Lhar, s.noise_k, s.noise_stride, \
+                                                           s.noise_pad, has_src ? 1 : 0, w.X0.as<float>(), A0, Cp)
+            switch (C / 32) {
+                case 1: B200_NOISE(1); break;
+                case 2: B200_NOISE(2); break;
+                case 4: B200_NOISE(4); break;
+                case 8: B200_NOISE(8); break;
+                case 16: B200_NOISE(16); break;
+                default: throw Error("noise branch: unsupported channel count");
+            }
+#undef B200_NOISE
             launches += 1, g_launch_count += 1;
             B200_CUDA(cudaGetLastError());
         }
@@ -482,8 +522,9 @@ void HifiganPlan::forward(const float* mel, const float* f0, const float* rand_i
     {   // lrelu(0.01) -> conv_post -> tanh (hifigan.py:169-171)
         const int C = stages.back().cout;
         const long long n = static_cast<long long>(B) * Lcur;
-        conv_post_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 7 * C * sizeof(float), st>>>(
-            w.S.as<float>(), post_w.as<float>(), post_b.as<float>(), B, Lcur, C, 7, wav);
+        B200_CHECK(C == 32, "conv_post kernel is specialised for 32 input channels");
+        conv_post_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, (7 * 32 + (256 + 6) * 33) * sizeof(float), st>>>(
+            w.S.as<float>(), post_w.as<float>(), post_b.as<float>(), B, Lcur, 7, wav);
         launches += 1, g_launch_count += 1;
         B200_CUDA(cudaGetLastError());
     }

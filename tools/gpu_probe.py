@@ -239,7 +239,20 @@ def stage_pairtest():
             print("   bad cols:", [i for i in range(N) if cols[i] > 1e-2][:24], "... count", int((cols > 1e-2).sum()))
 
 
-STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench, "vocoder": stage_vocoder, "vbench": stage_vbench, "proftarget": stage_proftarget, "pairtest": stage_pairtest}
+def stage_vproftarget():
+    """Target for ncu: two vocoder forwards at the cfg3 shape."""
+    import torch
+    h, sd, gen, O, synth = _voc_setup()
+    B, T = 32, 1875
+    g = torch.Generator().manual_seed(1)
+    mel = (torch.rand(B, 80, T, generator=g) * 5 - 6).cuda()
+    f0 = (torch.rand(B, T, generator=g) * 300 + 100).cuda()
+    for i in range(2):
+        gen(mel, f0, seed=i)
+    torch.cuda.synchronize()
+
+
+STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench, "vocoder": stage_vocoder, "vbench": stage_vbench, "proftarget": stage_proftarget, "pairtest": stage_pairtest, "vproftarget": stage_vproftarget}
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--run":
