@@ -631,6 +631,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) may overlap the tail of the
+    // previous kernel in the stream / graph; global memory written by it is only touched after this wait.  The
+    // trigger right behind it lets the NEXT kernel's CTAs be scheduled as soon as SMs drain.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     const TapSet& ts = args.taps;
 
     if (warp == 0 && lane == 0) {

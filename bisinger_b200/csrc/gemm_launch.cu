@@ -1,4 +1,5 @@
 // Instantiations + host dispatcher of conv_gemm_kernel, and TMA tensor-map encoding.
+#include <cstdlib>
 #include <mutex>
 
 #include "runtime.h"
@@ -43,6 +44,11 @@ int device_sm_count() {
 
 namespace {
 
+bool use_pdl() {
+    static const bool on = [] { const char* e = std::getenv("BSG_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 template <int N_TILE, int TERMS, int EPI, bool PAIR>
 void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
     using S = GemmSmem<N_TILE, TERMS, PAIR>;
@@ -55,26 +61,30 @@ void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
     if (sms == 0) sms = device_sm_count();
     if (args.num_tiles <= 0) return;
     B200_CHECK(args.a_rows >= kTileM && args.a_rows <= S::kASlotRows && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
-    if (!PAIR) {
-        const int grid = args.num_tiles < sms ? args.num_tiles : sms;
-        kern<<<grid, kGemmThreads, S::kTotal, stream>>>(args);
-    } else {
-        const int pairs = sms / 2;
-        const int grid = 2 * (args.num_tiles < pairs ? args.num_tiles : pairs);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kGemmThreads);
-        cfg.dynamicSmemBytes = S::kTotal;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        B200_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+    const int pairs = sms / 2;
+    const int grid = PAIR ? 2 * (args.num_tiles < pairs ? args.num_tiles : pairs) : (args.num_tiles < sms ? args.num_tiles : sms);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = S::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (use_pdl()) {   // the kernel's prologue overlaps the previous kernel's tail (griddepcontrol.wait inside)
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
     }
+    if (PAIR) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
     B200_CUDA(cudaGetLastError());
 }
 
