@@ -106,7 +106,8 @@ int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias
         B200_CHECK(Cin % 8 == 0 && N % n_tile == 0 && ntaps >= 1 && ntaps <= kMaxTaps, "bad shape");
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         const bool pair = (precision & 0x100) != 0;   // test hook: run the 2-CTA (cta_group::2) variant of the kernel
-        const int terms = (precision & 0xff) == BSG_PRECISION_BF16X3 ? 3 : 1;
+        const int prec = precision & 0xff;
+        const int terms = prec == BSG_PRECISION_BF16X3 ? 3 : (prec == BSG_PRECISION_FP16X2 ? 2 : 1);
         const size_t rows = static_cast<size_t>(B) * L;
         // activations -> bf16 hi/lo (same split kernel the plans use is file-local; do it on the host here)
         std::vector<float> a_host(rows * Cin);
@@ -114,6 +115,7 @@ int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias
         B200_CUDA(cudaStreamSynchronize(st));
         std::vector<uint16_t> ah(a_host.size()), al(a_host.size());
         for (size_t i = 0; i < a_host.size(); ++i) {
+            if (terms == 2) { ah[i] = f32_to_f16_bits(a_host[i]); al[i] = 0; continue; }   // fp16x2: one fp16 activation operand
             ah[i] = f32_to_bf16_bits(a_host[i]);
             al[i] = f32_to_bf16_bits(a_host[i] - bf16_bits_to_f32(ah[i]));
         }
@@ -130,7 +132,7 @@ int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias
                 for (int c = 0; c < Cin; ++c)
                     wp[(static_cast<size_t>(n) * ntaps + tp) * Cpad + c] = w_host[(static_cast<size_t>(n) * ntaps + tp) * Cin + c];
         PackedW pw;
-        pw.pack(wp, N, ntaps * Cpad);
+        pw.pack(wp, N, ntaps * Cpad, terms == 2);
         ConvGemmArgs a{};
         set_geometry(a, B, L, N, n_tile, pair);
         const int rows_box = set_taps(a, 0, 0, n_kb, shifts, ntaps, Cpad);
@@ -140,6 +142,7 @@ int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias
         a.epi.bias = d_bias.as<float>();
         a.epi.f32_a = out_dev;
         a.epi.out_pitch = N;
+        a.epi.acc_scale = pw.acc_scale;
         launch_conv_gemm(n_tile, terms, EPI_F32, a, st, pair);
         ++g_launch_count;
         B200_CUDA(cudaStreamSynchronize(st));

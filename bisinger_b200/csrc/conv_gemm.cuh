@@ -18,6 +18,12 @@
 // and each k-block issues A_hi*W_hi + A_lo*W_hi + A_hi*W_lo into the same fp32 accumulator (~16
 // mantissa bits).  The 100-step sampler needs it to stay within the 1e-2 mel tolerance.
 //
+// TERMS == 2 is the "fp16x2" contraction: activations are ONE fp16 operand, weights are carried as fp16 hi/lo
+// (pre-scaled by a power of two so that lo stays out of the subnormal range; EpiParams::acc_scale undoes it) and each
+// k-block issues A*W_hi + A*W_lo.  Weight rounding is the systematic error of the 100-step sampler; activation rounding
+// at 11 significant bits is not (tools/precision_study.py), so this mode meets the tolerance with 2/3 of
+// the MMAs and half the activation bytes of bf16x3.
+//
 // Warp roles (320 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer (one thread),
 // warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4; the two warps of a quadrant split the tile's columns --
 // a single warp per scheduler was instruction-latency bound, profiles/r01_b).  Before working on tile i every
@@ -80,6 +86,8 @@ struct EpiParams {
     float c0, c1, c2, c3, c4;  // POSTERIOR: sqrt_recip, sqrt_recipm1, coef1, coef2, sigma (0 at t==0) ; BIAS_ACT: scale, slope
     const unsigned long long* seed_ptr;  // POSTERIOR: device-resident Philox seed (read when aux0 == null)
     unsigned int step;         // POSTERIOR: Philox stream offset (executed step index)
+    float acc_scale;           // accumulators are multiplied by this on load (2^-p of the fp16x2 weight pre-scale; 0 => 1)
+    int out_fp16;              // out_hi receives ONE fp16 operand (consumer runs fp16x2) instead of bf16 hi[/lo]
 };
 
 struct ConvGemmArgs {
@@ -146,21 +154,21 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f,
 
 
 // ---- accumulator access -----------------------------------------------------------------------
-__device__ __forceinline__ void ld_acc32(uint32_t taddr, float (&v)[32]) {
+__device__ __forceinline__ void ld_acc32(uint32_t taddr, float (&v)[32], float scale) {
     uint32_t r[32];
     __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after any divergent store path
     tmem_ld32(taddr, r);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * scale;
 }
-__device__ __forceinline__ void ld_acc16(uint32_t taddr, float (&v)[16]) {
+__device__ __forceinline__ void ld_acc16(uint32_t taddr, float (&v)[16], float scale) {
     uint32_t r[16];
     __syncwarp();
     tmem_ld16(taddr, r);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * scale;
 }
 
 // ---- coalescing transpose ---------------------------------------------------------------------
@@ -206,12 +214,17 @@ __device__ __forceinline__ void chunk_transpose(float* stage, int lane, const fl
     }
 }
 // load one accumulator chunk (32 rows x 32 columns starting at column c) in transposed ownership
-__device__ __forceinline__ void ld_chunk_t(uint32_t tacc, int c, float* stage, int lane, float2 (&o)[16]) {
+__device__ __forceinline__ void ld_chunk_t(uint32_t tacc, int c, float* stage, int lane, float2 (&o)[16], float scale) {
     float v[32];
-    ld_acc32(tacc + c, v);
+    ld_acc32(tacc + c, v, scale);
     chunk_transpose(stage, lane, v, o);
 }
 // bf16 hi/lo split of two neighbouring values, packed for 4-byte stores
+// fp16 operand of the fp16x2 mode (saturating: an out-of-range activation must not become inf)
+__device__ __forceinline__ void st_half2(float2 y, __nv_bfloat16* dst) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(y.x, -65504.0f), 65504.0f), fminf(fmaxf(y.y, -65504.0f), 65504.0f));
+    *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ void st_split2(float2 y, __nv_bfloat16* hi, __nv_bfloat16* lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(y.x, y.y);
     const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
@@ -221,6 +234,13 @@ __device__ __forceinline__ void st_split2(float2 y, __nv_bfloat16* hi, __nv_bflo
         const __nv_bfloat162 l = __floats2bfloat162_rn(y.x - hx, y.y - hy);
         *reinterpret_cast<uint32_t*>(lo) = *reinterpret_cast<const uint32_t*>(&l);
     }
+}
+// next GEMM's A operand at element offset `off`: one fp16 value (fp16x2 consumer) or bf16 hi[/lo]
+// FMT: 0 = bf16 split, 1 = fp16, 2 = decided at run time by e.out_fp16
+template <int FMT>
+__device__ __forceinline__ void st_operand2(const EpiParams& e, float2 y, long long off) {
+    if (FMT == 1 || (FMT == 2 && e.out_fp16)) st_half2(y, e.out_hi + off);
+    else st_split2(y, e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr);
 }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
@@ -239,26 +259,27 @@ enum : int {
 // b: batch index, t_warp: first row (within the batch) of this warp's 32 accumulator lanes, grp: column group of the
 // warp (0/1: two warps share a TMEM lane quadrant and split the tile's columns), stage: the warp's transpose tile.
 // FULL: all 32 rows of the warp are inside the batch (no row predicates).  Rows t >= L are never stored.
-template <int N_TILE, int EPI, bool FULL>
+template <int N_TILE, int EPI, bool FULL, bool OUT16>
 __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t tacc, int b, int t_warp, int n_tile, int grp,
                                              float* stage, int lane) {
     const EpiParams& e = args.epi;
     const LanePos lp = lane_pos(lane);
+    const float sc = e.acc_scale != 0.0f ? e.acc_scale : 1.0f;
     const long long row_w = static_cast<long long>(b) * args.L + t_warp;   // global row of the warp's lane 0
     const int rows_left = args.L - t_warp - lp.r0;                          // row pair rp is valid iff 2*rp < rows_left
 #define B200_ROW_OK(rp) (FULL || 2 * (rp) < rows_left)
     // column range of this warp
     constexpr int kSplit = (N_TILE % 64 == 0) ? 2 : 1;
     constexpr int kColsPerGrp = N_TILE / kSplit;
-    if (kSplit == 1 && grp != 0) return;
+    if (EPI != EPI_POSTERIOR && kSplit == 1 && grp != 0) return;
     const int c_begin = grp * kColsPerGrp;
-    (void)rows_left; (void)c_begin; (void)row_w; (void)lp;
+    (void)rows_left; (void)c_begin; (void)row_w; (void)lp; (void)sc;
 
     if constexpr (EPI == EPI_F32) {
 #pragma unroll 1
         for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
             float2 o[16];
-            ld_chunk_t(tacc, c, stage, lane, o);
+            ld_chunk_t(tacc, c, stage, lane, o, sc);
             const int n = n_tile * N_TILE + c + lp.cc;
             const float2 bias = ldg2(e.bias + n);
             float* p = e.f32_a + (row_w + lp.r0) * e.out_pitch + n;
@@ -271,7 +292,7 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
 #pragma unroll 1
         for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
             float2 o[16];
-            ld_chunk_t(tacc, c, stage, lane, o);
+            ld_chunk_t(tacc, c, stage, lane, o, sc);
             const int n = n_tile * N_TILE + c + lp.cc;
             const float2 bias = ldg2(e.bias + n), d = ldg2(e.dvec + n);
             const long long off0 = (row_w + lp.r0) * e.out_pitch + n, st = 2LL * e.out_pitch;
@@ -281,7 +302,7 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
                     const long long off = off0 + rp * st;
                     const float2 x = make_float2(fmaxf(o[rp].x + bias.x, 0.0f), fmaxf(o[rp].y + bias.y, 0.0f));
                     st2(e.f32_a + off, x);
-                    st_split2(make_float2(x.x + d.x, x.y + d.y), e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr);
+                    st_operand2<2>(e, make_float2(x.x + d.x, x.y + d.y), off);
                 }
             }
         }
@@ -301,20 +322,20 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp)
                 if (B200_ROW_OK(rp)) cp[rp] = ld2(e.aux0 + cp0 + rp * cst);
-            ld_chunk_t(tacc, c, stage, lane, g);
+            ld_chunk_t(tacc, c, stage, lane, g, sc);
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp) { g[rp].x += cp[rp].x; g[rp].y += cp[rp].y; }
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp)
                 if (B200_ROW_OK(rp)) cp[rp] = ld2(e.aux0 + cp0 + HALF + rp * cst);
-            ld_chunk_t(tacc, HALF + c, stage, lane, f);
+            ld_chunk_t(tacc, HALF + c, stage, lane, f, sc);
             const long long off0 = (row_w + lp.r0) * static_cast<long long>(e.act_pitch) + e.out_col0 + ch, st = 2LL * e.act_pitch;
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp) {
                 if (B200_ROW_OK(rp)) {
                     const float2 z = make_float2(fast_sigmoid(g[rp].x) * fast_tanh(f[rp].x + cp[rp].x),
                                                  fast_sigmoid(g[rp].y) * fast_tanh(f[rp].y + cp[rp].y));
-                    st_split2(z, e.out_hi + off0 + rp * st, e.out_lo ? e.out_lo + off0 + rp * st : nullptr);
+                    st_operand2<OUT16 ? 1 : 0>(e, z, off0 + rp * st);
                 }
             }
         }
@@ -346,7 +367,7 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
                     if (B200_ROW_OK(rp)) xn[rp] = ld2(e.f32_a + off0 + 32 + rp * st);
             }
             float2 o[16];
-            ld_chunk_t(tacc, c, stage, lane, o);
+            ld_chunk_t(tacc, c, stage, lane, o, sc);
             const float2 bias = ldg2(e.bias + cl);
             float2 d = make_float2(0.f, 0.f);
             if (e.dvec != nullptr) d = ldg2(e.dvec + cl);
@@ -357,7 +378,7 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
                     const float2 y = make_float2((x[rp].x + o[rp].x + bias.x) * rs2, (x[rp].y + o[rp].y + bias.y) * rs2);
                     st2(e.f32_a + off, y);
                     if (e.dvec != nullptr)   // not needed after the last layer
-                        st_split2(make_float2(y.x + d.x, y.y + d.y), e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr);
+                        st_operand2<OUT16 ? 1 : 0>(e, make_float2(y.x + d.x, y.y + d.y), off);
                 }
             }
         }
@@ -366,7 +387,7 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
 #pragma unroll 1
         for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
             float2 o[16];
-            ld_chunk_t(tacc, c, stage, lane, o);
+            ld_chunk_t(tacc, c, stage, lane, o, sc);
             const int n = n_tile * N_TILE + c + lp.cc;
             const float2 bias = ldg2(e.bias + n);
             const long long off0 = (row_w + lp.r0) * e.out_pitch + n, st = 2LL * e.out_pitch;
@@ -374,77 +395,77 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp)
                 if (B200_ROW_OK(rp))
-                    st_split2(make_float2(fmaxf((o[rp].x + bias.x) * e.c0, lo_clamp), fmaxf((o[rp].y + bias.y) * e.c0, lo_clamp)),
-                              e.out_hi + off0 + rp * st, e.out_lo ? e.out_lo + off0 + rp * st : nullptr);
+                    st_operand2<2>(e, make_float2(fmaxf((o[rp].x + bias.x) * e.c0, lo_clamp), fmaxf((o[rp].y + bias.y) * e.c0, lo_clamp)),
+                                off0 + rp * st);
         }
     } else if constexpr (EPI == EPI_POSTERIOR) {
-        // row-per-thread ownership: row t_warp + lane (only warp group 0 gets here: kSplit == 1)
+        // row-per-thread ownership: row t_warp + lane.  x_t lives in the reference layout [B][M][T] (T contiguous): lanes hold
+        // consecutive t, so the per-channel accesses below are coalesced.  The channels are processed in chunks of 16 with all
+        // loads of a chunk issued before the first use (one exposed DRAM latency per chunk instead of one per channel:
+        // profiles/r01_d had this epilogue at 192 us per launch); the two warps of a TMEM lane quadrant alternate chunks.
+        static_assert(N_TILE % 16 == 0 && N_TILE <= 96, "posterior epilogue expects <= 96 mel bins, a multiple of 16");
+        constexpr int M = N_TILE;
         const int t = t_warp + lane;
         const bool row_ok = FULL || t < args.L;
         const long long row = row_w + lane;
-        // N_TILE == mel bins (80).  x_t lives in the reference layout [B][M][T] (T contiguous): lanes hold
-        // consecutive t, so the per-channel accesses below are coalesced.
-        static_assert(N_TILE % 16 == 0 && N_TILE <= 96, "posterior epilogue expects <= 96 mel bins");
-        const int M = N_TILE;
-        float xnew[N_TILE];
-        {
-            float v[32];
+        const long long LL = args.L;
+        const bool eps_only = (e.flags & 1) != 0;     // bsg_diffnet_forward: write the denoiser output, reference layout
+        float* xt = e.f32_a + (static_cast<long long>(b) * M) * LL + t;
+        const float* nz = (!eps_only && e.aux0) ? e.aux0 + (static_cast<long long>(b) * M) * LL + t : nullptr;
+        const bool draw = !eps_only && nz == nullptr && e.c4 != 0.0f;   // the noise of the t == 0 step is multiplied by zero (:165)
+        const unsigned long long seed = draw ? __ldg(e.seed_ptr) : 0ull;
+        const float mask = (e.f32_b != nullptr && row_ok && e.mel2ph != nullptr && !(e.mel2ph[row] > 0)) ? 0.0f : 1.0f;
+#pragma unroll 1
+        for (int c0 = grp * 16; c0 < N_TILE; c0 += 32) {
+            float acc[16], xv[16], zv[16];
+            if (row_ok && !eps_only) {
 #pragma unroll
-            for (int c = 0; c + 32 <= N_TILE; c += 32) {
-                ld_acc32(tacc + c, v);
+                for (int i = 0; i < 16; ++i) xv[i] = xt[static_cast<long long>(c0 + i) * LL];
+                if (nz != nullptr) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) xnew[c + i] = v[i];
-            }
-            if constexpr (N_TILE % 32 != 0) {
-                float w[16];
-                ld_acc16(tacc + (N_TILE / 32) * 32, w);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) xnew[(N_TILE / 32) * 32 + i] = w[i];
-            }
-        }
-        if (row_ok && (e.flags & 1)) {
-            // eps-only mode (bsg_diffnet_forward): write the denoiser output in the reference layout [B][M][T]
-            float* eo = e.f32_a + (static_cast<long long>(b) * M) * args.L + t;
-#pragma unroll
-            for (int c = 0; c < N_TILE; ++c) eo[static_cast<long long>(c) * args.L] = xnew[c] + __ldg(e.bias + c);
-        } else if (row_ok) {
-            float* xt = e.f32_a + (static_cast<long long>(b) * M) * args.L + t;
-            const float* nz = e.aux0 ? e.aux0 + (static_cast<long long>(b) * M) * args.L + t : nullptr;
-            const unsigned long long seed = (nz == nullptr && e.c4 != 0.0f) ? __ldg(e.seed_ptr) : 0ull;
-#pragma unroll
-            for (int c4 = 0; c4 < N_TILE; c4 += 4) {
-                // one Philox4x32-10 call yields the four normals of channels c4..c4+3 at this (b, t)
-                float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (nz == nullptr && e.c4 != 0.0f)   // the noise of the t == 0 step is multiplied by zero (:165): skip drawing it
-                    z4 = philox_normal4(seed, e.step, (static_cast<uint64_t>(b) * (M / 4) + c4 / 4) * args.L + t);
-                const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int c = c4 + i;
-                    const float eps = xnew[c] + __ldg(e.bias + c);
-                    const float x = xt[static_cast<long long>(c) * args.L];
-                    float x0 = e.c0 * x - e.c1 * eps;                       // predict_start_from_noise (:134-138)
-                    x0 = fminf(fmaxf(x0, -1.0f), 1.0f);                      // clamp_ (:153-154)
-                    const float mean = e.c2 * x0 + e.c3 * x;                 // q_posterior (:140-147)
-                    const float z = nz != nullptr ? nz[static_cast<long long>(c) * args.L] : zz[i];
-                    const float xn = mean + e.c4 * z;                        // (:166), c4 = 0 at t == 0
-                    xt[static_cast<long long>(c) * args.L] = xn;
-                    xnew[c] = xn;
+                    for (int i = 0; i < 16; ++i) zv[i] = nz[static_cast<long long>(c0 + i) * LL];
                 }
             }
+            ld_acc16(tacc + c0, acc, sc);
+            if (!row_ok) continue;
+            if (eps_only) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) xt[static_cast<long long>(c0 + i) * LL] = acc[i] + __ldg(e.bias + c0 + i);
+                continue;
+            }
+            if (nz == nullptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    // one Philox4x32-10 call yields the four normals of channels c0+4q .. c0+4q+3 at this (b, t)
+                    float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (draw) z4 = philox_normal4(seed, e.step, (static_cast<uint64_t>(b) * (M / 4) + (c0 >> 2) + q) * LL + t);
+                    zv[4 * q] = z4.x; zv[4 * q + 1] = z4.y; zv[4 * q + 2] = z4.z; zv[4 * q + 3] = z4.w;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float eps = acc[i] + __ldg(e.bias + c0 + i);
+                const float x = xv[i];
+                float x0 = e.c0 * x - e.c1 * eps;                       // predict_start_from_noise (:134-138)
+                x0 = fminf(fmaxf(x0, -1.0f), 1.0f);                      // clamp_ (:153-154)
+                const float mean = e.c2 * x0 + e.c3 * x;                 // q_posterior (:140-147)
+                xv[i] = mean + e.c4 * zv[i];                             // (:166), c4 = 0 at t == 0
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xt[static_cast<long long>(c0 + i) * LL] = xv[i];
             // bf16 operand copy [B][T][M] for the next step's input projection
             if (e.out_hi != nullptr) {
-                __nv_bfloat16* hrow = e.out_hi + row * e.out_pitch;
-                __nv_bfloat16* lrow = e.out_lo ? e.out_lo + row * e.out_pitch : nullptr;
+                __nv_bfloat16* hrow = e.out_hi + row * e.out_pitch + c0;
+                __nv_bfloat16* lrow = e.out_lo ? e.out_lo + row * e.out_pitch + c0 : nullptr;
 #pragma unroll
-                for (int c = 0; c < N_TILE; c += 8) {
+                for (int c = 0; c < 16; c += 8) {
                     uint32_t ph[4], pl[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float h0, h1;
                         __nv_bfloat16 bh0, bl0, bh1, bl1;
-                        split_bf16(xnew[c + 2 * i], h0, bh0, bl0);
-                        split_bf16(xnew[c + 2 * i + 1], h1, bh1, bl1);
+                        split_bf16(xv[c + 2 * i], h0, bh0, bl0);
+                        split_bf16(xv[c + 2 * i + 1], h1, bh1, bl1);
                         ph[i] = static_cast<uint32_t>(__bfloat16_as_ushort(bh0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bh1)) << 16);
                         pl[i] = static_cast<uint32_t>(__bfloat16_as_ushort(bl0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bl1)) << 16);
                     }
@@ -454,15 +475,14 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
             }
             // last step: mel_out = denorm_spec(x) * (mel2ph > 0)   (shallow_diffusion_tts.py:268-272,278-279)
             if (e.f32_b != nullptr) {
-                const float mask = (e.mel2ph == nullptr || e.mel2ph[row] > 0) ? 1.0f : 0.0f;
-                float* mo = e.f32_b + row * M;
+                float* mo = e.f32_b + row * M + c0;
 #pragma unroll
-                for (int c = 0; c < N_TILE; c += 4) {
+                for (int c = 0; c < 16; c += 4) {
                     float o[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float mn = __ldg(e.aux1 + c + i), mx = __ldg(e.aux2 + c + i);
-                        o[i] = ((xnew[c + i] + 1.0f) / 2.0f * (mx - mn) + mn) * mask;
+                        const float mn = __ldg(e.aux1 + c0 + c + i), mx = __ldg(e.aux2 + c0 + c + i);
+                        o[i] = ((xv[c + i] + 1.0f) / 2.0f * (mx - mn) + mn) * mask;
                     }
                     *reinterpret_cast<float4*>(mo + c) = make_float4(o[0], o[1], o[2], o[3]);
                 }
@@ -487,7 +507,7 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
                     if (B200_ROW_OK(rp)) s[rp] = ld2(e.f32_b + o32 + rp * st);
             }
             float2 o[16];
-            ld_chunk_t(tacc, c, stage, lane, o);
+            ld_chunk_t(tacc, c, stage, lane, o, sc);
             const float2 bias = ldg2(e.bias + n);
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp) {
@@ -561,11 +581,13 @@ __device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int 
 // ---------------------------------------------------------------------------------------------
 template <int N_TILE, int TERMS, bool PAIR = false>
 struct GemmSmem {
-    static constexpr int kASlotRows = TERMS == 3 ? 144 : 192;                       // halo tile capacity
+    static constexpr int kAParts = TERMS == 3 ? 2 : 1;                              // activations: hi/lo only in bf16x3
+    static constexpr int kBParts = TERMS >= 2 ? 2 : 1;                              // weights: hi/lo in bf16x3 and fp16x2
+    static constexpr int kASlotRows = TERMS == 1 ? 192 : 144;                       // halo tile capacity
     static constexpr int kAPartBytes = kASlotRows * kBlockK * 2;                    // one of hi / lo
     static constexpr int kBPartBytes = (PAIR ? N_TILE / 2 : N_TILE) * kBlockK * 2;       // PAIR: each CTA stages half of the N columns
-    static constexpr int kASlotBytes = (TERMS == 3 ? 2 : 1) * kAPartBytes;
-    static constexpr int kBSlotBytes = (TERMS == 3 ? 2 : 1) * kBPartBytes;
+    static constexpr int kASlotBytes = kAParts * kAPartBytes;
+    static constexpr int kBSlotBytes = kBParts * kBPartBytes;
     static constexpr int kAStages = TERMS == 3 ? 2 : 3;
     static constexpr int kBStagesRaw = (kSmemBudget - kAStages * kASlotBytes) / kBSlotBytes;
     static constexpr int kBStages = kBStagesRaw > 6 ? 6 : kBStagesRaw;
@@ -593,7 +615,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     using S = GemmSmem<N_TILE, TERMS, PAIR>;
     static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128");
     constexpr int kTmemCols = tmem_cols_for(2 * N_TILE);
-    constexpr uint32_t kIdesc = umma_idesc_bf16(PAIR ? 2 * kTileM : kTileM, N_TILE);
+    constexpr uint32_t kIdesc = umma_idesc_f16(PAIR ? 2 * kTileM : kTileM, N_TILE, /*fp16=*/TERMS == 2);
     constexpr int kTileRows = PAIR ? 2 * kTileM : kTileM;
 
     extern __shared__ uint8_t smem_raw[];
@@ -641,7 +663,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer (one per CTA) =================
-        const uint32_t a_bytes = static_cast<uint32_t>(args.a_rows) * kBlockK * 2 * (TERMS == 3 ? 2 : 1) * (PAIR ? 2 : 1);
+        const uint32_t a_bytes = static_cast<uint32_t>(args.a_rows) * kBlockK * 2 * S::kAParts * (PAIR ? 2 : 1);
         const uint32_t b_bytes = S::kBSlotBytes * (PAIR ? 2 : 1);
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
@@ -675,11 +697,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                     if constexpr (PAIR) {
                         if (rank == 0) mbar_arrive_expect_tx(&bfull_bar[bs], b_bytes);
                         tma_load_2d_pair(sb, &args.wmap[0], &bfull_bar[bs], wc, wrow);
-                        if (TERMS == 3) tma_load_2d_pair(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
+                        if (TERMS >= 2) tma_load_2d_pair(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
                     } else {
                         mbar_arrive_expect_tx(&bfull_bar[bs], b_bytes);
                         tma_load_2d(sb, &args.wmap[0], &bfull_bar[bs], wc, wrow);
-                        if (TERMS == 3) tma_load_2d(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
+                        if (TERMS >= 2) tma_load_2d(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
                     }
                     if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
                 }
@@ -713,16 +735,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                         const uint64_t db = umma_smem_desc<128>(b_hi + k * 32);
                         if constexpr (PAIR) {
                             umma_f16_pair(tacc, da, db, kIdesc, accumulate);
-                            if (TERMS == 3) {
-                                umma_f16_pair(tacc, umma_smem_desc<128>(a_lo + k * 32), db, kIdesc, 1);
-                                umma_f16_pair(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
-                            }
+                            if (TERMS == 3) umma_f16_pair(tacc, umma_smem_desc<128>(a_lo + k * 32), db, kIdesc, 1);
+                            if (TERMS >= 2) umma_f16_pair(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
                         } else {
                             umma_f16(tacc, da, db, kIdesc, accumulate);
-                            if (TERMS == 3) {
-                                umma_f16(tacc, umma_smem_desc<128>(a_lo + k * 32), db, kIdesc, 1);
-                                umma_f16(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
-                            }
+                            if (TERMS == 3) umma_f16(tacc, umma_smem_desc<128>(a_lo + k * 32), db, kIdesc, 1);
+                            if (TERMS >= 2) umma_f16(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
                         }
                         accumulate = 1;
                     }
@@ -758,8 +776,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 const int nt = tile + n_workers;
                 if (nt < args.num_tiles) prefetch_rmw_tile<N_TILE, EPI>(args, nt, kTileRows, rank * kTileM + quad * 32, grp, lane);
             }
-            if (args.L - t_warp >= 32) run_epilogue<N_TILE, EPI, true>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
-            else run_epilogue<N_TILE, EPI, false>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
+            // the fp16x2 per-layer GEMMs (gate, residual) feed fp16x2 consumers: fp16 operand output decided at compile time
+            if (args.L - t_warp >= 32) run_epilogue<N_TILE, EPI, true, TERMS == 2>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
+            else run_epilogue<N_TILE, EPI, false, TERMS == 2>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

@@ -163,8 +163,13 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     B200_CHECK(M == 80, "this build is specialised for 80 mel bins");
     B200_CHECK(L >= 1 && c.k_step >= 1 && c.k_step <= c.timesteps, "bad layer/step counts");
     B200_CHECK(c.dilation_cycle >= 1 && (1 << (c.dilation_cycle - 1)) * 2 + kTileM <= kXaBoxRows, "dilation cycle too long for the halo tile");
-    B200_CHECK(c.precision == BSG_PRECISION_BF16 || c.precision == BSG_PRECISION_BF16X3, "bad precision");
-    terms = c.precision == BSG_PRECISION_BF16X3 ? 3 : 1;
+    B200_CHECK(c.precision == BSG_PRECISION_BF16 || c.precision == BSG_PRECISION_BF16X3 || c.precision == BSG_PRECISION_FP16X2,
+               "bad precision");
+    // terms: the per-layer GEMMs (gate, residual, skip sum); terms_side: the once-per-step / once-per-batch GEMMs
+    // (conditioner projection, input projection, skip_projection, output_projection), which stay bf16x3 in fp16x2 mode
+    terms = c.precision == BSG_PRECISION_BF16X3 ? 3 : (c.precision == BSG_PRECISION_FP16X2 ? 2 : 1);
+    terms_side = terms == 2 ? 3 : terms;
+    const bool f16 = terms == 2;
     const size_t expect = static_cast<size_t>(C) * M + C + 4 * C * C + 4 * C + 4 * C * C + C +
                           static_cast<size_t>(L) * (2 * C * C * 3 + 2 * C + C * C + C + 2 * C * H + 2 * C + 2 * C * C + 2 * C) +
                           static_cast<size_t>(C) * C + C + static_cast<size_t>(M) * C + M;
@@ -209,11 +214,11 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
                     for (int ci = 0; ci < H; ++ci) gc[static_cast<size_t>(dst) * H + ci] = wc[static_cast<size_t>(src) * H + ci];
                     gb[dst] = bdil[src] + bc[src];
                 }
-        layers[l].g1.pack(g1, 2 * C, K1);
+        layers[l].g1.pack(g1, 2 * C, K1, f16);
         layers[l].gc.pack(gc, 2 * C, H);
         upload(layers[l].g1_bias, gb);
         // output projection: first half of the output channels = residual, second half = skip (net.py:77)
-        layers[l].g2.pack(std::vector<float>(wo.begin(), wo.begin() + static_cast<size_t>(C) * C), C, C);
+        layers[l].g2.pack(std::vector<float>(wo.begin(), wo.begin() + static_cast<size_t>(C) * C), C, C, f16);
         upload(layers[l].g2_bias, std::vector<float>(bo.begin(), bo.begin() + C));
         for (int o = 0; o < C; ++o) {
             for (int ci = 0; ci < C; ++ci) skip_w[static_cast<size_t>(o) * L * C + static_cast<size_t>(l) * C + ci] = wo[static_cast<size_t>(C + o) * C + ci];
@@ -227,7 +232,7 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     auto b_out = take(p, M);
     inproj.pack(w_in, C, M);
     upload(inproj_bias, b_in);
-    skipall.pack(skip_w, C, L * C);
+    skipall.pack(skip_w, C, L * C, f16);
     upload(skipall_bias, skip_b);
     skipproj.pack(w_skip, C, C);
     upload(skipproj_bias, b_skip);
@@ -262,8 +267,9 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
 
     // set the dynamic-smem attribute of every instantiation outside of any stream capture
     ConvGemmArgs none{};
-    for (int epi : {EPI_F32, EPI_INPROJ, EPI_GATE, EPI_RES_SKIP, EPI_RELU_BF16}) launch_conv_gemm(256, terms, epi, none, nullptr);
-    launch_conv_gemm(80, terms, EPI_POSTERIOR, none, nullptr);
+    for (int epi : {EPI_F32, EPI_INPROJ, EPI_RELU_BF16}) launch_conv_gemm(256, terms_side, epi, none, nullptr);
+    launch_conv_gemm(80, terms_side, EPI_POSTERIOR, none, nullptr);
+    launch_conv_gemm(256, terms, EPI_GATE, none, nullptr);
     launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, none, nullptr);
     launch_conv_gemm(kResTile, terms, EPI_RELU_BF16, none, nullptr);
     if (const char* np = std::getenv("BSG_NO_PAIR")) use_pair = !(np[0] == '1');
@@ -284,7 +290,7 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
     const size_t rows = static_cast<size_t>(B) * T;
     w->B = B;
     w->T = T;
-    const bool lo = terms == 3;
+    const bool lo = terms == 3, lo_side = terms_side == 3;
     w->xt.alloc(rows * M * 4);
     w->eps.alloc(rows * M * 4);
     w->xin_hi.alloc(rows * M * 2);
@@ -298,16 +304,18 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
     w->mel2ph.alloc(rows * 8);
     w->cp.alloc(static_cast<size_t>(cfg.residual_layers) * rows * 2 * C * 4);
     if (lo) {
-        w->xin_lo.alloc(rows * M * 2);
-        w->cond_lo.alloc(rows * H * 2);
         w->xa_lo.alloc(rows * C * 2);
         w->z_lo.alloc(rows * cfg.residual_layers * C * 2);
+    }
+    if (lo_side) {
+        w->xin_lo.alloc(rows * M * 2);
+        w->cond_lo.alloc(rows * H * 2);
         w->s_lo.alloc(rows * C * 2);
         w->h_lo.alloc(rows * C * 2);
     }
     auto mk = [&](CUtensorMap (&m)[2], const DevBuf& hi, const DevBuf& lo_, int ch, int box_rows = kTileM) {
         m[0] = make_act_tmap(hi.p, B, T, ch, 0, box_rows);
-        m[1] = lo ? make_act_tmap(lo_.p, B, T, ch, 0, box_rows) : m[0];
+        m[1] = lo_.p ? make_act_tmap(lo_.p, B, T, ch, 0, box_rows) : m[0];
     };
     mk(w->m_xin, w->xin_hi, w->xin_lo, M);
     mk(w->m_cond, w->cond_hi, w->cond_lo, H);
@@ -320,7 +328,10 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
     return ref;
 }
 
-static void set_w(ConvGemmArgs& a, PackedW& w, int n_tile) { w.maps(n_tile, a.wmap[0], a.wmap[1]); }
+static void set_w(ConvGemmArgs& a, PackedW& w, int n_tile) {
+    w.maps(n_tile, a.wmap[0], a.wmap[1]);
+    a.epi.acc_scale = w.acc_scale;
+}
 
 
 // cp[l] = conditioner_projection_l(cond) + its bias + the dilated conv's bias (net.py:68,71), all layers, once per call
@@ -336,7 +347,7 @@ void DiffusionPlan::precompute_cond(Workspace& w, cudaStream_t st) {
         a.epi.bias = ly.g1_bias.as<float>();
         a.epi.f32_a = w.cp.as<float>() + static_cast<size_t>(l) * w.B * w.T * 2 * C;
         a.epi.out_pitch = 2 * C;
-        launch_conv_gemm(256, terms, EPI_F32, a, st);
+        launch_conv_gemm(256, terms_side, EPI_F32, a, st);
         ++launches, ++g_launch_count;
     }
 }
@@ -356,6 +367,7 @@ ConvGemmArgs DiffusionPlan::gate_args(Workspace& w, int l) {
     (void)H;
     a.epi.out_hi = w.z_hi.as<__nv_bfloat16>();
     a.epi.out_lo = terms == 3 ? w.z_lo.as<__nv_bfloat16>() : nullptr;
+    a.epi.out_fp16 = terms == 2;
     a.epi.out_pitch = 2 * C;                         // pitch of the conditioner-projection rows (aux0)
     a.epi.act_pitch = cfg.residual_layers * C;       // pitch of the all-layer z matrix
     a.epi.out_col0 = l * C;
@@ -375,15 +387,35 @@ ConvGemmArgs DiffusionPlan::resskip_args(Workspace& w, int l, const float* lut_t
     a.epi.bias = ly.g2_bias.as<float>();
     a.epi.f32_a = w.xres.as<float>();
     a.epi.out_hi = w.xa_hi.as<__nv_bfloat16>(); a.epi.out_lo = lo ? w.xa_lo.as<__nv_bfloat16>() : nullptr;
+    a.epi.out_fp16 = terms == 2;
     a.epi.dvec = (l + 1 < L) ? lut_t + static_cast<size_t>(l + 1) * C : nullptr;
     a.epi.out_pitch = C;
     return a;
 }
 
+// skip sum of all layers as one K = L*C GEMM over the step's z matrix (net.py:77-78,126), / sqrt(L), -> s (bf16 hi/lo)
+ConvGemmArgs DiffusionPlan::skipsum_args(Workspace& w) {
+    const int C = cfg.residual_channels, L = cfg.residual_layers;
+    ConvGemmArgs a{};
+    const int nt = use_pair ? kSkipTilePair : kResTile;
+    set_geometry(a, w.B, w.T, C, nt, use_pair);
+    a.amap[0] = w.m_z[0]; a.amap[1] = w.m_z[1];
+    set_w(a, skipall, use_pair ? nt / 2 : nt);
+    set_taps(a, 0, 0, L * C / kBlockK, kOneTap, 1, 0);
+    a.epi.bias = skipall_bias.as<float>();
+    a.epi.out_hi = w.s_hi.as<__nv_bfloat16>();
+    a.epi.out_lo = w.s_lo.p ? w.s_lo.as<__nv_bfloat16>() : nullptr;
+    a.epi.out_pitch = C;
+    a.epi.flags = 1;                                        // no ReLU
+    a.epi.c0 = 1.0f / std::sqrt(static_cast<float>(L));
+    return a;
+}
+
 // Average duration of one hot kernel, measured with CUDA events on `st`: `reps` back-to-back launches cycling through
-// the layers (so weights change from launch to launch as in a real step).  which: 0 = gate GEMM, 1 = residual/skip GEMM.
+// the layers (so weights change from launch to launch as in a real step).  which: 0 = gate GEMM, 1 = residual GEMM,
+// 2 = skip-sum GEMM.
 float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t st) {
-    B200_CHECK(which == 0 || which == 1, "unknown kernel id");
+    B200_CHECK(which >= 0 && which <= 2, "unknown kernel id");
     B200_CHECK(reps > 0, "reps must be positive");
     B200_CUDA(cudaSetDevice(device));
     Workspace& w = workspace(B, T);
@@ -395,7 +427,8 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
         for (int i = 0; i < n; ++i) {
             const int l = i % L;
             if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, use_pair);
-            else launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
+            else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
+            else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, use_pair);
             ++launches, ++g_launch_count;
         }
     };
@@ -417,9 +450,8 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
                                  cudaStream_t st) {
     const int M = cfg.in_dims, H = cfg.hidden_size, C = cfg.residual_channels, L = cfg.residual_layers;
     const int B = w.B, T = w.T;
-    const bool lo = terms == 3;
     const float* lut_t = lut.as<float>() + static_cast<size_t>(t) * L * C;
-    auto nz = [&](const DevBuf& b) { return lo ? b.as<__nv_bfloat16>() : nullptr; };
+    auto nz = [&](const DevBuf& b) { return b.p ? b.as<__nv_bfloat16>() : nullptr; };
 
     {   // input projection + ReLU (net.py:116-118); writes x and (x + d_0)
         ConvGemmArgs a{};
@@ -430,9 +462,10 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         a.epi.bias = inproj_bias.as<float>();
         a.epi.f32_a = w.xres.as<float>();
         a.epi.out_hi = w.xa_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.xa_lo);
+        a.epi.out_fp16 = terms == 2;
         a.epi.dvec = lut_t;
         a.epi.out_pitch = C;
-        launch_conv_gemm(256, terms, EPI_INPROJ, a, st);
+        launch_conv_gemm(256, terms_side, EPI_INPROJ, a, st);
         ++launches, ++g_launch_count;
     }
     for (int l = 0; l < L; ++l) {
@@ -442,18 +475,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         ++launches, ++g_launch_count;
     }
     {   // skip sum: sum_l (W_skip,l z_l + b_skip,l) / sqrt(L)  (net.py:77-78,126) as one K = L*C GEMM over the step's z matrix
-        ConvGemmArgs a{};
-        const int nt = use_pair ? kSkipTilePair : kResTile;
-        set_geometry(a, B, T, C, nt, use_pair);
-        a.amap[0] = w.m_z[0]; a.amap[1] = w.m_z[1];
-        set_w(a, skipall, use_pair ? nt / 2 : nt);
-        set_taps(a, 0, 0, L * C / kBlockK, kOneTap, 1, 0);
-        a.epi.bias = skipall_bias.as<float>();
-        a.epi.out_hi = w.s_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.s_lo);
-        a.epi.out_pitch = C;
-        a.epi.flags = 1;                                        // no ReLU
-        a.epi.c0 = 1.0f / std::sqrt(static_cast<float>(L));
-        launch_conv_gemm(nt, terms, EPI_RELU_BF16, a, st, use_pair);
+        launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, use_pair);
         ++launches, ++g_launch_count;
     }
     {   // skip_projection + ReLU (net.py:127-128)
@@ -466,7 +488,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         a.epi.out_hi = w.h_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.h_lo);
         a.epi.out_pitch = C;
         a.epi.c0 = 1.0f;
-        launch_conv_gemm(256, terms, EPI_RELU_BF16, a, st);
+        launch_conv_gemm(256, terms_side, EPI_RELU_BF16, a, st);
         ++launches, ++g_launch_count;
     }
     {   // output_projection (net.py:129) fused with the DDPM posterior update (shallow_diffusion_tts.py:149-166)
@@ -494,7 +516,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
             a.epi.step = static_cast<unsigned>(k_exec);
         }
         a.epi.out_pitch = M;
-        launch_conv_gemm(80, terms, EPI_POSTERIOR, a, st);
+        launch_conv_gemm(80, terms_side, EPI_POSTERIOR, a, st);
         ++launches, ++g_launch_count;
     }
 }
@@ -508,7 +530,7 @@ void DiffusionPlan::sample(const float* cond, const float* fs2_mel, const float*
     Workspace& w = workspace(B, T);
     const int M = cfg.in_dims, H = cfg.hidden_size, K = cfg.k_step;
     const size_t rows = static_cast<size_t>(B) * T;
-    const bool lo = terms == 3;
+    const bool lo = terms_side == 3;
 
     B200_CUDA(cudaMemcpyAsync(d_seed.p, &seed, sizeof(seed), cudaMemcpyHostToDevice, st));
     {
@@ -575,7 +597,7 @@ void DiffusionPlan::denoise(const float* spec, int t, const float* cond, int B, 
     Workspace& w = workspace(B, T);
     const int M = cfg.in_dims, H = cfg.hidden_size;
     const size_t rows = static_cast<size_t>(B) * T;
-    const bool lo = terms == 3;
+    const bool lo = terms_side == 3;
     const size_t n = rows * H;
     split_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256 + 1), 256, 0, st>>>(cond, w.cond_hi.as<__nv_bfloat16>(),
                                                                                 lo ? w.cond_lo.as<__nv_bfloat16>() : nullptr, n);

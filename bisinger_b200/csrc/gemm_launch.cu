@@ -100,6 +100,7 @@ void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, 
     B200_CASE(256, 1, EPI_F32) B200_CASE(256, 3, EPI_F32) B200_CASE(128, 1, EPI_F32) B200_CASE(128, 3, EPI_F32)
     B200_CASE(64, 1, EPI_F32) B200_CASE(32, 1, EPI_F32)
     B200_PAIR(256, 1, EPI_F32) B200_PAIR(256, 3, EPI_F32) B200_PAIR(128, 3, EPI_F32)
+    B200_CASE(256, 2, EPI_F32) B200_CASE(128, 2, EPI_F32) B200_PAIR(256, 2, EPI_F32) B200_PAIR(128, 2, EPI_F32)
     // DiffNet
     B200_CASE(256, 1, EPI_INPROJ) B200_CASE(256, 3, EPI_INPROJ)
     B200_CASE(256, 1, EPI_GATE) B200_CASE(256, 3, EPI_GATE) B200_PAIR(256, 1, EPI_GATE) B200_PAIR(256, 3, EPI_GATE)
@@ -107,6 +108,9 @@ void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, 
     B200_CASE(256, 1, EPI_RELU_BF16) B200_CASE(256, 3, EPI_RELU_BF16) B200_CASE(128, 1, EPI_RELU_BF16) B200_CASE(128, 3, EPI_RELU_BF16)
     B200_PAIR(256, 1, EPI_RELU_BF16) B200_PAIR(256, 3, EPI_RELU_BF16) B200_PAIR(128, 1, EPI_RELU_BF16) B200_PAIR(128, 3, EPI_RELU_BF16)
     B200_CASE(80, 1, EPI_POSTERIOR) B200_CASE(80, 3, EPI_POSTERIOR)
+    // DiffNet, fp16x2 per-layer GEMMs
+    B200_CASE(256, 2, EPI_GATE) B200_PAIR(256, 2, EPI_GATE) B200_CASE(128, 2, EPI_RES_SKIP)
+    B200_CASE(128, 2, EPI_RELU_BF16) B200_PAIR(256, 2, EPI_RELU_BF16)
     // HiFi-GAN
     B200_CASE(256, 1, EPI_BIAS_ACT) B200_CASE(128, 1, EPI_BIAS_ACT) B200_CASE(64, 1, EPI_BIAS_ACT) B200_CASE(32, 1, EPI_BIAS_ACT)
     throw Error("conv_gemm: no instantiation for n_tile=" + std::to_string(n_tile) + " terms=" + std::to_string(terms) +

@@ -25,7 +25,8 @@ public:
 
     bsg_diffnet_config cfg;
     int device;
-    int terms = 1;
+    int terms = 1;        // MMAs per product of the per-layer GEMMs: 1 bf16, 2 fp16x2, 3 bf16x3
+    int terms_side = 1;   // same for the once-per-step GEMMs (bf16x3 in fp16x2 mode)
     bool use_graphs = true;
     bool use_pair = true;    // 2-CTA (cta_group::2) tiles for the tensor-bound GEMMs (gate GEMM, skip-sum GEMM)
     unsigned long long launches = 0;
@@ -44,6 +45,7 @@ private:
     void precompute_cond(Workspace& w, cudaStream_t st);
     ConvGemmArgs gate_args(Workspace& w, int l);
     ConvGemmArgs resskip_args(Workspace& w, int l, const float* lut_t);
+    ConvGemmArgs skipsum_args(Workspace& w);
     void enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail, cudaStream_t st);
 
     std::vector<Layer> layers;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace b200 {
 
@@ -199,14 +200,15 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
     d |= layout << 61;                                              // swizzle mode   [61,64)
     return d;
 }
-// Instruction descriptor for kind::f16: A,B bf16 (K-major), D fp32, M x N tile.
-__device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4)                 // D format: f32
-           | (1u << 7)               // A format: bf16
-           | (1u << 10)              // B format: bf16
-           | (0u << 15) | (0u << 16) // A, B K-major
+// Instruction descriptor for kind::f16: A,B bf16 or fp16 (K-major), D fp32, M x N tile.
+__device__ __forceinline__ constexpr uint32_t umma_idesc_f16(int M, int N, bool fp16) {
+    return (1u << 4)                           // D format: f32
+           | ((fp16 ? 0u : 1u) << 7)           // A format: 0 = fp16, 1 = bf16
+           | ((fp16 ? 0u : 1u) << 10)          // B format
+           | (0u << 15) | (0u << 16)           // A, B K-major
            | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
+__device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N) { return umma_idesc_f16(M, N, false); }
 
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

@@ -2,8 +2,10 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -143,10 +145,22 @@ inline int set_taps(ConvGemmArgs& a, int a_src, int a_col0, int n_kb, const int*
 }
 inline int halo_rows(int span) { return ((kTileM + span) + 7) / 8 * 8; }
 
-// Packed bf16 (hi, lo) weight matrix on the device
+// round-to-nearest-even fp32 -> fp16 on the host (packer)
+inline uint16_t f32_to_f16_bits(float f) {
+    const __half_raw r = static_cast<__half_raw>(__float2half_rn(f));
+    return r.x;
+}
+inline float f16_bits_to_f32(uint16_t b) {
+    __half_raw r;
+    r.x = b;
+    return __half2float(__half(r));
+}
+
+// Packed (hi, lo) weight matrix on the device: bf16 pair (bf16 / bf16x3 modes) or fp16 pair pre-scaled by 2^p (fp16x2)
 struct PackedW {
     DevBuf hi, lo;
     int N = 0, K = 0;
+    float acc_scale = 1.0f;   // 2^-p: what the epilogue multiplies the accumulators with
     CUtensorMap tm[2];     // cached TMA descriptors (hi, lo) for box = 64 x tm_ntile
     int tm_ntile = 0;
     void maps(int n_tile, CUtensorMap& mhi, CUtensorMap& mlo) {
@@ -159,13 +173,34 @@ struct PackedW {
         mlo = tm[1];
     }
     // w: row-major [N][K] fp32 on the host
-    void pack(const std::vector<float>& w, int n, int k) {
+    void pack(const std::vector<float>& w, int n, int k, bool fp16 = false) {
         N = n;
         K = k;
+        tm_ntile = 0;
         std::vector<uint16_t> h(w.size()), l(w.size());
-        for (size_t i = 0; i < w.size(); ++i) {
-            h[i] = f32_to_bf16_bits(w[i]);
-            l[i] = f32_to_bf16_bits(w[i] - bf16_bits_to_f32(h[i]));
+        if (!fp16) {
+            acc_scale = 1.0f;
+            for (size_t i = 0; i < w.size(); ++i) {
+                h[i] = f32_to_bf16_bits(w[i]);
+                l[i] = f32_to_bf16_bits(w[i] - bf16_bits_to_f32(h[i]));
+            }
+        } else {
+            // hi = fp16(w * 2^p), lo = fp16(w * 2^p - hi) with the largest |w| * 2^p in [8192, 16384): the low parts of all but the
+            // tiniest weights are normal fp16 numbers (a subnormal lo would lose its mantissa bits)
+            float mx = 0.0f;
+            for (float v : w) mx = std::fmax(mx, std::fabs(v));
+            int p = 0;
+            if (mx > 0.0f && std::isfinite(mx)) {
+                p = 13 - static_cast<int>(std::floor(std::log2(mx)));
+                p = p < -14 ? -14 : (p > 24 ? 24 : p);
+            }
+            const float up = std::ldexp(1.0f, p);
+            acc_scale = std::ldexp(1.0f, -p);
+            for (size_t i = 0; i < w.size(); ++i) {
+                const float v = w[i] * up;
+                h[i] = f32_to_f16_bits(v);
+                l[i] = f32_to_f16_bits(v - f16_bits_to_f32(h[i]));
+            }
         }
         upload(hi, h);
         upload(lo, l);

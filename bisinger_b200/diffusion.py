@@ -99,7 +99,7 @@ class B200DiffNet(nn.Module):
         """spec [B,1,M,T], diffusion_step [B] (all equal, as the sampler passes it, shallow_diffusion_tts.py:267),
         cond [B,H,T] -> [B,1,M,T]."""
         if self._standalone_plan is None:
-            self._standalone_plan = DiffusionPlan(self, precision="bf16x3")
+            self._standalone_plan = DiffusionPlan(self, precision=_lib.DEFAULT_PRECISION)
         t = int(diffusion_step.reshape(-1)[0].item())
         if not bool((diffusion_step == t).all()):
             raise RuntimeError("B200DiffNet: all batch rows must share one diffusion step (as in p_sample)")
@@ -110,7 +110,7 @@ class DiffusionPlan:
     """Owner of one ``bsg_diffusion_plan`` handle."""
 
     def __init__(self, denoise_fn: B200DiffNet, sched: Optional[dict] = None, timesteps: Optional[int] = None,
-                 K_step: Optional[int] = None, spec_min=None, spec_max=None, precision: str = "bf16x3",
+                 K_step: Optional[int] = None, spec_min=None, spec_max=None, precision: str = _lib.DEFAULT_PRECISION,
                  device: Optional[torch.device] = None):
         L = _lib.lib()
         if device is None:
@@ -233,7 +233,7 @@ class B200GaussianDiffusion(nn.Module):
 
     def __init__(self, phone_encoder, out_dims, denoise_fn, timesteps=1000, K_step=1000, loss_type="l1", betas=None,
                  spec_min=None, spec_max=None, fs2: Optional[nn.Module] = None, hparams: Optional[dict] = None,
-                 precision: str = "bf16x3"):
+                 precision: str = _lib.DEFAULT_PRECISION):
         super().__init__()
         hp = _hp(hparams)
         self.hparams = hp

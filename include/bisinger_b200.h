@@ -37,6 +37,8 @@ extern "C" {
 /* contraction precision of the tensor-core GEMMs */
 #define BSG_PRECISION_BF16 0   /* bf16 operands, fp32 accumulate                                   */
 #define BSG_PRECISION_BF16X3 1 /* bf16 hi/lo split operands, 3 MMAs per product, fp32 accumulate   */
+#define BSG_PRECISION_FP16X2 2 /* fp16 activations x fp16 hi/lo split weights, 2 MMAs per product, fp32 accumulate (per-layer
+                                  GEMMs of the sampler; its once-per-step GEMMs run BF16X3)       */
 
 typedef struct bsg_diffusion_plan bsg_diffusion_plan;
 typedef struct bsg_hifigan_plan bsg_hifigan_plan;
@@ -109,7 +111,8 @@ int bsg_diffnet_forward(bsg_diffusion_plan* plan, const float* spec, int t, cons
 /* Measurement hook for bench.py's roofline line: average duration (ms, CUDA events on `stream`) of `reps` back-to-back
  * launches of one hot kernel at batch shape (B, T), cycling through the residual layers.
  *   which = 0: dilated-conv + conditioner GEMM with the sigmoid*tanh gate epilogue (net.py:67-74)
- *   which = 1: output-projection GEMM with the residual / skip epilogue (net.py:76-78)
+ *   which = 1: residual half of the output-projection GEMM with the residual epilogue (net.py:76-78)
+ *   which = 2: skip halves of all layers' output projections as one K = L*C GEMM (net.py:77-78,126)
  * The kernels run on the plan's workspace (whatever the last sample left there); results are discarded.       */
 int bsg_diffusion_time_kernel(bsg_diffusion_plan* plan, int which, int B, int T, int reps, float* avg_ms, void* stream);
 

@@ -21,6 +21,7 @@ Every function cites the reference file:line it follows; paths are relative to
 Optional ``operand`` argument: None = exact fp32 (the oracle proper).  "bf16"/"fp16"
 rounds the *operands* of every contraction to that type and accumulates in fp32 -- a model
 of what a tensor-core path computes, used by tests to tell precision effects from bugs.
+"fp16x2" models the sampler's default mode: fp16 activations x fp16 hi/lo-split weights.
 """
 from __future__ import annotations
 
@@ -36,10 +37,28 @@ LRELU_SLOPE = 0.1  # modules/hifigan/hifigan.py:11
 
 
 def _rnd(x: Tensor, operand: Optional[str]) -> Tensor:
+    """Activation operand of a contraction as the emulated tensor-core path sees it."""
     if operand is None:
         return x
-    dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[operand]
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp16x2": torch.float16}[operand]
     return x.to(dt).to(torch.float32)
+
+
+def _rnd_side(x: Tensor, operand: Optional[str]) -> Tensor:
+    """Activation operand of the once-per-step / once-per-batch GEMMs (conditioner projection, input projection,
+    skip_projection, output_projection): the "fp16x2" mode runs those as bf16x3 (~16 bits, modelled as hi + lo)."""
+    if operand == "fp16x2":
+        hi = x.to(torch.bfloat16).to(torch.float32)
+        return hi + (x - hi).to(torch.bfloat16).to(torch.float32)
+    return _rnd(x, operand)
+
+
+def _rnd_w(w: Tensor, operand: Optional[str]) -> Tensor:
+    """Weight operand: "fp16x2" carries weights as an fp16 hi/lo pair (~21 bits), modelled as hi + lo."""
+    if operand == "fp16x2":
+        hi = w.to(torch.float16).to(torch.float32)
+        return hi + (w - hi).to(torch.float16).to(torch.float32)
+    return _rnd(w, operand)
 
 
 # --------------------------------------------------------------------------------------
@@ -79,14 +98,14 @@ def residual_block(p: Dict[str, Tensor], i: int, dilation: int, x: Tensor, cond:
     """usr/diff/net.py:66-78.  x [B,C,T], cond [B,H,T], step [B,C] -> (x', skip)."""
     pre = f"residual_layers.{i}."
     d = F.linear(step, p[pre + "diffusion_projection.weight"], p[pre + "diffusion_projection.bias"])
-    c = F.conv1d(_rnd(cond, operand), _rnd(p[pre + "conditioner_projection.weight"], operand),
+    c = F.conv1d(_rnd_side(cond, operand), _rnd_w(p[pre + "conditioner_projection.weight"], operand),
                  p[pre + "conditioner_projection.bias"])
     y = x + d[:, :, None]
-    y = F.conv1d(_rnd(y, operand), _rnd(p[pre + "dilated_conv.weight"], operand),
+    y = F.conv1d(_rnd(y, operand), _rnd_w(p[pre + "dilated_conv.weight"], operand),
                  p[pre + "dilated_conv.bias"], padding=dilation, dilation=dilation) + c
     gate, filt = torch.chunk(y, 2, dim=1)
     y = torch.sigmoid(gate) * torch.tanh(filt)
-    y = F.conv1d(_rnd(y, operand), _rnd(p[pre + "output_projection.weight"], operand),
+    y = F.conv1d(_rnd(y, operand), _rnd_w(p[pre + "output_projection.weight"], operand),
                  p[pre + "output_projection.bias"])
     residual, skip = torch.chunk(y, 2, dim=1)
     return (x + residual) / math.sqrt(2.0), skip
@@ -98,7 +117,7 @@ def diffnet_forward(p: Dict[str, Tensor], spec: Tensor, t: Tensor, cond: Tensor,
     C = p["input_projection.weight"].shape[0]
     L = n_residual_layers(p)
     x = spec[:, 0]
-    x = F.conv1d(_rnd(x, operand), _rnd(p["input_projection.weight"], operand), p["input_projection.bias"])
+    x = F.conv1d(_rnd_side(x, operand), _rnd_w(p["input_projection.weight"], operand), p["input_projection.bias"])
     x = F.relu(x)
     step = step_embedding(p, t, C)
     skip_sum = None
@@ -106,9 +125,9 @@ def diffnet_forward(p: Dict[str, Tensor], spec: Tensor, t: Tensor, cond: Tensor,
         x, s = residual_block(p, i, 2 ** (i % dilation_cycle), x, cond, step, operand)
         skip_sum = s if skip_sum is None else skip_sum + s
     x = skip_sum / math.sqrt(L)
-    x = F.conv1d(_rnd(x, operand), _rnd(p["skip_projection.weight"], operand), p["skip_projection.bias"])
+    x = F.conv1d(_rnd_side(x, operand), _rnd_w(p["skip_projection.weight"], operand), p["skip_projection.bias"])
     x = F.relu(x)
-    x = F.conv1d(_rnd(x, operand), _rnd(p["output_projection.weight"], operand), p["output_projection.bias"])
+    x = F.conv1d(_rnd_side(x, operand), _rnd_w(p["output_projection.weight"], operand), p["output_projection.bias"])
     return x[:, None]
 
 
@@ -267,10 +286,10 @@ def resblock1(p: Dict[str, Tensor], pre: str, x: Tensor, k: int, dilations: Sequ
     """ResBlock1.forward, hifigan.py:54-61."""
     for m, d in enumerate(dilations):
         xt = F.leaky_relu(x, LRELU_SLOPE)
-        xt = F.conv1d(_rnd(xt, operand), _rnd(p[f"{pre}convs1.{m}.weight"], operand), p[f"{pre}convs1.{m}.bias"],
+        xt = F.conv1d(_rnd(xt, operand), _rnd_w(p[f"{pre}convs1.{m}.weight"], operand), p[f"{pre}convs1.{m}.bias"],
                       dilation=d, padding=(k * d - d) // 2)
         xt = F.leaky_relu(xt, LRELU_SLOPE)
-        xt = F.conv1d(_rnd(xt, operand), _rnd(p[f"{pre}convs2.{m}.weight"], operand), p[f"{pre}convs2.{m}.bias"],
+        xt = F.conv1d(_rnd(xt, operand), _rnd_w(p[f"{pre}convs2.{m}.weight"], operand), p[f"{pre}convs2.{m}.bias"],
                       dilation=1, padding=(k - 1) // 2)
         x = xt + x
     return x
@@ -288,10 +307,10 @@ def hifigan_forward(p: Dict[str, Tensor], h: dict, mel: Tensor, f0: Optional[Ten
     har = None
     if f0 is not None:
         har = nsf_source(p, f0, hop, rand_ini, src_noise, h["audio_sample_rate"])
-    x = F.conv1d(_rnd(mel, operand), _rnd(p["conv_pre.weight"], operand), p["conv_pre.bias"], padding=3)
+    x = F.conv1d(_rnd(mel, operand), _rnd_w(p["conv_pre.weight"], operand), p["conv_pre.bias"], padding=3)
     for i, (u, k) in enumerate(zip(rates, ksz)):
         x = F.leaky_relu(x, LRELU_SLOPE)
-        x = F.conv_transpose1d(_rnd(x, operand), _rnd(p[f"ups.{i}.weight"], operand), p[f"ups.{i}.bias"],
+        x = F.conv_transpose1d(_rnd(x, operand), _rnd_w(p[f"ups.{i}.weight"], operand), p[f"ups.{i}.bias"],
                                stride=u, padding=(k - u) // 2)
         if har is not None:
             if i + 1 < len(rates):

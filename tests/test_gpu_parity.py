@@ -24,14 +24,15 @@ def dev():
     return torch.device("cuda", 0)
 
 
-@pytest.fixture(scope="module")
-def diff(dev):
+# fp16x2 is the default contraction mode of the sampler, bf16x3 the alternative; both must meet the north-star tolerance
+@pytest.fixture(scope="module", params=["fp16x2", "bf16x3"])
+def diff(dev, request):
     from bisinger_b200 import B200DiffNet, DiffusionPlan
     sd = synth.diffnet_state(1234)
     net = B200DiffNet(80)
     net.load_state_dict(sd, strict=True)
     sched = O.schedule_buffers(O.linear_beta_schedule(K_STEP, MAX_BETA))
-    plan = DiffusionPlan(net, sched, K_STEP, K_STEP, synth.SPEC_MIN, synth.SPEC_MAX, precision="bf16x3", device=dev)
+    plan = DiffusionPlan(net, sched, K_STEP, K_STEP, synth.SPEC_MIN, synth.SPEC_MAX, precision=request.param, device=dev)
     return sd, sched, plan
 
 
@@ -62,6 +63,9 @@ def _conv_ref(a, w, bias, shifts):
     (2, 300, 256, 512, [-8, 0, 8], 256, 1), (3, 77, 80, 256, [0], 256, 1), (2, 200, 64, 64, [-1, 0, 1], 64, 0),
     (2, 200, 32, 32, [-3, 0, 3], 32, 0), (1, 1, 64, 128, [0], 128, 0), (1, 129, 64, 128, [-25, 0, 25], 128, 0),
     (1, 1000, 128, 128, [-5, -4, -3, -2, -1, 0, 1, 2, 3, 4, 5], 128, 0),
+    (2, 300, 256, 512, [-8, 0, 8], 256, 2), (1, 1875, 256, 256, [0], 128, 2), (3, 77, 256, 256, [-1, 0, 1], 256, 2),
+    (2, 300, 256, 512, [-8, 0, 8], 256, 2 | 0x100), (4, 1000, 512, 256, [0], 256, 2 | 0x100),          # fp16x2, also on 2-CTA tiles
+    (2, 300, 256, 512, [-2, 0, 2], 256, 1 | 0x100), (1, 1875, 256, 256, [0], 128, 1 | 0x100),          # bf16x3 on 2-CTA tiles
 ])
 def test_conv_kernel_selftest(dev, case):
     """The tcgen05 implicit-GEMM kernel alone: taps as row shifts with zero padding, ragged L, channel tails (80, 32)."""
@@ -75,8 +79,11 @@ def test_conv_kernel_selftest(dev, case):
     sh = (C.c_int * len(shifts))(*shifts)
     _lib.check(_lib.lib().bsg_selftest_conv(_lib.dev_ptr(a), _lib.fptr(w), _lib.fptr(bias), B, L, Cin, N, len(shifts), sh, n_tile, prec,
                                             _lib.dev_ptr(out), None))
-    if prec == 0:   # bf16 operands: compare with the exactly-rounded operands (fp32 accumulate => ~1e-6)
+    if prec & 0xff == 0:   # bf16 operands: compare with the exactly-rounded operands (fp32 accumulate => ~1e-6)
         ref = _conv_ref(a.bfloat16().float(), w.bfloat16().float().to(dev), bias.to(dev), shifts)
+        tol = 2e-5
+    elif prec & 0xff == 2:  # fp16x2: fp16 activations (exactly-rounded reference) x ~21-bit split weights
+        ref = _conv_ref(a.half().float(), w.to(dev), bias.to(dev), shifts)
         tol = 2e-5
     else:           # bf16x3: ~16 mantissa bits against the unrounded operands
         ref = _conv_ref(a, w.to(dev), bias.to(dev), shifts)
@@ -90,7 +97,8 @@ def test_diffnet_forward_vs_golden(golden, diff, dev, i):
     c = EPS_CASES[i]
     inp = synth.kernel_inputs(c["seed"], c["B"], c["T"], 1)
     eps = plan.denoise(inp["start_noise"].to(dev), c["t"], inp["cond"].to(dev)).cpu().numpy()
-    assert np.abs(eps - golden[f"eps.{i}"]).max() < 5e-4     # single evaluation, eps rms ~0.9
+    # single evaluation, eps rms ~0.9; fp16x2 rounds the activations to 11 significant bits
+    assert np.abs(eps - golden[f"eps.{i}"]).max() < (5e-4 if plan.precision == "bf16x3" else 4e-3)
 
 
 @pytest.mark.parametrize("i", range(len(DIFF_CASES)))
@@ -237,4 +245,4 @@ def test_drop_in_module_surface(dev):
     eps = net.to(dev)(inp["start_noise"].to(dev), torch.full((2,), 10, device=dev), inp["cond"].to(dev).transpose(1, 2))
     with torch.no_grad():
         eref = O.diffnet_forward(sd, inp["start_noise"], torch.full((2,), 10), inp["cond"].transpose(1, 2))
-    assert float((eps.cpu() - eref).abs().max()) < 5e-4
+    assert float((eps.cpu() - eref).abs().max()) < 4e-3    # default fp16x2 contraction, single evaluation

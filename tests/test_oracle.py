@@ -92,6 +92,21 @@ def test_operand_rounding_model_orders(sd_diff):
     assert 1e-3 < e < 0.2
 
 
+def test_fp16x2_model_meets_mel_tolerance(sd_diff):
+    """The contraction mode the CUDA sampler runs by default (fp16 activations x split fp16 weights), emulated on
+    the oracle over all 100 steps: inside the north-star tolerance with margin, while plain bf16 operands are far outside."""
+    K = 100
+    sched = O.schedule_buffers(O.linear_beta_schedule(K, 0.06))
+    smin, smax = torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX)
+    inp = synth.kernel_inputs(8, 1, 48, K)
+    with torch.no_grad():
+        run = lambda op: O.diffusion_infer(sd_diff, sched, smin, smax, inp["cond"], K, inp["step_noise"], inp["fs2_mel"],
+                                           inp["start_noise"], operand=op)
+        ref, f16, bf = run(None), run("fp16x2"), run("bf16")
+    assert float((f16 - ref).abs().max()) < 5e-3
+    assert float((bf - ref).abs().max()) > 2e-2
+
+
 reference_present = __import__("ref_shim").available()
 
 

@@ -201,7 +201,7 @@ def stage_vbench():
 def stage_proftarget():
     """Target for ncu: a few launches of one DiffNet layer kernel (BSG_WHICH = 0 gate / 1 residual-skip) at the cfg3 shape."""
     import torch
-    sd, sched, plan, inp, O, synth = _diff_setup(1, 8, 100, os.environ.get("BSG_PREC", "bf16x3"))
+    sd, sched, plan, inp, O, synth = _diff_setup(1, 8, 100, os.environ.get("BSG_PREC", "fp16x2"))
     which = int(os.environ.get("BSG_WHICH", "1"))
     print("kernel", which, "ms", plan.time_kernel(which, 32, 1875, 4))
 

@@ -1,0 +1,110 @@
+"""CPU study of operand-precision schemes for the 100-step sampler (emulation on the oracle, test infrastructure).
+Each scheme says how the operands of the contractions are represented; accumulation is fp32 (emulated in fp32/fp64)."""
+import math, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import torch, torch.nn.functional as F
+import svs_oracle as O, synth
+
+def r(x, dt):
+    return x.to(dt).float()
+def split(x, dt):
+    h = r(x, dt)
+    return h, r(x - h, dt)
+
+class Scheme:
+    """a_terms / w_terms: 1 or 2 pieces of `dt`; cross = drop lo*lo"""
+    def __init__(self, name, dt, a_terms, w_terms, state16=False, per=None):
+        self.name, self.dt, self.a, self.w, self.state16, self.per = name, dt, a_terms, w_terms, state16, per or {}
+    def conv(self, which, x, w, b, **kw):
+        dt, a, wt = self.per.get(which, (self.dt, self.a, self.w))
+        if dt is None:
+            return F.conv1d(x, w, b, **kw)
+        xh, xl = split(x, dt)
+        wh, wl = split(w, dt)
+        y = F.conv1d(xh, wh, b, **kw)
+        if a == 2:
+            y = y + F.conv1d(xl, wh, None, **kw)
+        if wt == 2:
+            y = y + F.conv1d(xh, wl, None, **kw)
+        return y
+
+def diffnet(p, spec, t, cond, S, cp_cache):
+    C = p["input_projection.weight"].shape[0]
+    L = O.n_residual_layers(p)
+    x = F.relu(S.conv("in", spec[:, 0], p["input_projection.weight"], p["input_projection.bias"]))
+    step = O.step_embedding(p, t, C)
+    zs = []
+    for i in range(L):
+        pre = f"residual_layers.{i}."
+        dil = 2 ** (i % 4)
+        d = F.linear(step, p[pre + "diffusion_projection.weight"], p[pre + "diffusion_projection.bias"])
+        if i not in cp_cache:
+            cp_cache[i] = S.conv("cond", cond, p[pre + "conditioner_projection.weight"], p[pre + "conditioner_projection.bias"])
+        xa = x + d[:, :, None]
+        if S.state16:
+            h, l = split(xa, torch.bfloat16)
+            xa = h + l
+            x = xa - d[:, :, None]     # the state is re-derived from the stored operand
+        y = S.conv("gate", xa, p[pre + "dilated_conv.weight"], p[pre + "dilated_conv.bias"], padding=dil, dilation=dil) + cp_cache[i]
+        g, f = torch.chunk(y, 2, dim=1)
+        z = torch.sigmoid(g) * torch.tanh(f)
+        zs.append(z)
+        w = p[pre + "output_projection.weight"]; b = p[pre + "output_projection.bias"]
+        res = S.conv("res", z, w[:C], b[:C])
+        x = (x + res) / math.sqrt(2.0)
+    zall = torch.cat(zs, 1)
+    wall = torch.cat([p[f"residual_layers.{i}.output_projection.weight"][C:] for i in range(L)], 1)
+    ball = sum(p[f"residual_layers.{i}.output_projection.bias"][C:] for i in range(L))
+    s = S.conv("skip", zall, wall, ball) / math.sqrt(L)
+    h = F.relu(S.conv("sp", s, p["skip_projection.weight"], p["skip_projection.bias"]))
+    return S.conv("out", h, p["output_projection.weight"], p["output_projection.bias"])[:, None]
+
+def sample(p, sched, inp, K, S):
+    smin, smax = torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX)
+    cond = inp["cond"].transpose(1, 2)
+    xs = O.norm_spec(inp["fs2_mel"], smin, smax).transpose(1, 2)[:, None]
+    x = O.q_sample(sched, xs, K - 1, inp["start_noise"])
+    cache = {}
+    for k, t in enumerate(reversed(range(K))):
+        B = x.shape[0]
+        eps = diffnet(p, x, torch.full((B,), t), cond, S, cache)
+        x0 = (sched["sqrt_recip_alphas_cumprod"][t] * x - sched["sqrt_recipm1_alphas_cumprod"][t] * eps).clamp(-1, 1)
+        mean = sched["posterior_mean_coef1"][t] * x0 + sched["posterior_mean_coef2"][t] * x
+        x = mean + (0.0 if t == 0 else 1.0) * (0.5 * sched["posterior_log_variance_clipped"][t]).exp() * inp["step_noise"][k]
+    return O.denorm_spec(x[:, 0].transpose(1, 2), smin, smax)
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    K = 100
+    bf, hf = torch.bfloat16, torch.float16
+    schemes = [
+        Scheme("fp32", None, 1, 1),
+        Scheme("bf16x3", bf, 2, 2),
+        Scheme("bf16x3+state16", bf, 2, 2, state16=True),
+        Scheme("fp16x1", hf, 1, 1),
+        Scheme("fp16 Wsplit", hf, 1, 2),
+        Scheme("fp16 Asplit", hf, 2, 1),
+        Scheme("bf16x3, skip/sp/out/in fp16 Wsplit", bf, 2, 2, per={k: (hf, 1, 2) for k in ("skip", "sp", "out", "in")}),
+        Scheme("bf16x3, res fp16 Wsplit", bf, 2, 2, per={"res": (hf, 1, 2)}),
+        Scheme("bf16x3, gate fp16 Wsplit", bf, 2, 2, per={"gate": (hf, 1, 2)}),
+    ]
+    sel = sys.argv[1:]
+    for seed, (B, T) in ((7, (2, 40)), (8, (1, 96))):
+        sd = synth.diffnet_state(1234)
+        sched = O.schedule_buffers(O.linear_beta_schedule(K, 0.06))
+        inp = synth.kernel_inputs(seed, B, T, K)
+        with torch.no_grad():
+            ref = None
+            for S in schemes:
+                if sel and S.name != "fp32" and not any(s in S.name for s in sel):
+                    continue
+                t0 = time.time()
+                out = sample(sd, sched, inp, K, S)
+                if S.name == "fp32":
+                    ref = out
+                    base = O.diffusion_infer(sd, sched, torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX), inp["cond"], K, inp["step_noise"], inp["fs2_mel"], inp["start_noise"])
+                    print(f"seed {seed} {B}x{T}: restructured fp32 vs oracle {(out - base).abs().max():.2e}")
+                    ref = base
+                else:
+                    print(f"seed {seed} {B}x{T}: {S.name:45s} max|mel-ref| {(out - ref).abs().max():.3e}  mean {(out - ref).abs().mean():.2e}  ({time.time() - t0:.0f}s)", flush=True)
