@@ -105,7 +105,8 @@ int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias
         B200_CHECK(a_dev && w_host && bias_host && shifts && out_dev, "null argument");
         B200_CHECK(Cin % 8 == 0 && N % n_tile == 0 && ntaps >= 1 && ntaps <= kMaxTaps, "bad shape");
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        const bool pair = (precision & 0x100) != 0;   // test hook: run the 2-CTA (cta_group::2) variant of the kernel
+        // test hooks: 0x100 = the 2-CTA (cta_group::2) variant of the kernel, 0x200 = two pairs per cluster with multicast weights
+        const int pair = (precision & 0x200) ? 2 : ((precision & 0x100) ? 1 : 0);
         const int prec = precision & 0xff;
         const int terms = prec == BSG_PRECISION_BF16X3 ? 3 : (prec == BSG_PRECISION_FP16X2 ? 2 : 1);
         const size_t rows = static_cast<size_t>(B) * L;
@@ -134,11 +135,11 @@ int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias
         PackedW pw;
         pw.pack(wp, N, ntaps * Cpad, terms == 2);
         ConvGemmArgs a{};
-        set_geometry(a, B, L, N, n_tile, pair);
+        set_geometry(a, B, L, N, n_tile, pair != 0);
         const int rows_box = set_taps(a, 0, 0, n_kb, shifts, ntaps, Cpad);
         a.amap[0] = make_act_tmap(d_ah.p, B, L, Cin, 0, rows_box);
         a.amap[1] = make_act_tmap(d_al.p, B, L, Cin, 0, rows_box);
-        pw.maps(pair ? n_tile / 2 : n_tile, a.wmap[0], a.wmap[1]);
+        pw.maps(pair == 2 ? n_tile / 4 : (pair ? n_tile / 2 : n_tile), a.wmap[0], a.wmap[1]);
         a.epi.bias = d_bias.as<float>();
         a.epi.f32_a = out_dev;
         a.epi.out_pitch = N;

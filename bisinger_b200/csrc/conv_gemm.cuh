@@ -41,6 +41,9 @@ constexpr int kTileM = 128;
 constexpr int kBlockK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kMaxTaps = 11;
 constexpr int kGemmThreads = 32 * (2 + 8);   // producer, MMA, 8 epilogue warps
+#ifndef B200_ASTAGES2
+#define B200_ASTAGES2 3
+#endif
 constexpr int kSmemBudget = 200 * 1024;
 
 // The taps of one convolution: all read the same A source / channel range, each with its own row shift and its own
@@ -101,7 +104,16 @@ struct ConvGemmArgs {
     int a_rows;            // rows of the A halo box (multiple of 8, 128 + max_shift - min_shift rounded up)
     TapSet taps;
     EpiParams epi;
+    unsigned long long* trace;   // optional [grid][16] cycle counters of the three roles (tools/gpu_probe.py tracetarget), or null
 };
+
+// mbar_wait that adds the cycles spent waiting to *acc when tracing
+__device__ __forceinline__ void mbar_wait_tr(uint64_t* bar, uint32_t parity, bool tr, long long& acc) {
+    if (!tr) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG + Box-Muller (production noise path; parity tests inject noise)
@@ -311,6 +323,7 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
         // the same N_TILE/2 channels (weight rows permuted by the packer).
         constexpr int HALF = N_TILE / 2;
         static_assert(HALF % 64 == 0, "gate epilogue splits HALF over two warp groups");
+        const int abl = e.flags;   // ablation bits (timing experiments only): 1 no cp loads, 2 no transposes, 4 no stores, 8 no MUFU math
 #pragma unroll 1
         for (int c = grp * (HALF / 2); c < (grp + 1) * (HALF / 2); c += 32) {
             const int nb = n_tile * N_TILE + c + lp.cc;   // packed column of the gate pre-activation ; filter at +HALF
@@ -320,22 +333,44 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
             const long long cp0 = (row_w + lp.r0) * static_cast<long long>(e.out_pitch) + nb, cst = 2LL * e.out_pitch;
             float2 g[16], f[16], cp[16];
 #pragma unroll
-            for (int rp = 0; rp < 16; ++rp)
-                if (B200_ROW_OK(rp)) cp[rp] = ld2(e.aux0 + cp0 + rp * cst);
-            ld_chunk_t(tacc, c, stage, lane, g, sc);
+            for (int rp = 0; rp < 16; ++rp) cp[rp] = make_float2(0.f, 0.f);
+            if (!(abl & 1)) {
+#pragma unroll
+                for (int rp = 0; rp < 16; ++rp)
+                    if (B200_ROW_OK(rp)) cp[rp] = ld2(e.aux0 + cp0 + rp * cst);
+            }
+            if (abl & 2) {
+                float v[32];
+                ld_acc32(tacc + c, v, sc);
+#pragma unroll
+                for (int rp = 0; rp < 16; ++rp) g[rp] = make_float2(v[2 * rp], v[2 * rp + 1]);
+            } else {
+                ld_chunk_t(tacc, c, stage, lane, g, sc);
+            }
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp) { g[rp].x += cp[rp].x; g[rp].y += cp[rp].y; }
+            if (!(abl & 1)) {
 #pragma unroll
-            for (int rp = 0; rp < 16; ++rp)
-                if (B200_ROW_OK(rp)) cp[rp] = ld2(e.aux0 + cp0 + HALF + rp * cst);
-            ld_chunk_t(tacc, HALF + c, stage, lane, f, sc);
+                for (int rp = 0; rp < 16; ++rp)
+                    if (B200_ROW_OK(rp)) cp[rp] = ld2(e.aux0 + cp0 + HALF + rp * cst);
+            }
+            if (abl & 2) {
+                float v[32];
+                ld_acc32(tacc + HALF + c, v, sc);
+#pragma unroll
+                for (int rp = 0; rp < 16; ++rp) f[rp] = make_float2(v[2 * rp], v[2 * rp + 1]);
+            } else {
+                ld_chunk_t(tacc, HALF + c, stage, lane, f, sc);
+            }
             const long long off0 = (row_w + lp.r0) * static_cast<long long>(e.act_pitch) + e.out_col0 + ch, st = 2LL * e.act_pitch;
 #pragma unroll
             for (int rp = 0; rp < 16; ++rp) {
                 if (B200_ROW_OK(rp)) {
-                    const float2 z = make_float2(fast_sigmoid(g[rp].x) * fast_tanh(f[rp].x + cp[rp].x),
-                                                 fast_sigmoid(g[rp].y) * fast_tanh(f[rp].y + cp[rp].y));
-                    st_operand2<OUT16 ? 1 : 0>(e, z, off0 + rp * st);
+                    float2 z;
+                    if (abl & 8) z = make_float2(g[rp].x * (f[rp].x + cp[rp].x), g[rp].y * (f[rp].y + cp[rp].y));
+                    else z = make_float2(fast_sigmoid(g[rp].x) * fast_tanh(f[rp].x + cp[rp].x),
+                                         fast_sigmoid(g[rp].y) * fast_tanh(f[rp].y + cp[rp].y));
+                    if (!(abl & 4) || z.x == 123.456f) st_operand2<OUT16 ? 1 : 0>(e, z, off0 + rp * st);
                 }
             }
         }
@@ -588,7 +623,7 @@ struct GemmSmem {
     static constexpr int kBPartBytes = (PAIR ? N_TILE / 2 : N_TILE) * kBlockK * 2;       // PAIR: each CTA stages half of the N columns
     static constexpr int kASlotBytes = kAParts * kAPartBytes;
     static constexpr int kBSlotBytes = kBParts * kBPartBytes;
-    static constexpr int kAStages = TERMS == 3 ? 2 : 3;
+    static constexpr int kAStages = TERMS == 3 ? 2 : (TERMS == 2 ? B200_ASTAGES2 : 3);
     static constexpr int kBStagesRaw = (kSmemBudget - kAStages * kASlotBytes) / kBSlotBytes;
     static constexpr int kBStages = kBStagesRaw > 6 ? 6 : kBStagesRaw;
     static constexpr int kOperandBytes = kAStages * kASlotBytes + kBStages * kBSlotBytes;
@@ -610,8 +645,16 @@ __host__ __device__ constexpr int tmem_cols_for(int n) {
 // weights, the leader CTA (rank 0) issues every MMA (M = 256) and each CTA's TMEM receives the accumulators of its own
 // 128 rows.  Per MMA every SM reads 8 KB of shared memory instead of 12 KB, which is what a single CTA could not
 // sustain next to the TMA fill (profiles/r01_d: 1-CTA SS-mode MMAs were shared-memory-bandwidth bound).
-template <int N_TILE, int TERMS, int EPI, bool PAIR>
+//
+// MC = true (needs PAIR): clusters of FOUR CTAs = two pairs that work on two different 256-row tiles with the SAME weight
+// rows.  Every weight tile is fetched from L2 once per cluster: CTA r loads a quarter of the N rows and multicasts it to
+// the CTA with the same rank-in-pair in the other pair (cp.async.bulk.tensor ... .multicast::cluster).  A weight slot is
+// free when BOTH pairs' MMAs have retired (tcgen05.commit multicast to all four CTAs, barrier count 2).  L2->SM traffic
+// per MMA drops by a third (weights are two thirds of it), which is what starves the MMA issuer in the 2-CTA kernel
+// (profiles/r01_g: ~25 % of the issuer's cycles wait on operand barriers at 7.4 TB/s of L2->SM traffic).
+template <int N_TILE, int TERMS, int EPI, bool PAIR, bool MC = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs args) {
+    static_assert(!MC || PAIR, "weight multicast is built on 2-CTA tiles");
     using S = GemmSmem<N_TILE, TERMS, PAIR>;
     static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128");
     constexpr int kTmemCols = tmem_cols_for(2 * N_TILE);
@@ -634,13 +677,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;           // 0 = leader
-    const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-    const int n_workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int crank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;          // rank in the cluster
+    const int rank = crank & 1;                                                // rank in the CTA pair, 0 = leader
+    const int pidx = MC ? (crank >> 1) : 0;                                    // which pair of the cluster
+    const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pidx));        // the two CTAs of this pair
+    constexpr int kClusterCtas = MC ? 4 : (PAIR ? 2 : 1);
+    const int worker = static_cast<int>(blockIdx.x) / kClusterCtas;
+    const int n_workers = static_cast<int>(gridDim.x) / kClusterCtas;
+    // MC: a work unit is (pair of consecutive row tiles, n_tile); pair `pidx` takes row tile 2*mp + pidx (it may not exist:
+    // then its loads are zero-filled by the TMA unit (batch index out of range) and its epilogue stores nothing)
+    const int n_row_tiles = args.B * args.tiles_per_batch;
+    const int n_units = MC ? ((n_row_tiles + 1) / 2) * args.n_tiles_n : args.num_tiles;
+#define B200_UNIT_TO_TILE(unit) (MC ? ((2 * ((unit) / args.n_tiles_n) + pidx) * args.n_tiles_n + (unit) % args.n_tiles_n) : (unit))
 
     if (threadIdx.x == 32) {
         for (int s = 0; s < S::kAStages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); }
-        for (int s = 0; s < S::kBStages; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
+        for (int s = 0; s < S::kBStages; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], MC ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * kEpiWarps : kEpiWarps); }
         fence_barrier_init();
     }
@@ -667,15 +719,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         const uint32_t b_bytes = S::kBSlotBytes * (PAIR ? 2 : 1);
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
-        for (int tile = worker; tile < args.num_tiles; tile += n_workers) {
+        const bool tr = args.trace != nullptr;
+        long long w_a = 0, w_b = 0;
+        const long long t_begin = tr ? clock64() : 0;
+        for (int unit = worker; unit < n_units; unit += n_workers) {
+            const int tile = B200_UNIT_TO_TILE(unit);
             const int n_tile = tile % args.n_tiles_n;
             const int m = tile / args.n_tiles_n;
             const int b = m / args.tiles_per_batch;
             const int t0 = (m % args.tiles_per_batch) * kTileRows + rank * kTileM;
-            const int wrow = args.w_row0 + n_tile * N_TILE + rank * (N_TILE / 2);
+            const int wrow = args.w_row0 + n_tile * N_TILE + rank * (N_TILE / 2) + (MC ? pidx * (N_TILE / 4) : 0);
             for (int kb = 0; kb < ts.n_kb; ++kb) {
                 // one halo tile of activations per 64-channel k-block ...
-                mbar_wait(&aempty_bar[as], aph ^ 1);
+                mbar_wait_tr(&aempty_bar[as], aph ^ 1, tr, w_a);
                 uint8_t* sa = smem_a + as * S::kASlotBytes;
                 const int ac = ts.a_col0 + kb * kBlockK, ar = t0 + ts.row_shift;
                 if constexpr (PAIR) {
@@ -691,10 +747,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 if (++as == S::kAStages) { as = 0; aph ^= 1; }
                 // ... and one weight tile per tap
                 for (int tp = 0; tp < ts.n_taps; ++tp) {
-                    mbar_wait(&bempty_bar[bs], bph ^ 1);
+                    mbar_wait_tr(&bempty_bar[bs], bph ^ 1, tr, w_b);
                     uint8_t* sb = smem_b + bs * S::kBSlotBytes;
                     const int wc = ts.w_col0[tp] + kb * kBlockK;
-                    if constexpr (PAIR) {
+                    if constexpr (MC) {
+                        // this CTA's quarter of the N rows, written to the same slot of the CTA with the same rank-in-pair in both pairs
+                        if (rank == 0) mbar_arrive_expect_tx(&bfull_bar[bs], b_bytes);
+                        const uint16_t mc_mask = static_cast<uint16_t>(5u << rank);
+                        uint8_t* dq = sb + pidx * (S::kBPartBytes / 2);
+                        tma_load_2d_pair_mc(dq, &args.wmap[0], &bfull_bar[bs], wc, wrow, mc_mask);
+                        if (TERMS >= 2) tma_load_2d_pair_mc(dq + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow, mc_mask);
+                    } else if constexpr (PAIR) {
                         if (rank == 0) mbar_arrive_expect_tx(&bfull_bar[bs], b_bytes);
                         tma_load_2d_pair(sb, &args.wmap[0], &bfull_bar[bs], wc, wrow);
                         if (TERMS >= 2) tma_load_2d_pair(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
@@ -707,23 +770,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 }
             }
         }
+        if (tr) {
+            unsigned long long* t = args.trace + blockIdx.x * 16;
+            t[4] = clock64() - t_begin; t[5] = w_a; t[6] = w_b;
+        }
     } else if (warp == 1 && lane == 0 && rank == 0) {
         // ================= MMA issuer (single thread; leader CTA only in PAIR mode) =================
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
         int it = 0;
-        for (int tile = worker; tile < args.num_tiles; tile += n_workers, ++it) {
+        const bool tr = args.trace != nullptr;
+        long long w_t = 0, w_a = 0, w_b = 0;
+        const long long t_begin = tr ? clock64() : 0;
+        for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
             const int acc = it & 1;
-            mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+            mbar_wait_tr(&tempty_bar[acc], ((it >> 1) & 1) ^ 1, tr, w_t);
             tc_fence_after();
             const uint32_t tacc = tmem_base + acc * N_TILE;
             uint32_t accumulate = 0;
             for (int kb = 0; kb < ts.n_kb; ++kb) {
-                mbar_wait(&afull_bar[as], aph);
+                mbar_wait_tr(&afull_bar[as], aph, tr, w_a);
                 tc_fence_after();
                 const uint32_t a_slot = smem_u32(smem_a + as * S::kASlotBytes);
                 for (int tp = 0; tp < ts.n_taps; ++tp) {
-                    mbar_wait(&bfull_bar[bs], bph);
+                    mbar_wait_tr(&bfull_bar[bs], bph, tr, w_b);
                     tc_fence_after();
                     const uint32_t a_hi = a_slot + ts.row_off[tp] * (kBlockK * 2);   // tap = row offset into the halo tile
                     const uint32_t a_lo = a_hi + S::kAPartBytes;
@@ -744,40 +814,50 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                         }
                         accumulate = 1;
                     }
-                    // free the weight slot (in both CTAs) when these MMAs retire
-                    if constexpr (PAIR) umma_commit_pair(&bempty_bar[bs]); else umma_commit(&bempty_bar[bs]);
+                    // free the weight slot (in both CTAs; MC: one of the two arrivals in all four) when these MMAs retire
+                    if constexpr (PAIR) umma_commit_pair(&bempty_bar[bs], MC ? static_cast<uint16_t>(0xF) : pair_mask); else umma_commit(&bempty_bar[bs]);
                     if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
                 }
                 // free the halo tile after its last tap
-                if constexpr (PAIR) umma_commit_pair(&aempty_bar[as]); else umma_commit(&aempty_bar[as]);
+                if constexpr (PAIR) umma_commit_pair(&aempty_bar[as], pair_mask); else umma_commit(&aempty_bar[as]);
                 if (++as == S::kAStages) { as = 0; aph ^= 1; }
             }
             // accumulator complete -> epilogue (of both CTAs)
-            if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+            if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc], pair_mask); else umma_commit(&tfull_bar[acc]);
+        }
+        if (tr) {
+            unsigned long long* t = args.trace + blockIdx.x * 16;
+            t[0] = clock64() - t_begin; t[1] = w_t; t[2] = w_a; t[3] = w_b; t[10] = it;
         }
     } else if (warp >= 2 && warp < 2 + kEpiWarps) {
         // ================= Epilogue warps =================
         const int quad = warp & 3;
         int it = 0;
         // PAIR: the accumulator-free barrier lives in the leader CTA (its MMA thread waits on it)
-        const uint32_t tempty_remote0 = PAIR ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0;
-        for (int tile = worker; tile < args.num_tiles; tile += n_workers, ++it) {
+        const uint32_t tempty_remote0 = PAIR ? map_to_cta(smem_u32(&tempty_bar[0]), static_cast<uint32_t>(crank & ~1)) : 0;
+        const bool tr = args.trace != nullptr && warp == 2 && lane == 0;
+        long long w_f = 0;
+        const long long t_begin = tr ? clock64() : 0;
+        for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
+            const int tile = B200_UNIT_TO_TILE(unit);
             const int acc = it & 1;
             const int n_tile = tile % args.n_tiles_n;
             const int m = tile / args.n_tiles_n;
             const int b = m / args.tiles_per_batch;
             const int t_warp = (m % args.tiles_per_batch) * kTileRows + rank * kTileM + quad * 32;
-            mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+            mbar_wait_tr(&tfull_bar[acc], (it >> 1) & 1, tr, w_f);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * N_TILE;
             float* stage = xpose + (warp - 2) * kStageFloatsPerWarp;
             const int grp = (warp - 2) >> 2;
             if constexpr (EPI == EPI_RES_SKIP || EPI == EPI_BIAS_ACT || EPI == EPI_GATE) {
-                const int nt = tile + n_workers;
-                if (nt < args.num_tiles) prefetch_rmw_tile<N_TILE, EPI>(args, nt, kTileRows, rank * kTileM + quad * 32, grp, lane);
+                const int nu = unit + n_workers;
+                if (nu < n_units && B200_UNIT_TO_TILE(nu) < args.num_tiles)
+                    prefetch_rmw_tile<N_TILE, EPI>(args, B200_UNIT_TO_TILE(nu), kTileRows, rank * kTileM + quad * 32, grp, lane);
             }
             // the fp16x2 per-layer GEMMs (gate, residual) feed fp16x2 consumers: fp16 operand output decided at compile time
-            if (args.L - t_warp >= 32) run_epilogue<N_TILE, EPI, true, TERMS == 2>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
+            if (MC && b >= args.B) { /* the odd row tile of the last unit does not exist */ }
+            else if (args.L - t_warp >= 32) run_epilogue<N_TILE, EPI, true, TERMS == 2>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
             else run_epilogue<N_TILE, EPI, false, TERMS == 2>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
             tc_fence_before();
             __syncwarp();
@@ -785,6 +865,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 if constexpr (PAIR) mbar_arrive_remote(tempty_remote0 + acc * 8);
                 else mbar_arrive(&tempty_bar[acc]);
             }
+        }
+        if (tr) {
+            unsigned long long* t = args.trace + blockIdx.x * 16;
+            t[7] = clock64() - t_begin; t[8] = w_f;
         }
     }
 
@@ -794,6 +878,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         tc_fence_after();
         if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
     }
+#undef B200_UNIT_TO_TILE
 }
 
 }  // namespace b200

@@ -17,6 +17,7 @@
 // Per step: 1 + 2L + 3 launches of conv_gemm_kernel; all K steps are captured in one CUDA graph when the
 // noise is generated on the device.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -273,8 +274,16 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, none, nullptr);
     launch_conv_gemm(kResTile, terms, EPI_RELU_BF16, none, nullptr);
     if (const char* np = std::getenv("BSG_NO_PAIR")) use_pair = !(np[0] == '1');
-    launch_conv_gemm(256, terms, EPI_GATE, none, nullptr, true);
-    launch_conv_gemm(kSkipTilePair, terms, EPI_RELU_BF16, none, nullptr, true);
+    gate_mode = skip_mode = use_pair ? 1 : 0;
+    if (const char* mc = std::getenv("BSG_MC")) {   // bit 0: gate GEMM, bit 1: skip-sum GEMM on 4-CTA clusters with multicast weights
+        const int bits = std::atoi(mc);
+        if (use_pair && terms == 2 && (bits & 1)) gate_mode = 2;
+        if (use_pair && terms >= 2 && (bits & 2)) skip_mode = 2;
+    }
+    launch_conv_gemm(256, terms, EPI_GATE, none, nullptr, 1);
+    launch_conv_gemm(kSkipTilePair, terms, EPI_RELU_BF16, none, nullptr, 1);
+    if (gate_mode == 2) launch_conv_gemm(256, terms, EPI_GATE, none, nullptr, 2);
+    if (skip_mode == 2) launch_conv_gemm(kSkipTilePair, terms, EPI_RELU_BF16, none, nullptr, 2);
 }
 
 DiffusionPlan::~DiffusionPlan() = default;
@@ -357,9 +366,9 @@ ConvGemmArgs DiffusionPlan::gate_args(Workspace& w, int l) {
     const int H = cfg.hidden_size, C = cfg.residual_channels;
     Layer& ly = layers[l];
     ConvGemmArgs a{};
-    set_geometry(a, w.B, w.T, 2 * C, 256, use_pair);
+    set_geometry(a, w.B, w.T, 2 * C, 256, gate_mode != 0);
     a.amap[0] = w.m_xa[0]; a.amap[1] = w.m_xa[1];
-    set_w(a, ly.g1, use_pair ? 128 : 256);   // 2-CTA tiles: each CTA stages half of the 256 weight rows
+    set_w(a, ly.g1, 256 >> gate_mode);   // 2-CTA tiles: each CTA stages half of the 256 weight rows (multicast: loads a quarter)
     const int shifts[3] = {-ly.dilation, 0, ly.dilation};
     set_taps(a, 0, 0, C / kBlockK, shifts, 3, C);
     a.a_rows = kXaBoxRows;   // the xa tensor maps are encoded once with the box of the largest dilation
@@ -371,6 +380,7 @@ ConvGemmArgs DiffusionPlan::gate_args(Workspace& w, int l) {
     a.epi.out_pitch = 2 * C;                         // pitch of the conditioner-projection rows (aux0)
     a.epi.act_pitch = cfg.residual_layers * C;       // pitch of the all-layer z matrix
     a.epi.out_col0 = l * C;
+    if (const char* ab = std::getenv("BSG_ABLATE")) a.epi.flags = std::atoi(ab);   // timing experiments only (wrong results)
     return a;
 }
 
@@ -398,9 +408,9 @@ ConvGemmArgs DiffusionPlan::skipsum_args(Workspace& w) {
     const int C = cfg.residual_channels, L = cfg.residual_layers;
     ConvGemmArgs a{};
     const int nt = use_pair ? kSkipTilePair : kResTile;
-    set_geometry(a, w.B, w.T, C, nt, use_pair);
+    set_geometry(a, w.B, w.T, C, nt, skip_mode != 0);
     a.amap[0] = w.m_z[0]; a.amap[1] = w.m_z[1];
-    set_w(a, skipall, use_pair ? nt / 2 : nt);
+    set_w(a, skipall, nt >> skip_mode);
     set_taps(a, 0, 0, L * C / kBlockK, kOneTap, 1, 0);
     a.epi.bias = skipall_bias.as<float>();
     a.epi.out_hi = w.s_hi.as<__nv_bfloat16>();
@@ -426,9 +436,9 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
     auto run = [&](int n) {
         for (int i = 0; i < n; ++i) {
             const int l = i % L;
-            if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, use_pair);
+            if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
             else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
-            else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, use_pair);
+            else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
             ++launches, ++g_launch_count;
         }
     };
@@ -441,6 +451,35 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
     B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (std::getenv("BSG_TRACE")) {
+        // one more launch with the per-role cycle counters (conv_gemm.cuh: ConvGemmArgs::trace), averaged over the CTAs
+        const int grid = 2 * device_sm_count();
+        DevBuf tb;
+        tb.alloc(static_cast<size_t>(grid) * 16 * 8);
+        B200_CUDA(cudaMemsetAsync(tb.p, 0, static_cast<size_t>(grid) * 16 * 8, st));
+        ConvGemmArgs a = which == 0 ? gate_args(w, 1) : (which == 1 ? resskip_args(w, 1, lut.as<float>()) : skipsum_args(w));
+        a.trace = tb.as<unsigned long long>();
+        if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, a, st, gate_mode);
+        else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, a, st);
+        else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, a, st, skip_mode);
+        std::vector<unsigned long long> h(static_cast<size_t>(grid) * 16);
+        B200_CUDA(cudaMemcpyAsync(h.data(), tb.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        double s[16] = {0};
+        int n_mma = 0, n_cta = 0;
+        for (int c = 0; c < grid; ++c) {
+            if (h[c * 16 + 4] == 0) continue;
+            ++n_cta;
+            if (h[c * 16 + 0]) ++n_mma;
+            for (int i = 0; i < 16; ++i) s[i] += static_cast<double>(h[c * 16 + i]);
+        }
+        if (n_mma && n_cta)
+            std::fprintf(stderr,
+                         "TRACE kernel %d: MMA thread total %.0f clk (tiles %.2f) wait tmem-empty %.0f a-full %.0f b-full %.0f | producer total %.0f "
+                         "wait a-empty %.0f b-empty %.0f | epilogue warp total %.0f wait t-full %.0f\n",
+                         which, s[0] / n_mma, s[10] / n_mma, s[1] / n_mma, s[2] / n_mma, s[3] / n_mma, s[4] / n_cta, s[5] / n_cta, s[6] / n_cta,
+                         s[7] / n_cta, s[8] / n_cta);
+    }
     return ms / static_cast<float>(reps);
 }
 
@@ -469,13 +508,13 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         ++launches, ++g_launch_count;
     }
     for (int l = 0; l < L; ++l) {
-        launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, use_pair);
+        launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
         ++launches, ++g_launch_count;
         launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut_t), st);
         ++launches, ++g_launch_count;
     }
     {   // skip sum: sum_l (W_skip,l z_l + b_skip,l) / sqrt(L)  (net.py:77-78,126) as one K = L*C GEMM over the step's z matrix
-        launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, use_pair);
+        launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
         ++launches, ++g_launch_count;
     }
     {   // skip_projection + ReLU (net.py:127-128)

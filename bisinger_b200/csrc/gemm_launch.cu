@@ -19,7 +19,7 @@ EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 
-CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool bytes) {
     CUtensorMap m;
     cuuint64_t gdim[5];
     cuuint64_t gstr[4];
@@ -28,7 +28,7 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     B200_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base must be 16-byte aligned");
     for (int i = 0; i + 1 < rank; ++i) B200_CHECK(gstr[i] % 16 == 0, "tensor map strides must be multiples of 16 bytes");
-    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+    CUresult r = get_encode_tiled()(&m, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                                     gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
@@ -49,20 +49,40 @@ bool use_pdl() {
     return on;
 }
 
-template <int N_TILE, int TERMS, int EPI, bool PAIR>
+template <int N_TILE, int TERMS, int EPI, bool PAIR, bool MC = false>
 void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
     using S = GemmSmem<N_TILE, TERMS, PAIR>;
-    auto kern = conv_gemm_kernel<N_TILE, TERMS, EPI, PAIR>;
+    auto kern = conv_gemm_kernel<N_TILE, TERMS, EPI, PAIR, MC>;
     static std::once_flag once;   // per instantiation
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal); });
     B200_CUDA(attr_err);
     static int sms = 0;
     if (sms == 0) sms = device_sm_count();
-    if (args.num_tiles <= 0) return;
-    B200_CHECK(args.a_rows >= kTileM && args.a_rows <= S::kASlotRows && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
+    if (args.num_tiles > 0)
+        B200_CHECK(args.a_rows >= kTileM && args.a_rows <= S::kASlotRows && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
     const int pairs = sms / 2;
-    const int grid = PAIR ? 2 * (args.num_tiles < pairs ? args.num_tiles : pairs) : (args.num_tiles < sms ? args.num_tiles : sms);
+    int grid = PAIR ? 2 * (args.num_tiles < pairs ? args.num_tiles : pairs) : (args.num_tiles < sms ? args.num_tiles : sms);
+    if (MC) {
+        // clusters of four CTAs: the GPCs cannot host sms/4 of them at once -- ask the driver (33 on B200)
+        static int max_clusters = 0;
+        if (max_clusters == 0) {
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(4 * 64);
+            q.blockDim = dim3(kGemmThreads);
+            q.dynamicSmemBytes = S::kTotal;
+            cudaLaunchAttribute qa;
+            qa.id = cudaLaunchAttributeClusterDimension;
+            qa.val.clusterDim.x = 4; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
+            q.attrs = &qa;
+            q.numAttrs = 1;
+            B200_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q));
+            B200_CHECK(max_clusters > 0, "no 4-CTA cluster fits on this device");
+        }
+        const int units = ((args.B * args.tiles_per_batch + 1) / 2) * args.n_tiles_n;
+        grid = 4 * (units < max_clusters ? units : max_clusters);
+    }
+    if (args.num_tiles <= 0) return;   // attribute / occupancy set-up call (outside of any stream capture)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);
@@ -77,7 +97,7 @@ void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
     }
     if (PAIR) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.x = MC ? 4 : 2;
         attr[na].val.clusterDim.y = 1;
         attr[na].val.clusterDim.z = 1;
         ++na;
@@ -93,9 +113,11 @@ void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
 #define B200_CASE(NT, TM, EP) \
     if (!pair && n_tile == NT && terms == TM && epi == EP) return launch_inst<NT, TM, EP, false>(args, stream);
 #define B200_PAIR(NT, TM, EP) \
-    if (pair && n_tile == NT && terms == TM && epi == EP) return launch_inst<NT, TM, EP, true>(args, stream);
+    if (pair == 1 && n_tile == NT && terms == TM && epi == EP) return launch_inst<NT, TM, EP, true>(args, stream);
+#define B200_MC(NT, TM, EP) \
+    if (pair == 2 && n_tile == NT && terms == TM && epi == EP) return launch_inst<NT, TM, EP, true, true>(args, stream);
 
-void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream, bool pair) {
+void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream, int pair) {
     // unit-test GEMMs
     B200_CASE(256, 1, EPI_F32) B200_CASE(256, 3, EPI_F32) B200_CASE(128, 1, EPI_F32) B200_CASE(128, 3, EPI_F32)
     B200_CASE(64, 1, EPI_F32) B200_CASE(32, 1, EPI_F32)
@@ -108,13 +130,16 @@ void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, 
     B200_CASE(256, 1, EPI_RELU_BF16) B200_CASE(256, 3, EPI_RELU_BF16) B200_CASE(128, 1, EPI_RELU_BF16) B200_CASE(128, 3, EPI_RELU_BF16)
     B200_PAIR(256, 1, EPI_RELU_BF16) B200_PAIR(256, 3, EPI_RELU_BF16) B200_PAIR(128, 1, EPI_RELU_BF16) B200_PAIR(128, 3, EPI_RELU_BF16)
     B200_CASE(80, 1, EPI_POSTERIOR) B200_CASE(80, 3, EPI_POSTERIOR)
+    // two CTA pairs per cluster with multicast weights
+    B200_MC(256, 1, EPI_F32) B200_MC(256, 2, EPI_F32) B200_MC(256, 3, EPI_F32) B200_MC(128, 2, EPI_F32)
+    B200_MC(256, 2, EPI_GATE) B200_MC(256, 2, EPI_RELU_BF16) B200_MC(256, 3, EPI_RELU_BF16)
     // DiffNet, fp16x2 per-layer GEMMs
     B200_CASE(256, 2, EPI_GATE) B200_PAIR(256, 2, EPI_GATE) B200_CASE(128, 2, EPI_RES_SKIP)
     B200_CASE(128, 2, EPI_RELU_BF16) B200_PAIR(256, 2, EPI_RELU_BF16)
     // HiFi-GAN
     B200_CASE(256, 1, EPI_BIAS_ACT) B200_CASE(128, 1, EPI_BIAS_ACT) B200_CASE(64, 1, EPI_BIAS_ACT) B200_CASE(32, 1, EPI_BIAS_ACT)
     throw Error("conv_gemm: no instantiation for n_tile=" + std::to_string(n_tile) + " terms=" + std::to_string(terms) +
-                " epi=" + std::to_string(epi) + (pair ? " (pair)" : ""));
+                " epi=" + std::to_string(epi) + (pair == 2 ? " (pair, multicast)" : (pair ? " (pair)" : "")));
 }
 
 }  // namespace b200

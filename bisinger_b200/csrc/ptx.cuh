@@ -96,6 +96,23 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f8f6f4: 8-bit operands (K = 32 per instruction), fp32 accumulate; shares the accumulator with kind::f16 MMAs.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -160,6 +177,15 @@ __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const void* des
         ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Multicast variant for clusters of two CTA pairs: the box is written at the same CTA-relative offset in every CTA of
+// `cta_mask`, and complete_tx is credited to the barrier at the (peer-bit-masked) offset in the leader CTA of each
+// destination CTA's pair.
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar) & kPeerBitMask), "h"(cta_mask), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {   // one warp in EACH CTA of the pair
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
 }
@@ -179,9 +205,9 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
         : "memory");
 }
 // arrive (once each) on the mbarrier at this shared-memory offset in BOTH CTAs when the issued MMAs have completed
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask = 3) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"(static_cast<uint16_t>(3))
+                 "h"(cta_mask)
                  : "memory");
 }
 
@@ -207,6 +233,11 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc_f16(int M, int N, bool 
            | ((fp16 ? 0u : 1u) << 10)          // B format
            | (0u << 15) | (0u << 16)           // A, B K-major
            | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// Instruction descriptor for kind::f8f6f4 with 8-bit operands: format 0 = e4m3, 1 = e5m2 (K-major), D fp32.
+__device__ __forceinline__ constexpr uint32_t umma_idesc_f8(int M, int N, int a_fmt, int b_fmt) {
+    return (1u << 4) | (static_cast<uint32_t>(a_fmt) << 7) | (static_cast<uint32_t>(b_fmt) << 10) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 __device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N) { return umma_idesc_f16(M, N, false); }
 

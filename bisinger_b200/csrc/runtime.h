@@ -91,8 +91,10 @@ using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
 
-// bf16 tensor, dims given innermost-first; strides (bytes) for dims 1..rank-1; SWIZZLE_128B, zero OOB fill.
-CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+// 16-bit (bf16 / fp16) tensor -- or 8-bit with bytes = true -- dims given innermost-first; strides (bytes) for dims 1..rank-1;
+// SWIZZLE_128B, zero OOB fill.
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                           bool bytes = false);
 
 // activations [B][L][C] (channels-last), box = 64 channels x box_rows rows (the halo tile of one k-block)
 inline CUtensorMap make_act_tmap(const void* base, int B, int L, int C, int row_pitch_elems = 0, int box_rows = kTileM) {
@@ -114,8 +116,9 @@ inline CUtensorMap make_w_tmap(const void* base, int N, int K, int n_tile, int r
 int device_sm_count();
 
 // Launch one instantiation of conv_gemm_kernel (defined in gemm_launch.cu)
-// pair = true: 2-CTA clusters on 256-row tiles (tcgen05 cta_group::2); the weight tensor map box must then be n_tile/2 rows
-void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream, bool pair = false);
+// pair = 1: 2-CTA clusters on 256-row tiles (tcgen05 cta_group::2); the weight tensor map box must then be n_tile/2 rows
+// pair = 2: clusters of two such pairs with multicast weight tiles; weight tensor map box = n_tile/4 rows
+void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream, int pair = 0);
 
 // fills the tile-geometry fields of args from (B, L, N_total, n_tile)
 inline void set_geometry(ConvGemmArgs& a, int B, int L, int n_total, int n_tile, bool pair = false) {

@@ -206,7 +206,12 @@ def stage_proftarget():
     print("kernel", which, "ms", plan.time_kernel(which, 32, 1875, 4))
 
 
-def stage_pairtest():
+def stage_mctest():
+    """two CTA pairs per cluster with multicast weights (precision | 0x200)"""
+    stage_pairtest(0x200)
+
+
+def stage_pairtest(flag=0x100):
     """2-CTA (cta_group::2) variant of the conv kernel through the self-test entry (precision | 0x100)."""
     import ctypes as C, torch
     from bisinger_b200 import _lib
@@ -215,15 +220,17 @@ def stage_pairtest():
     cases = [
         (1, 256, 64, 256, [0], 256, 0), (1, 256, 256, 256, [0], 256, 0), (2, 300, 256, 512, [-2, 0, 2], 256, 0),
         (2, 300, 256, 512, [-8, 0, 8], 256, 1), (1, 1875, 256, 256, [0], 128, 1), (3, 77, 256, 256, [-1, 0, 1], 256, 1),
-        (4, 1000, 512, 256, [0], 128, 1),
+        (4, 1000, 512, 256, [0], 128, 1), (5, 600, 256, 512, [-4, 0, 4], 256, 2), (32, 1875, 256, 512, [-8, 0, 8], 256, 2),
     ]
+    if flag == 0x200:
+        cases = [c for c in cases if c[5] == 256]
     for (B, Lr, Cin, N, shifts, n_tile, prec) in cases:
         a = torch.randn(B, Lr, Cin, device="cuda")
         w = torch.randn(N, len(shifts), Cin) / (Cin * len(shifts)) ** 0.5
         bias = torch.randn(N)
         out = torch.full((B, Lr, N), float("nan"), device="cuda")
         sh = (C.c_int * len(shifts))(*shifts)
-        st = L.bsg_selftest_conv(_lib.dev_ptr(a), _lib.fptr(w.contiguous()), _lib.fptr(bias), B, Lr, Cin, N, len(shifts), sh, n_tile, prec | 0x100,
+        st = L.bsg_selftest_conv(_lib.dev_ptr(a), _lib.fptr(w.contiguous()), _lib.fptr(bias), B, Lr, Cin, N, len(shifts), sh, n_tile, prec | flag,
                                  _lib.dev_ptr(out), None)
         if st != 0:
             print("PAIR CASE", (B, Lr, Cin, N, shifts, n_tile, prec), "ERROR", L.bsg_last_error().decode()); continue
@@ -252,7 +259,7 @@ def stage_vproftarget():
     torch.cuda.synchronize()
 
 
-STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench, "vocoder": stage_vocoder, "vbench": stage_vbench, "proftarget": stage_proftarget, "pairtest": stage_pairtest, "vproftarget": stage_vproftarget}
+STAGES = {"selftest": stage_selftest, "denoise": stage_denoise, "sample": stage_sample, "bench": stage_bench, "vocoder": stage_vocoder, "vbench": stage_vbench, "proftarget": stage_proftarget, "pairtest": stage_pairtest, "mctest": stage_mctest, "vproftarget": stage_vproftarget}
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--run":

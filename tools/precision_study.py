@@ -27,6 +27,13 @@ class Scheme:
             y = y + F.conv1d(xl, wh, None, **kw)
         if wt == 2:
             y = y + F.conv1d(xh, wl, None, **kw)
+        if wt == 8:   # weight correction term on the fp8 pipe: e4m3(A) x e4m3(W_lo * 2^p)
+            f8 = torch.float8_e4m3fn
+            sc = 2.0 ** math.floor(math.log2(224.0 / float(wl.abs().max())))
+            y = y + F.conv1d(r(x, f8), r(wl * sc, f8), None, **kw) / sc
+        if wt == 52:  # weight correction term on the fp8 pipe sharing the accumulator scale: e4m3(A) x e5m2(W_lo * 2^s), s fixed by fp16 W_hi
+            sc = 2.0 ** math.floor(math.log2(32768.0 / float(w.abs().max())))
+            y = y + F.conv1d(r(x, torch.float8_e4m3fn), r(wl * sc, torch.float8_e5m2), None, **kw) / sc
         return y
 
 def diffnet(p, spec, t, cond, S, cp_cache):
@@ -41,6 +48,8 @@ def diffnet(p, spec, t, cond, S, cp_cache):
         d = F.linear(step, p[pre + "diffusion_projection.weight"], p[pre + "diffusion_projection.bias"])
         if i not in cp_cache:
             cp_cache[i] = S.conv("cond", cond, p[pre + "conditioner_projection.weight"], p[pre + "conditioner_projection.bias"])
+            if "cp" in S.per:   # storage type of the hoisted conditioner projection
+                cp_cache[i] = r(cp_cache[i] + p[pre + "dilated_conv.bias"][None, :, None], S.per["cp"]) - p[pre + "dilated_conv.bias"][None, :, None]
         xa = x + d[:, :, None]
         if S.state16:
             h, l = split(xa, torch.bfloat16)
@@ -89,6 +98,23 @@ if __name__ == "__main__":
         Scheme("bf16x3, res fp16 Wsplit", bf, 2, 2, per={"res": (hf, 1, 2)}),
         Scheme("bf16x3, gate fp16 Wsplit", bf, 2, 2, per={"gate": (hf, 1, 2)}),
     ]
+    W2, W1, W8 = (hf, 1, 2), (hf, 1, 1), (hf, 1, 8)
+    side = {k: (bf, 2, 2) for k in ("cond", "in", "sp", "out")}
+    schemes += [
+        Scheme("cur: fp16 Wsplit layer, bf16x3 side", hf, 1, 2, per=side),
+        Scheme("cur but gate fp16x1", hf, 1, 2, per={**side, "gate": W1}),
+        Scheme("cur but res fp16x1", hf, 1, 2, per={**side, "res": W1}),
+        Scheme("cur but skip fp16x1", hf, 1, 2, per={**side, "skip": W1}),
+        Scheme("cur but gate+res+skip fp16x1", hf, 1, 2, per={**side, "gate": W1, "res": W1, "skip": W1}),
+        Scheme("cur but gate fp8corr", hf, 1, 2, per={**side, "gate": W8}),
+        Scheme("cur but gate+res+skip fp8corr", hf, 1, 2, per={**side, "gate": W8, "res": W8, "skip": W8}),
+    ]
+    W52 = (hf, 1, 52)
+    schemes += [Scheme("cur but gate e5m2corr", hf, 1, 2, per={**side, "gate": W52}),
+                Scheme("cur but gate+res+skip e5m2corr", hf, 1, 2, per={**side, "gate": W52, "res": W52, "skip": W52})]
+    schemes += [Scheme("cur but gate e5m2corr + cp fp16", hf, 1, 2, per={**side, "gate": W52, "cp": hf}),
+                Scheme("cur but cp fp16", hf, 1, 2, per={**side, "cp": hf}),
+                Scheme("cur but cp bf16", hf, 1, 2, per={**side, "cp": bf})]
     sel = sys.argv[1:]
     for seed, (B, T) in ((7, (2, 40)), (8, (1, 96))):
         sd = synth.diffnet_state(1234)
