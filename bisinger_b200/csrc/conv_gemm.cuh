@@ -272,13 +272,12 @@ enum : int {
 // warp (0/1: two warps share a TMEM lane quadrant and split the tile's columns), stage: the warp's transpose tile.
 // FULL: all 32 rows of the warp are inside the batch (no row predicates).  Rows t >= L are never stored.
 template <int N_TILE, int EPI, bool FULL, bool OUT16>
-__device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t tacc, int b, int t_warp, int n_tile, int grp,
+__device__ __forceinline__ void run_epilogue(const EpiParams& e, int Lrows, uint32_t tacc, int b, int t_warp, int n_tile, int grp,
                                              float* stage, int lane) {
-    const EpiParams& e = args.epi;
     const LanePos lp = lane_pos(lane);
     const float sc = e.acc_scale != 0.0f ? e.acc_scale : 1.0f;
-    const long long row_w = static_cast<long long>(b) * args.L + t_warp;   // global row of the warp's lane 0
-    const int rows_left = args.L - t_warp - lp.r0;                          // row pair rp is valid iff 2*rp < rows_left
+    const long long row_w = static_cast<long long>(b) * Lrows + t_warp;   // global row of the warp's lane 0
+    const int rows_left = Lrows - t_warp - lp.r0;                          // row pair rp is valid iff 2*rp < rows_left
 #define B200_ROW_OK(rp) (FULL || 2 * (rp) < rows_left)
     // column range of this warp
     constexpr int kSplit = (N_TILE % 64 == 0) ? 2 : 1;
@@ -441,9 +440,9 @@ __device__ __forceinline__ void run_epilogue(const ConvGemmArgs& args, uint32_t 
         static_assert(N_TILE % 16 == 0 && N_TILE <= 96, "posterior epilogue expects <= 96 mel bins, a multiple of 16");
         constexpr int M = N_TILE;
         const int t = t_warp + lane;
-        const bool row_ok = FULL || t < args.L;
+        const bool row_ok = FULL || t < Lrows;
         const long long row = row_w + lane;
-        const long long LL = args.L;
+        const long long LL = Lrows;
         const bool eps_only = (e.flags & 1) != 0;     // bsg_diffnet_forward: write the denoiser output, reference layout
         float* xt = e.f32_a + (static_cast<long long>(b) * M) * LL + t;
         const float* nz = (!eps_only && e.aux0) ? e.aux0 + (static_cast<long long>(b) * M) * LL + t : nullptr;
@@ -857,8 +856,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             }
             // the fp16x2 per-layer GEMMs (gate, residual) feed fp16x2 consumers: fp16 operand output decided at compile time
             if (MC && b >= args.B) { /* the odd row tile of the last unit does not exist */ }
-            else if (args.L - t_warp >= 32) run_epilogue<N_TILE, EPI, true, TERMS == 2>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
-            else run_epilogue<N_TILE, EPI, false, TERMS == 2>(args, tacc, b, t_warp, n_tile, grp, stage, lane);
+            else if (args.L - t_warp >= 32) run_epilogue<N_TILE, EPI, true, TERMS == 2>(args.epi, args.L, tacc, b, t_warp, n_tile, grp, stage, lane);
+            else run_epilogue<N_TILE, EPI, false, TERMS == 2>(args.epi, args.L, tacc, b, t_warp, n_tile, grp, stage, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

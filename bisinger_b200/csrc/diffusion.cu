@@ -23,6 +23,7 @@
 #include <memory>
 
 #include "plans.h"
+#include "diffnet_layer.cuh"
 
 namespace b200 {
 
@@ -282,6 +283,10 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     }
     launch_conv_gemm(256, terms, EPI_GATE, none, nullptr, 1);
     launch_conv_gemm(kSkipTilePair, terms, EPI_RELU_BF16, none, nullptr, 1);
+    // one fused kernel per ResidualBlock (diffnet_layer.cuh) in the fp16x2 mode; BSG_NO_FUSE=1 keeps the two-launch path
+    use_fused = use_pair && terms == 2;
+    if (const char* nf = std::getenv("BSG_NO_FUSE")) use_fused = use_fused && !(nf[0] == '1');
+    if (use_fused) { LayerArgs la{}; launch_diffnet_layer(la, nullptr); }
     if (gate_mode == 2) launch_conv_gemm(256, terms, EPI_GATE, none, nullptr, 2);
     if (skip_mode == 2) launch_conv_gemm(kSkipTilePair, terms, EPI_RELU_BF16, none, nullptr, 2);
 }
@@ -403,6 +408,24 @@ ConvGemmArgs DiffusionPlan::resskip_args(Workspace& w, int l, const float* lut_t
     return a;
 }
 
+// one whole ResidualBlock: gate GEMM of both channel halves + residual GEMM per 256-row tile (diffnet_layer.cuh)
+static LayerArgs fused_args(const ConvGemmArgs& g, const ConvGemmArgs& r, int dilation, int z_col0) {
+    LayerArgs a{};
+    a.xa = g.amap[0];
+    a.z = r.amap[0];
+    a.wg[0] = g.wmap[0]; a.wg[1] = g.wmap[1];
+    a.wr[0] = r.wmap[0]; a.wr[1] = r.wmap[1];
+    a.B = g.B; a.T = g.L;
+    a.tiles_per_batch = (g.L + 2 * kTileM - 1) / (2 * kTileM);
+    a.n_row_tiles = a.B * a.tiles_per_batch;
+    a.dilation = dilation;
+    a.a_rows = g.a_rows;
+    a.z_col0 = z_col0;
+    a.gate = g.epi;
+    a.res = r.epi;
+    return a;
+}
+
 // skip sum of all layers as one K = L*C GEMM over the step's z matrix (net.py:77-78,126), / sqrt(L), -> s (bf16 hi/lo)
 ConvGemmArgs DiffusionPlan::skipsum_args(Workspace& w) {
     const int C = cfg.residual_channels, L = cfg.residual_layers;
@@ -425,7 +448,8 @@ ConvGemmArgs DiffusionPlan::skipsum_args(Workspace& w) {
 // the layers (so weights change from launch to launch as in a real step).  which: 0 = gate GEMM, 1 = residual GEMM,
 // 2 = skip-sum GEMM.
 float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t st) {
-    B200_CHECK(which >= 0 && which <= 2, "unknown kernel id");
+    B200_CHECK(which >= 0 && which <= 3, "unknown kernel id");
+    B200_CHECK(which != 3 || use_fused, "the fused layer kernel is not enabled in this plan");
     B200_CHECK(reps > 0, "reps must be positive");
     B200_CUDA(cudaSetDevice(device));
     Workspace& w = workspace(B, T);
@@ -436,7 +460,8 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
     auto run = [&](int n) {
         for (int i = 0; i < n; ++i) {
             const int l = i % L;
-            if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
+            if (which == 3) launch_diffnet_layer(fused_args(gate_args(w, l), resskip_args(w, l, lut.as<float>()), layers[l].dilation, l * cfg.residual_channels), st);
+            else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
             else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
             else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
             ++launches, ++g_launch_count;
@@ -459,7 +484,11 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
         B200_CUDA(cudaMemsetAsync(tb.p, 0, static_cast<size_t>(grid) * 16 * 8, st));
         ConvGemmArgs a = which == 0 ? gate_args(w, 1) : (which == 1 ? resskip_args(w, 1, lut.as<float>()) : skipsum_args(w));
         a.trace = tb.as<unsigned long long>();
-        if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, a, st, gate_mode);
+        if (which == 3) {
+            LayerArgs la = fused_args(gate_args(w, 1), resskip_args(w, 1, lut.as<float>()), layers[1].dilation, cfg.residual_channels);
+            la.trace = tb.as<unsigned long long>();
+            launch_diffnet_layer(la, st);
+        } else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, a, st, gate_mode);
         else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, a, st);
         else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, a, st, skip_mode);
         std::vector<unsigned long long> h(static_cast<size_t>(grid) * 16);
@@ -479,6 +508,9 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
                          "wait a-empty %.0f b-empty %.0f | epilogue warp total %.0f wait t-full %.0f\n",
                          which, s[0] / n_mma, s[10] / n_mma, s[1] / n_mma, s[2] / n_mma, s[3] / n_mma, s[4] / n_cta, s[5] / n_cta, s[6] / n_cta,
                          s[7] / n_cta, s[8] / n_cta);
+        if (which == 3 && n_cta)
+            std::fprintf(stderr, "TRACE fused layer: producer waits for z %.0f clk | epilogue warp busy in gate ops %.0f, in residual ops %.0f (row tiles %.2f)\n",
+                         s[9] / n_cta, s[11] / n_cta, s[12] / n_cta, n_mma ? s[10] / n_mma : 0.0);
     }
     return ms / static_cast<float>(reps);
 }
@@ -508,6 +540,11 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         ++launches, ++g_launch_count;
     }
     for (int l = 0; l < L; ++l) {
+        if (use_fused) {
+            launch_diffnet_layer(fused_args(gate_args(w, l), resskip_args(w, l, lut_t), layers[l].dilation, l * C), st);
+            ++launches, ++g_launch_count;
+            continue;
+        }
         launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
         ++launches, ++g_launch_count;
         launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut_t), st);

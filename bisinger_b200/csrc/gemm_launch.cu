@@ -3,6 +3,7 @@
 #include <mutex>
 
 #include "runtime.h"
+#include "diffnet_layer.cuh"
 
 namespace b200 {
 
@@ -109,6 +110,41 @@ void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// One fused DiffNet layer (diffnet_layer.cuh): CTA pairs over the 256-row tiles, persistent.
+void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream) {
+    using S = GemmSmem<256, 2, true>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(diffnet_layer_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes); });
+    B200_CUDA(attr_err);
+    static int sms = 0;
+    if (sms == 0) sms = device_sm_count();
+    if (args.n_row_tiles <= 0) return;
+    B200_CHECK(args.a_rows >= kTileM && args.a_rows <= S::kASlotRows && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
+    const int pairs = sms / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (args.n_row_tiles < pairs ? args.n_row_tiles : pairs));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = kLayerSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (use_pdl()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, diffnet_layer_kernel<0>, args));
+    B200_CUDA(cudaGetLastError());
+}
 
 #define B200_CASE(NT, TM, EP) \
     if (!pair && n_tile == NT && terms == TM && epi == EP) return launch_inst<NT, TM, EP, false>(args, stream);

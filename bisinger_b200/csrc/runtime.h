@@ -120,6 +120,10 @@ int device_sm_count();
 // pair = 2: clusters of two such pairs with multicast weight tiles; weight tensor map box = n_tile/4 rows
 void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, cudaStream_t stream, int pair = 0);
 
+// One fused DiffNet layer (diffnet_layer.cuh); args.n_row_tiles == 0 only sets the kernel attributes up
+struct LayerArgs;
+void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream);
+
 // fills the tile-geometry fields of args from (B, L, N_total, n_tile)
 inline void set_geometry(ConvGemmArgs& a, int B, int L, int n_total, int n_tile, bool pair = false) {
     a.B = B;

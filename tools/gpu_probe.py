@@ -95,7 +95,10 @@ def stage_denoise():
 
 def stage_sample():
     import torch
-    for prec, (B, T) in (("bf16x3", (2, 100)), ("bf16x3", (1, 333)), ("bf16", (2, 100))):
+    cases = (("bf16x3", (2, 100)), ("bf16x3", (1, 333)), ("bf16", (2, 100)))
+    if os.environ.get("BSG_PREC"):
+        cases = tuple((os.environ["BSG_PREC"], bt) for bt in ((2, 100), (1, 333), (3, 700)))
+    for prec, (B, T) in cases:
         K = 100
         sd, sched, plan, inp, O, synth = _diff_setup(B, T, K, prec)
         smin, smax = torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX)
