@@ -12,7 +12,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbisinger_b200.so")
+LIB_PATH = os.environ.get("BSG_LIB_PATH") or os.path.join(_HERE, "libbisinger_b200.so")   # BSG_LIB_PATH: A/B builds in experiments
 
 BSG_PRECISION_BF16 = 0
 BSG_PRECISION_BF16X3 = 1

@@ -31,6 +31,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cstdint>
 
 #include "ptx.cuh"
@@ -91,6 +92,7 @@ struct EpiParams {
     unsigned int step;         // POSTERIOR: Philox stream offset (executed step index)
     float acc_scale;           // accumulators are multiplied by this on load (2^-p of the fp16x2 weight pre-scale; 0 => 1)
     int out_fp16;              // out_hi receives ONE fp16 operand (consumer runs fp16x2) instead of bf16 hi[/lo]
+    uint8_t* out8;             // INPROJ: also write e4m3(x + d) [rows][out_pitch] (A operand of the fp8 correction MMAs), or null
 };
 
 struct ConvGemmArgs {
@@ -314,6 +316,8 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, int Lrows, uint
                     const float2 x = make_float2(fmaxf(o[rp].x + bias.x, 0.0f), fmaxf(o[rp].y + bias.y, 0.0f));
                     st2(e.f32_a + off, x);
                     st_operand2<2>(e, make_float2(x.x + d.x, x.y + d.y), off);
+                    if (e.out8 != nullptr)
+                        *reinterpret_cast<uint16_t*>(e.out8 + off) = __nv_cvt_float2_to_fp8x2(make_float2(x.x + d.x, x.y + d.y), __NV_SATFINITE, __NV_E4M3);
                 }
             }
         }

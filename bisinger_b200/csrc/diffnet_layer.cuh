@@ -1,38 +1,60 @@
-// One DiffNet ResidualBlock (usr/diff/net.py:58-78) as ONE persistent 2-CTA kernel: the dilated-conv gate GEMM of both
-// channel halves and the residual half of the output projection of a 256-row tile run as a stream of three GEMM "ops" on
-// the same producer / MMA / epilogue pipeline as conv_gemm_kernel:
+// One DiffNet ResidualBlock (usr/diff/net.py:58-78) as ONE persistent 2-CTA kernel.
 //
-//     G(n,0)  G(n,1)   : acc[256 rows x 256] = conv_dilated(xa)[:, gate|filter rows of channel half h]   (K = 3 x 256)
-//                        epilogue EPI_GATE: + conditioner projection, sigmoid*tanh -> z (fp16, all-layer z matrix)
-//     R(n)             : acc[256 rows x 256] = z[rows, layer columns] * W_res^T                            (K = 256)
-//                        epilogue EPI_RES_SKIP: x = (x + acc + b)/sqrt2 -> x f32, fp16(x + d_next) -> next layer's conv input
+// Per 256-row tile n (128 rows per CTA of the pair) three GEMM "ops" run on one producer / MMA / epilogue pipeline:
+//     G(n,0)  G(n,1)   : acc[256 x 256] = conv_dilated(xa)[:, gate | filter rows of channel half h]            (K = 3 x 256)
+//                        epilogue: + conditioner projection, sigmoid * tanh -> z (fp16, the all-layer z matrix)
+//     R(n)             : acc[256 x 256] = z[rows, this layer's columns] * W_res^T                               (K = 256)
+//                        epilogue: x = (x + acc + b) / sqrt2 -> x f32 ; fp16 / e4m3 of (x + d_next) -> next layer's conv input
+// issued in the order  G(0,0) G(0,1) | G(1,0) R(0) G(1,1) | G(2,0) R(1) G(2,1) | ... | R(last)  so that the gate epilogue of
+// tile n (which R(n) depends on) overlaps the first gate GEMM of tile n+1.  TMEM holds two 256-column accumulators that
+// alternate op by op.  R(n) reads the z rows the same CTA has just written: they go to global memory anyway (the skip sum
+// of the step is one K = L*C GEMM over that matrix) and come back through L2 by TMA; the epilogue warps order their stores
+// before the async-proxy reads with fence.proxy.async + an mbarrier the TMA producer waits on.
 //
-// R(n) reads the z rows the same CTA has just written: they go to global memory anyway (the skip sum of the step is one
-// K = L*C GEMM over that matrix), come back through L2 by TMA and need no shared-memory tile; the epilogue warps order
-// their global stores before the async-proxy reads with fence.proxy.async + an mbarrier the TMA producer waits on.
-// Ops are issued in the order  G(0,0) G(0,1) | G(1,0) R(0) G(1,1) | G(2,0) R(1) G(2,1) | ... | R(last)  so that the gate
-// epilogue of tile n (which R(n) depends on) overlaps the first gate GEMM of tile n+1; TMEM holds two 256-column
-// accumulators that alternate op by op exactly like the tile double-buffering of conv_gemm_kernel.
-// Versus two launches per layer this removes the residual kernel's launch, its HBM-bound pass (it was 1/3 of the layer
-// time with the tensor pipe at 21 %, profiles/r01_g) and one full read of z.
+// Contraction (fp16x2 mode, tools/precision_study.py): activations are ONE fp16 operand; the weights are fp16(W 2^p) plus a
+// correction.  In the gate GEMM (3/4 of the FLOPs) the correction term runs on the fp8 pipe at twice the rate:
+//     acc += fp16(A) * fp16(W_hi)  [kind::f16, K = 16]   +   e4m3(A) * e5m2(W 2^p - W_hi)  [kind::f8f6f4, K = 32]
+// into the same fp32 accumulator (hardware-checked: csrc/experiments.cu bsg_experiment_f8).  The correction only has to be
+// good to a few bits: what it removes is the SYSTEMATIC fp16 weight-rounding error that would add up over the 100 steps.
+// The residual GEMM keeps two fp16 MMAs per product (its z operand has no 8-bit copy).
+//
+// Epilogue: the fp32 streams the epilogue consumes (conditioner projection cp, residual stream x) move by TMA through a ring of [128 rows x 16 columns] shared-memory boxes (SWIZZLE_64B) fed by a second producer warp,
+// and every epilogue thread works on ONE accumulator row exactly as tcgen05.ld delivers it -- no shared-memory transposes,
+// no global loads in the epilogue warps, 32-byte (full-sector) row stores for the 16-/8-bit outputs.  The register/LSU
+// epilogue of conv_gemm.cuh needed 15-20k cycles per op here and paced the kernel (profiles/r01_g, r01_h).
+//
+// Warps: 0 = operand producer (TMA), 1 = MMA issuer (leader CTA), 2..9 = epilogue (TMEM lane quadrant = warp % 4, two
+// column groups), 10 = epilogue-operand producer (TMA loads of cp / x boxes, TMA stores of the updated x boxes).
 #pragma once
 #include "conv_gemm.cuh"
 
 namespace b200 {
 
 struct LayerArgs {
-    CUtensorMap xa;        // conv input fp16 [B][T][C], box = 64 channels x a_rows rows
+    CUtensorMap xa16;      // conv input fp16 [B][T][C], box = 64 channels x a_rows rows
+    CUtensorMap xa8;       // conv input e4m3 [B][T][C], box = 128 channels x a_rows rows
     CUtensorMap z;         // all-layer gated activations fp16 [B][T][L*C], box = 64 x 128
-    CUtensorMap wg[2];     // dilated-conv weights fp16 hi / lo [2C (gate/filter permuted)][3C], box = 64 x 128
+    CUtensorMap wg16;      // dilated-conv weights fp16(W 2^p) [2C (gate/filter permuted)][3C], box = 64 x 128
+    CUtensorMap wg8;       // e5m2 correction of the same, box = 128 x 128
     CUtensorMap wr[2];     // residual half of the output projection fp16 hi / lo [C][C], box = 64 x 128
+    CUtensorMap cp;        // conditioner projection + biases f32 [B][T][2C] (packed column order), box = 16 x 128, SWIZZLE_64B
+    CUtensorMap x;         // residual stream f32 [B][T][C], box = 16 x 128, SWIZZLE_64B (loaded and stored)
     int B, T;
     int tiles_per_batch;   // ceil(T / 256)
     int n_row_tiles;       // B * tiles_per_batch
     int dilation;
-    int a_rows;            // rows of the xa halo box (128 + 2 * max dilation, multiple of 8)
+    int a_rows;            // rows of the xa halo boxes (128 + 2 * max dilation, multiple of 8)
     int z_col0;            // first column of this layer in the z matrix
-    EpiParams gate;        // EPI_GATE parameters   (aux0 = conditioner projection, out_hi = z, ...)
-    EpiParams res;         // EPI_RES_SKIP parameters (f32_a = x, out_hi = next xa, dvec = next step embedding, ...)
+    int z_pitch;           // elements per row of the z matrix
+    __half* z_out;         // z matrix base
+    float* x_out;          // residual stream (same buffer the x boxes are loaded from)
+    __half* xa16_out;      // next layer's conv input (null after the last layer); NOT the buffer behind xa16 / xa8: other tiles
+                           // still read halo rows of this layer's input while this tile's rows are written
+    uint8_t* xa8_out;
+    const float* bias_r;   // [C] residual bias
+    const float* dvec;     // [C] next layer's step embedding (null after the last layer)
+    float gscale, rscale;  // 2^-p of the gate / residual weight packing
+    int flags;             // timing ablations (bit 0: no gate math)
     unsigned long long* trace;
 };
 
@@ -47,15 +69,6 @@ __device__ __forceinline__ LayerOp layer_op(int j, int cnt) {
     return LayerOp{0, q + 1, r == 0 ? 0 : 1};
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// Epilogues of the fused layer kernel.  Same arithmetic and data ownership as EPI_GATE / EPI_RES_SKIP of conv_gemm.cuh
-// (lane = two neighbouring columns of 16 rows after the shared-memory transpose), but software-pipelined ACROSS chunks
-// and ops: the fp32 operands a chunk needs from global memory (conditioner projection / residual stream) are loaded
-// into registers while the previous chunk -- possibly of the previous op -- is still doing its math and stores, so
-// the L2 round trip is off the critical path (the unfused epilogues exposed four of them per op and paced the kernel:
-// profiles/r01_g).
-// ---------------------------------------------------------------------------------------------
 #ifndef B200_GATE_MATH
 #define B200_GATE_MATH 2
 #endif
@@ -71,7 +84,7 @@ __device__ __forceinline__ float gate_act(float g, float f) {
     // fp16 rounding z gets anyway
     return fmaf(0.5f, tanh_approx(0.5f * g), 0.5f) * tanh_approx(f);
 #elif B200_GATE_MATH == 1
-    // three MUFU ops: a = e^-g, b = e^-2f, z = (1 - b) / ((1 + a)(1 + b)); arguments clamped so that nothing overflows to inf/inf
+    // three MUFU ops: a = e^-g, b = e^-2f, z = (1 - b) / ((1 + a)(1 + b)); arguments clamped so that nothing becomes inf/inf
     const float a = __expf(-fmaxf(g, -80.0f));
     const float b = __expf(-2.0f * fmaxf(f, -40.0f));
     return __fdividef(1.0f - b, (1.0f + a) * (1.0f + b));
@@ -80,88 +93,119 @@ __device__ __forceinline__ float gate_act(float g, float f) {
 #endif
 }
 
-// The epilogue warps walk a flat sequence of 16-column chunks (gate op: 4 per warp, residual op: 8 per warp).
-constexpr int kChunkCols = 16;
-constexpr int kGateChunks = 4, kResChunks = 8;
-constexpr int kStage16Pitch = 20;                              // floats; conflict-free 16-byte row writes, <= 2-way on the reads
-constexpr int kStage16Bytes = 32 * kStage16Pitch * 4;          // per warp
-struct EpiChunk {
-    int kind;          // 0 = gate op, 1 = residual op, -1 = past the end
-    int j, h, c;       // op index, channel half (gate ops), chunk index within the op
-    long long row_w;   // global row of the warp's lane 0
-    int rows_left;     // T - t_warp - (lane's row within a group of four): row 4*rp + r0 is valid iff 4*rp < rows_left
-};
-// after the transpose lane l owns columns cc, cc+1 of rows 4*rp + r0 (rp = 0..7): a warp instruction covers four 64-byte row segments
-struct LanePos16 {
-    int r0, cc;
-};
-__device__ __forceinline__ LanePos16 lane_pos16(int lane) { return LanePos16{lane >> 3, (lane & 7) * 2}; }
-
-// 32 rows x 16 accumulator columns starting at column c -> transposed ownership, scaled
-__device__ __forceinline__ void ld_chunk16_t(uint32_t tacc, int c, uint32_t stage_s, int lane, const LanePos16& lp, float2 (&o)[8], float scale) {
-    float v[16];
-    ld_acc16(tacc + c, v, scale);
-    const uint32_t wr = stage_s + lane * (kStage16Pitch * 4);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) sts128(wr + j * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    __syncwarp();
-    const uint32_t rd = stage_s + (lp.r0 * kStage16Pitch + lp.cc) * 4;
-#pragma unroll
-    for (int rp = 0; rp < 8; ++rp) o[rp] = lds64(rd + rp * (4 * kStage16Pitch * 4));
-    __syncwarp();
+// Two gated activations at once in half2 arithmetic: t = tanh.approx.f16x2 (one MUFU op for two values),
+// z = (0.5 t(g/2) + 0.5) * t(f).  gh = g / 2 (already halved), f: fp32 pre-activations.  The result is the fp16 pair that is
+// stored; its error (fp16 rounding of the tanh arguments and results, ~2^-10 relative) is of the size of the fp16 rounding
+// z gets in any case, and like it changes pseudo-randomly from step to step (no systematic part).
+__device__ __forceinline__ uint32_t gate_act_h2(float gh0, float gh1, float f0, float f1) {
+    const __half2 g = __floats2half2_rn(gh0, gh1), f = __floats2half2_rn(f0, f1);
+    uint32_t tg, tf;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tg) : "r"(*reinterpret_cast<const uint32_t*>(&g)));
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tf) : "r"(*reinterpret_cast<const uint32_t*>(&f)));
+    const __half2 half = __float2half2_rn(0.5f);
+    const __half2 sg = __hfma2(*reinterpret_cast<const __half2*>(&tg), half, half);
+    const __half2 z = __hmul2(sg, *reinterpret_cast<const __half2*>(&tf));
+    return *reinterpret_cast<const uint32_t*>(&z);
 }
 
-// issue the global loads of chunk k: gate = conditioner projection of the gate / filter columns, residual = x
-__device__ __forceinline__ void layer_epi_prefetch(const LayerArgs& a, const EpiChunk& k, int grp, const LanePos16& lp, float2 (&pa)[8],
-                                                   float2 (&pb)[8]) {
-    if (a.gate.flags & 1) {   // timing ablation: no global operand loads (results wrong)
-#pragma unroll
-        for (int rp = 0; rp < 8; ++rp) { pa[rp] = make_float2(0.f, 0.f); pb[rp] = make_float2(0.f, 0.f); }
-        return;
-    }
-    if (k.kind == 0) {
-        const int col = k.h * 256 + grp * 64 + k.c * kChunkCols + lp.cc;
-        const float* p = a.gate.aux0 + (k.row_w + lp.r0) * static_cast<long long>(a.gate.out_pitch) + col;
-        const long long st = 4LL * a.gate.out_pitch;
-#pragma unroll
-        for (int rp = 0; rp < 8; ++rp) {
-            if (4 * rp < k.rows_left) { pa[rp] = ld2(p + rp * st); pb[rp] = ld2(p + 128 + rp * st); }
-        }
-    } else if (k.kind == 1) {
-        const int col = grp * 128 + k.c * kChunkCols + lp.cc;
-        const float* p = a.res.f32_a + (k.row_w + lp.r0) * 256LL + col;
-#pragma unroll
-        for (int rp = 0; rp < 8; ++rp) {
-            if (4 * rp < k.rows_left) pa[rp] = ld2(p + rp * 1024);
-        }
-    }
+// ---------------------------------------------------------------------------------------------
+// shared-memory plan
+// ---------------------------------------------------------------------------------------------
+struct LayerSmem {
+    static constexpr int kASlotBytes = 144 * 128;              // halo tile: 144 rows x 128 B (64 fp16 or 128 e4m3 channels)
+    static constexpr int kAStages = 3;
+    static constexpr int kWSlotBytes = 128 * 128;              // weight tile: 128 N rows x 128 B
+    static constexpr int kWStages = 6;
+    static constexpr int kEBoxBytes = 128 * 16 * 4;            // epilogue box: 128 rows x 16 fp32
+#ifndef B200_ESTAGES
+#define B200_ESTAGES 9
+#endif
+    static constexpr int kEStages = B200_ESTAGES;
+    static constexpr int kVecBytes = 2 * 256 * 4;              // residual bias + next step embedding
+    static constexpr int kBarBytes = 512;
+    static constexpr int kOffW = kAStages * kASlotBytes;
+    static constexpr int kOffE = kOffW + kWStages * kWSlotBytes;
+    static constexpr int kOffVec = kOffE + kEStages * kEBoxBytes;
+    static constexpr int kOffBar = kOffVec + kVecBytes;
+    static constexpr int kTotal = kOffBar + kBarBytes + 1024;  // + manual 1024-byte alignment
+    static_assert(kTotal <= 227 * 1024, "shared memory budget");
+    static_assert((2 * kAStages + 2 * kWStages + 2 * kEStages + 6) * 8 + 8 <= kBarBytes, "barrier area too small");
+    static_assert(kOffW % 1024 == 0 && kOffE % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+};
+constexpr int kLayerThreads = 32 * 11;
+constexpr int kBoxesPerOp = 16;
+
+// byte offset of 16-byte chunk k (4 fp32 columns) of row r in a SWIZZLE_64B box
+__device__ __forceinline__ uint32_t ebox_off(int r, int k) { return static_cast<uint32_t>(r * 64 + ((k ^ ((r >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_half2_nc(float a, float b) {   // values known to be far inside the fp16 range
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {   // one instruction, out-of-range -> +-65504
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// sigmoid(2 gh) * tanh(f) with two MUFU ops: sigmoid(g) = 0.5 tanh(g / 2) + 0.5; tanh.approx.f32 has a relative error of 2^-11,
+// the size of the fp16 rounding z gets anyway (measured: 2.0e-3 max mel error after 100 steps against 1.3e-3 with exp/rcp)
+__device__ __forceinline__ float gate_half(float gh, float f) { return fmaf(0.5f, tanh_approx(gh), 0.5f) * tanh_approx(f); }
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+    return lo | (hi << 16);
+}
+__device__ __forceinline__ void tma_load_3d_local(uint32_t smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_dst), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* desc, uint32_t smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(desc), "r"(smem_src), "r"(c0), "r"(c1),
+                 "r"(c2)
+                 : "memory");
 }
 
-// LO8: the weight-correction term of the gate GEMM runs on the fp8 pipe (see below); 0 = two fp16 MMAs per product
-constexpr int kLayerSmemBytes = GemmSmem<256, 2, true>::kTotal + kEpiWarps * kStage16Bytes - GemmSmem<256, 2, true>::kXposeBytes;
-template <int LO8>
-__global__ void __launch_bounds__(kGemmThreads, 1) diffnet_layer_kernel(const __grid_constant__ LayerArgs args) {
-    using S = GemmSmem<256, 2, true>;
+template <int VARIANT>   // (a template only so that the header can be included from several translation units)
+__global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const __grid_constant__ LayerArgs args) {
+    using S = LayerSmem;
     constexpr int C = 256;
-    constexpr uint32_t kIdesc = umma_idesc_f16(2 * kTileM, 256, /*fp16=*/true);
+    constexpr uint32_t kIdesc16 = umma_idesc_f16(2 * kTileM, 256, /*fp16=*/true);
+    constexpr uint32_t kIdesc8 = umma_idesc_f8(2 * kTileM, 256, /*A e4m3*/ 0, /*B e5m2*/ 1);
     constexpr int kTileRows = 2 * kTileM;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + S::kAStages * S::kASlotBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOperandBytes);
+    const uint32_t smem_a = smem_u32(smem);
+    const uint32_t smem_w = smem_a + S::kOffW;
+    const uint32_t smem_e = smem_a + S::kOffE;
+    float* vec = reinterpret_cast<float*>(smem + S::kOffVec);        // [0,256) residual bias, [256,512) next step embedding
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
     uint64_t* afull_bar = bars;
     uint64_t* aempty_bar = afull_bar + S::kAStages;
-    uint64_t* bfull_bar = aempty_bar + S::kAStages;
-    uint64_t* bempty_bar = bfull_bar + S::kBStages;
-    uint64_t* tfull_bar = bempty_bar + S::kBStages;
+    uint64_t* wfull_bar = aempty_bar + S::kAStages;
+    uint64_t* wempty_bar = wfull_bar + S::kWStages;
+    uint64_t* efull_bar = wempty_bar + S::kWStages;
+    uint64_t* edone_bar = efull_bar + S::kEStages;
+    uint64_t* tfull_bar = edone_bar + S::kEStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* zfull_bar = tempty_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zfull_bar + 1);
-    float* xpose = reinterpret_cast<float*>(smem + S::kOperandBytes + S::kBarBytes);
-    static_assert((2 * S::kAStages + 2 * S::kBStages + 5) * 8 + 8 <= S::kBarBytes, "barrier area too small");
-    static_assert(kEpiWarps * kStage16Bytes <= S::kXposeBytes + 1024 + 1024, "transpose staging: see kLayerSmemBytes");
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zfull_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -169,15 +213,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) diffnet_layer_kernel(const __
     const int worker = static_cast<int>(blockIdx.x >> 1);
     const int n_workers = static_cast<int>(gridDim.x >> 1);
     const int cnt = (args.n_row_tiles - worker + n_workers - 1) / n_workers;   // row tiles of this CTA pair
+    const int n_ops = 3 * cnt;
 
     if (threadIdx.x == 32) {
         for (int s = 0; s < S::kAStages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); }
-        for (int s = 0; s < S::kBStages; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
+        for (int s = 0; s < S::kWStages; ++s) { mbar_init(&wfull_bar[s], 1); mbar_init(&wempty_bar[s], 1); }
+        for (int s = 0; s < S::kEStages; ++s) { mbar_init(&efull_bar[s], 1); mbar_init(&edone_bar[s], 4); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * kEpiWarps); }
-        mbar_init(zfull_bar, 2 * kEpiWarps);   // both gate epilogues of a row tile, every epilogue warp of THIS CTA
+        // z rows of local row tile n published: both gate epilogues, every epilogue warp of THIS CTA.  Two barriers (n & 1):
+        // a fast warp may publish tile n+1 before a slow one has published tile n, never tile n+2 (the accumulator hand-over
+        // keeps the warps within two ops of each other)
+        for (int a = 0; a < 2; ++a) mbar_init(&zfull_bar[a], 2 * kEpiWarps);
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {   // per-column vectors of the residual epilogue (weights / LUT: not written by the previous kernel)
+        const int c = threadIdx.x - 64;
+        vec[c] = args.bias_r[c];
+        vec[256 + c] = args.dvec ? args.dvec[c] : 0.0f;
+    }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -189,39 +243,46 @@ __global__ void __launch_bounds__(kGemmThreads, 1) diffnet_layer_kernel(const __
     const bool tr_on = args.trace != nullptr;
 
     if (warp == 0 && lane == 0) {
-        // ================= TMA producer (one per CTA) =================
-        int as = 0, bs = 0;
-        uint32_t aph = 0, bph = 0;
+        // ================= operand producer (one per CTA) =================
+        int as = 0, ws = 0;
+        uint32_t aph = 0, wph = 0;
         long long w_a = 0, w_b = 0, w_z = 0;
         const long long t_begin = tr_on ? clock64() : 0;
-        const uint32_t b_bytes = S::kBSlotBytes * 2;
-        for (int j = 0; j < 3 * cnt; ++j) {
+        auto load_a = [&](const CUtensorMap* map, uint32_t bytes, int c0, int row, int b) {
+            mbar_wait_tr(&aempty_bar[as], aph ^ 1, tr_on, w_a);
+            if (rank == 0) mbar_arrive_expect_tx(&afull_bar[as], bytes * 2);
+            tma_load_3d_pair(reinterpret_cast<void*>(smem + as * S::kASlotBytes), map, &afull_bar[as], c0, row, b);
+            if (++as == S::kAStages) { as = 0; aph ^= 1; }
+        };
+        auto load_w = [&](const CUtensorMap* map, int c0, int row) {
+            mbar_wait_tr(&wempty_bar[ws], wph ^ 1, tr_on, w_b);
+            if (rank == 0) mbar_arrive_expect_tx(&wfull_bar[ws], S::kWSlotBytes * 2);
+            tma_load_2d_pair(reinterpret_cast<void*>(smem + S::kOffW + ws * S::kWSlotBytes), map, &wfull_bar[ws], c0, row);
+            if (++ws == S::kWStages) { ws = 0; wph ^= 1; }
+        };
+        const uint32_t halo_bytes = static_cast<uint32_t>(args.a_rows) * 128;
+        for (int j = 0; j < n_ops; ++j) {
             const LayerOp op = layer_op(j, cnt);
-            const int kind = op.kind, n = op.n, h = op.h;
-            const int m = worker + n * n_workers;
+            const int m = worker + op.n * n_workers;
             const int b = m / args.tiles_per_batch;
             const int t0 = (m % args.tiles_per_batch) * kTileRows + rank * kTileM;
-            const int n_taps = kind == 0 ? 3 : 1;
-            const CUtensorMap* amap = kind == 0 ? &args.xa : &args.z;
-            const CUtensorMap* wmap = kind == 0 ? args.wg : args.wr;
-            const uint32_t a_bytes = (kind == 0 ? static_cast<uint32_t>(args.a_rows) : static_cast<uint32_t>(kTileM)) * kBlockK * 2 * 2;
-            const int a_col0 = kind == 0 ? 0 : args.z_col0;
-            const int a_row = kind == 0 ? t0 - args.dilation : t0;
-            const int wrow = (kind == 0 ? h * 256 : 0) + rank * 128;
-            if (kind == 1) mbar_wait_tr(zfull_bar, static_cast<uint32_t>(n & 1), tr_on, w_z);   // this CTA's z rows of tile n are in global memory
-            for (int kb = 0; kb < C / kBlockK; ++kb) {
-                mbar_wait_tr(&aempty_bar[as], aph ^ 1, tr_on, w_a);
-                if (rank == 0) mbar_arrive_expect_tx(&afull_bar[as], a_bytes);
-                tma_load_3d_pair(smem_a + as * S::kASlotBytes, amap, &afull_bar[as], a_col0 + kb * kBlockK, a_row, b);
-                if (++as == S::kAStages) { as = 0; aph ^= 1; }
-                for (int tp = 0; tp < n_taps; ++tp) {
-                    mbar_wait_tr(&bempty_bar[bs], bph ^ 1, tr_on, w_b);
-                    uint8_t* sb = smem_b + bs * S::kBSlotBytes;
-                    const int wc = tp * C + kb * kBlockK;
-                    if (rank == 0) mbar_arrive_expect_tx(&bfull_bar[bs], b_bytes);
-                    tma_load_2d_pair(sb, &wmap[0], &bfull_bar[bs], wc, wrow);
-                    tma_load_2d_pair(sb + S::kBPartBytes, &wmap[1], &bfull_bar[bs], wc, wrow);
-                    if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
+            if (op.kind == 0) {
+                const int wrow = op.h * 256 + rank * 128;
+                for (int k8 = 0; k8 < 2; ++k8) {
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int kb = 2 * k8 + kk;
+                        load_a(&args.xa16, halo_bytes, kb * 64, t0 - args.dilation, b);
+                        for (int tp = 0; tp < 3; ++tp) load_w(&args.wg16, tp * C + kb * 64, wrow);
+                    }
+                    load_a(&args.xa8, halo_bytes, k8 * 128, t0 - args.dilation, b);
+                    for (int tp = 0; tp < 3; ++tp) load_w(&args.wg8, tp * C + k8 * 128, wrow);
+                }
+            } else {
+                mbar_wait_tr(&zfull_bar[op.n & 1], static_cast<uint32_t>((op.n >> 1) & 1), tr_on, w_z);   // this CTA's z rows of tile n are in global memory
+                for (int kb = 0; kb < 4; ++kb) {
+                    load_a(&args.z, kTileM * 128, args.z_col0 + kb * 64, t0, b);
+                    load_w(&args.wr[0], kb * 64, rank * 128);
+                    load_w(&args.wr[1], kb * 64, rank * 128);
                 }
             }
         }
@@ -231,173 +292,242 @@ __global__ void __launch_bounds__(kGemmThreads, 1) diffnet_layer_kernel(const __
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
         // ================= MMA issuer (leader CTA) =================
-        int as = 0, bs = 0, it = 0;
-        uint32_t aph = 0, bph = 0;
+        int as = 0, ws = 0;
+        uint32_t aph = 0, wph = 0;
         long long w_t = 0, w_a = 0, w_b = 0;
         const long long t_begin = tr_on ? clock64() : 0;
-        for (int j = 0; j < 3 * cnt; ++j) {
-            const int kind = layer_op(j, cnt).kind;
-            const int acc = it & 1;
-            mbar_wait_tr(&tempty_bar[acc], ((it >> 1) & 1) ^ 1, tr_on, w_t);
+        uint32_t accumulate = 0;
+        uint32_t tacc = 0;
+        // four MMAs of one weight slot against the A tile at a_op (16-bit: K = 16 each, 8-bit: K = 32 each; both advance 32 bytes)
+        auto mma_slot = [&](uint32_t a_op, bool eight) {
+            mbar_wait_tr(&wfull_bar[ws], wph, tr_on, w_b);
             tc_fence_after();
-            const uint32_t tacc = tmem_base + acc * 256;
-            const int n_taps = kind == 0 ? 3 : 1;
-            const uint32_t tap_stride = kind == 0 ? static_cast<uint32_t>(args.dilation) * (kBlockK * 2) : 0;   // taps = row offsets 0, d, 2d of the halo tile
-            uint32_t accumulate = 0;
-            for (int kb = 0; kb < C / kBlockK; ++kb) {
-                mbar_wait_tr(&afull_bar[as], aph, tr_on, w_a);
-                tc_fence_after();
-                const uint32_t a_slot = smem_u32(smem_a + as * S::kASlotBytes);
-                for (int tp = 0; tp < n_taps; ++tp) {
-                    mbar_wait_tr(&bfull_bar[bs], bph, tr_on, w_b);
-                    tc_fence_after();
-                    const uint32_t a_op = a_slot + tp * tap_stride;
-                    const uint32_t b_hi = smem_u32(smem_b + bs * S::kBSlotBytes);
-                    const uint32_t b_lo = b_hi + S::kBPartBytes;
+            const uint32_t b_op = smem_w + ws * S::kWSlotBytes;
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t da = umma_smem_desc<128>(a_op + k * 32);
-                        umma_f16_pair(tacc, da, umma_smem_desc<128>(b_hi + k * 32), kIdesc, accumulate);
-                        umma_f16_pair(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
-                        accumulate = 1;
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t da = umma_smem_desc<128>(a_op + k * 32), db = umma_smem_desc<128>(b_op + k * 32);
+                if (eight) umma_f8_pair(tacc, da, db, kIdesc8, accumulate);
+                else umma_f16_pair(tacc, da, db, kIdesc16, accumulate);
+                accumulate = 1;
+            }
+            umma_commit_pair(&wempty_bar[ws]);
+            if (++ws == S::kWStages) { ws = 0; wph ^= 1; }
+        };
+        auto wait_a = [&]() {
+            mbar_wait_tr(&afull_bar[as], aph, tr_on, w_a);
+            tc_fence_after();
+            return smem_a + as * S::kASlotBytes;
+        };
+        auto free_a = [&]() {
+            umma_commit_pair(&aempty_bar[as]);
+            if (++as == S::kAStages) { as = 0; aph ^= 1; }
+        };
+        const uint32_t tap_stride = static_cast<uint32_t>(args.dilation) * 128;   // taps = rows 0, d, 2d of the halo tile
+        for (int j = 0; j < n_ops; ++j) {
+            const int kind = layer_op(j, cnt).kind;
+            const int acc = j & 1;
+            mbar_wait_tr(&tempty_bar[acc], ((j >> 1) & 1) ^ 1, tr_on, w_t);
+            tc_fence_after();
+            tacc = tmem_base + acc * 256;
+            accumulate = 0;
+            if (kind == 0) {
+                for (int k8 = 0; k8 < 2; ++k8) {
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint32_t a_slot = wait_a();
+                        for (int tp = 0; tp < 3; ++tp) mma_slot(a_slot + tp * tap_stride, false);
+                        free_a();
                     }
-                    umma_commit_pair(&bempty_bar[bs]);
-                    if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
+                    const uint32_t a_slot = wait_a();
+                    for (int tp = 0; tp < 3; ++tp) mma_slot(a_slot + tp * tap_stride, true);
+                    free_a();
                 }
-                umma_commit_pair(&aempty_bar[as]);
-                if (++as == S::kAStages) { as = 0; aph ^= 1; }
+            } else {
+                for (int kb = 0; kb < 4; ++kb) {
+                    const uint32_t a_slot = wait_a();
+                    mma_slot(a_slot, false);
+                    mma_slot(a_slot, false);
+                    free_a();
+                }
             }
             umma_commit_pair(&tfull_bar[acc]);
-            ++it;
         }
         if (tr_on) {
             unsigned long long* t = args.trace + blockIdx.x * 16;
             t[0] = clock64() - t_begin; t[1] = w_t; t[2] = w_a; t[3] = w_b; t[10] = cnt;
         }
-    } else if (warp >= 2 && warp < 2 + kEpiWarps) {
-        // ================= Epilogue warps =================
-        const int quad = warp & 3;
-        const int grp = (warp - 2) >> 2;
-        const uint32_t stage_s = smem_u32(reinterpret_cast<uint8_t*>(xpose) + (warp - 2) * kStage16Bytes);
-        const LanePos16 lp = lane_pos16(lane);
-        const uint32_t tempty_remote0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
-        const bool tr = tr_on && warp == 2 && lane == 0;
-        long long w_f = 0, t_gate = 0, t_res = 0, t_op = 0;
-        const long long t_begin = tr ? clock64() : 0;
-        const int n_ops = 3 * cnt;
-        const float gsc = args.gate.acc_scale != 0.0f ? args.gate.acc_scale : 1.0f;
-        const float rsc = args.res.acc_scale != 0.0f ? args.res.acc_scale : 1.0f;
-        const float rs2 = 0.70710678118654752440f;
-
-        auto chunk_at = [&](int j, int c) {
-            EpiChunk k;
-            k.j = j; k.c = c; k.h = 0; k.row_w = 0; k.rows_left = 0; k.kind = -1;
-            if (j >= n_ops) return k;
+    } else if (warp == 10 && lane == 0) {
+        // ================= epilogue-operand producer: cp / x boxes in, updated x boxes out =================
+        // box q of this CTA: op j = q / 16, i = q % 16.  gate op: chunk c = i / 4, column group g = (i / 2) % 2, i % 2 = gate / filter
+        // columns of cp; residual op: chunk c = i / 2, group g = i % 2 of x.  Slot = q % kEStages.
+        const int n_boxes = n_ops * kBoxesPerOp;
+        long long w_e = 0;
+        auto box_coords = [&](int q, int& kind, int& col, int& row, int& b) {
+            const int j = q / kBoxesPerOp, i = q % kBoxesPerOp;
             const LayerOp op = layer_op(j, cnt);
             const int m = worker + op.n * n_workers;
-            const int b = m / args.tiles_per_batch;
-            const int t_warp = (m % args.tiles_per_batch) * kTileRows + rank * kTileM + quad * 32;
-            k.kind = op.kind; k.h = op.h;
-            k.row_w = static_cast<long long>(b) * args.T + t_warp;
-            k.rows_left = args.T - t_warp - lp.r0;
-            return k;
+            b = m / args.tiles_per_batch;
+            row = (m % args.tiles_per_batch) * kTileRows + rank * kTileM;
+            kind = op.kind;
+            if (kind == 0) col = op.h * 256 + ((i >> 1) & 1) * 64 + (i >> 2) * 16 + (i & 1) * 128;
+            else col = (i & 1) * 128 + (i >> 1) * 16;
         };
-        auto next_of = [&](const EpiChunk& k) {
-            const int n_chunks = k.kind == 0 ? kGateChunks : kResChunks;
-            return (k.c + 1 < n_chunks) ? chunk_at(k.j, k.c + 1) : chunk_at(k.j + 1, 0);
-        };
-        // one chunk: its global operands are already in (pa, pb)
-        auto do_chunk = [&](const EpiChunk& k, float2 (&pa)[8], float2 (&pb)[8]) {
-            const int acc = k.j & 1;
-            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
-            if (k.c == 0) {
-                // L2 prefetch of the fp32 rows the same kind of op will read for the next row tile
-                const LayerOp op = layer_op(k.j, cnt);
-                if (op.n + 1 < cnt) {
-                    const int m2 = worker + (op.n + 1) * n_workers;
-                    const int b2 = m2 / args.tiles_per_batch;
-                    const int t2 = (m2 % args.tiles_per_batch) * kTileRows + rank * kTileM + quad * 32;
-                    const int rows = min(32, args.T - t2);
-                    const long long row0 = static_cast<long long>(b2) * args.T + t2;
-                    for (int idx = lane; idx < rows * 4; idx += 32) {
-                        const int r = idx >> 2, q = idx & 3;
-                        const float* p = k.kind == 0
-                            ? args.gate.aux0 + (row0 + r) * static_cast<long long>(args.gate.out_pitch) + op.h * 256 + grp * 64 + (q >> 1) * 128 + (q & 1) * 32
-                            : args.res.f32_a + (row0 + r) * 256LL + grp * 128 + q * 32;
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                    }
-                }
-                mbar_wait_tr(&tfull_bar[acc], (k.j >> 1) & 1, tr, w_f);
-                tc_fence_after();
-                if (tr) t_op = clock64();
+        for (int q = 0; q < n_boxes; ++q) {
+            const int s = q % S::kEStages;
+            const uint32_t dst = smem_e + s * S::kEBoxBytes;
+            if (q >= S::kEStages) mbar_wait_tr(&edone_bar[s], ((q / S::kEStages) - 1) & 1, tr_on, w_e);   // previous occupant consumed by its four warps
+            if (q < n_boxes) {
+                int kind, col, row, b;
+                box_coords(q, kind, col, row, b);
+                mbar_arrive_expect_tx(&efull_bar[s], S::kEBoxBytes);
+                tma_load_3d_local(dst, kind == 0 ? &args.cp : &args.x, &efull_bar[s], col, row, b);
             }
-            if (k.kind == 0) {
-                // ---- gate: columns [cg, cg+16) = gate pre-activations, +128 = filter pre-activations of the same channels
-                const int cg = grp * 64 + k.c * kChunkCols;
-                float2 g[8], f[8];
-                ld_chunk16_t(tacc, cg, stage_s, lane, lp, g, gsc);
-                ld_chunk16_t(tacc, 128 + cg, stage_s, lane, lp, f, gsc);
-                __nv_bfloat16* zp = args.gate.out_hi + (k.row_w + lp.r0) * static_cast<long long>(args.gate.act_pitch) + args.gate.out_col0 +
-                                    k.h * 128 + cg + lp.cc;
-                const long long st = 4LL * args.gate.act_pitch;
-#pragma unroll
-                for (int rp = 0; rp < 8; ++rp) {
-                    if (4 * rp < k.rows_left && !(args.gate.flags & 4))
-                        st_half2(make_float2(gate_act(g[rp].x + pa[rp].x, f[rp].x + pb[rp].x), gate_act(g[rp].y + pa[rp].y, f[rp].y + pb[rp].y)),
-                                 zp + rp * st);
-                }
-            } else {
-                // ---- residual: x <- (x + W_res z + b) / sqrt(2)  (net.py:76-78); fp16(x + d_next) is the next layer's conv input
-                const int cl = grp * 128 + k.c * kChunkCols + lp.cc;
-                float2 o[8];
-                ld_chunk16_t(tacc, grp * 128 + k.c * kChunkCols, stage_s, lane, lp, o, rsc);
-                const float2 bias = ldg2(args.res.bias + cl);
-                float2 d = make_float2(0.f, 0.f);
-                if (args.res.dvec != nullptr) d = ldg2(args.res.dvec + cl);
-                const long long off0 = (k.row_w + lp.r0) * 256LL + cl;
-#pragma unroll
-                for (int rp = 0; rp < 8; ++rp) {
-                    if (4 * rp < k.rows_left && !(args.gate.flags & 4)) {
-                        const long long off = off0 + rp * 1024;
-                        const float2 y = make_float2((pa[rp].x + o[rp].x + bias.x) * rs2, (pa[rp].y + o[rp].y + bias.y) * rs2);
-                        st2(args.res.f32_a + off, y);
-                        if (args.res.dvec != nullptr) st_half2(make_float2(y.x + d.x, y.y + d.y), args.res.out_hi + off);
-                    }
-                }
-            }
-            if (k.c + 1 == (k.kind == 0 ? kGateChunks : kResChunks)) {   // op done: hand the accumulator back
-                if (k.kind == 0) {
-                    // the z rows written above are read back by this CTA's TMA loads of R(n): order the generic-proxy stores
-                    // before the async proxy, then signal the producer
-                    asm volatile("fence.proxy.async.global;" ::: "memory");
-                    __threadfence_block();
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (k.kind == 0) mbar_arrive(zfull_bar);
-                    mbar_arrive_remote(tempty_remote0 + acc * 8);
-                }
-                if (tr) { if (k.kind == 0) t_gate += clock64() - t_op; else t_res += clock64() - t_op; }
-            }
-        };
-
-        // ping-pong operand registers: the loads of chunk q+1 are issued before chunk q is processed
-        float2 a0[8], b0[8], a1[8], b1[8];
-        EpiChunk k0 = chunk_at(0, 0);
-        layer_epi_prefetch(args, k0, grp, lp, a0, b0);
-        while (k0.kind >= 0) {
-            const EpiChunk k1 = next_of(k0);
-            layer_epi_prefetch(args, k1, grp, lp, a1, b1);
-            do_chunk(k0, a0, b0);
-            if (k1.kind < 0) break;
-            k0 = next_of(k1);
-            layer_epi_prefetch(args, k0, grp, lp, a0, b0);
-            do_chunk(k1, a1, b1);
         }
+        if (tr_on) args.trace[blockIdx.x * 16 + 13] = w_e;
+    } else if (warp >= 2 && warp < 2 + kEpiWarps) {
+        // ================= epilogue warps: thread = one accumulator row =================
+        const int quad = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const int r_box = quad * 32 + lane;                 // row of this thread in the CTA's 128-row boxes
+        const uint32_t tempty_remote0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
+        const bool tr = tr_on && warp == 2 && lane == 0;
+        long long w_f = 0, w_e = 0, t_gate = 0, t_res = 0;
+        const long long t_begin = tr ? clock64() : 0;
+        const float rs2 = 0.70710678118654752440f;
+        const uint32_t vec_s = smem_u32(vec);
+        uint32_t xo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xo[k] = ebox_off(r_box, k);
+
+        bool z_pending = false;   // z rows stored by the previous gate op, not yet fenced / signalled
+        int z_tile = 0;           // ... and the local row tile they belong to
+        auto publish_z = [&]() {
+            // the z rows are read back by this CTA's TMA loads of R(n): order the generic-proxy stores before the async
+            // proxy, then signal the producer.  Deferred to the start of the next op (the stores have drained by then and
+            // the fence returns at once) unless that op is the residual GEMM that needs them.
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&zfull_bar[z_tile & 1]);
+            z_pending = false;
+        };
+        for (int j = 0; j < n_ops; ++j) {
+            const LayerOp op = layer_op(j, cnt);
+            const int acc = j & 1;
+            const int m = worker + op.n * n_workers;
+            const int b = m / args.tiles_per_batch;
+            const int t = (m % args.tiles_per_batch) * kTileRows + rank * kTileM + r_box;   // this thread's row in the batch item
+            const bool row_ok = t < args.T;
+            const long long row = static_cast<long long>(b) * args.T + t;
+            mbar_wait_tr(&tfull_bar[acc], (j >> 1) & 1, tr, w_f);
+            tc_fence_after();
+            const long long t_op = tr ? clock64() : 0;
+            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+            const int q_op = j * kBoxesPerOp;
+            if (op.kind == 0) {
+                // ---- gate: z = sigmoid(acc_g + cp_g) * tanh(acc_f + cp_f)   (net.py:71-74)
+                // (loops kept rolled: with the four roles' code paths resident the unrolled epilogue stalled on instruction fetch)
+                const float hs = 0.5f * args.gscale;
+                __half* zrow = args.z_out + row * args.z_pitch + args.z_col0 + op.h * 128;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int cg = grp * 64 + c * 16;          // gate columns [cg, cg+16), filter columns +128
+                    const int q = q_op + 4 * c + 2 * grp;      // boxes q (cp of the gate columns), q + 1 (filter columns)
+                    const int sg = q % S::kEStages, sf = (q + 1) % S::kEStages;
+                    uint32_t vg[16], vf[16];
+                    __syncwarp();
+                    tmem_ld16(tacc + cg, vg);
+                    tmem_ld16(tacc + 128 + cg, vf);
+                    mbar_wait_tr(&efull_bar[sg], (q / S::kEStages) & 1, tr, w_e);
+                    mbar_wait_tr(&efull_bar[sf], ((q + 1) / S::kEStages) & 1, tr, w_e);
+                    float4 pg[4], pf[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        pg[k] = lds128(smem_e + sg * S::kEBoxBytes + xo[k]);
+                        pf[k] = lds128(smem_e + sf * S::kEBoxBytes + xo[k]);
+                    }
+#ifndef B200_PUBLISH_NOW
+                    if (c == 1 && z_pending) publish_z();   // the previous gate op's z rows (its stores have long drained)
+#endif
+                    tmem_ld_wait16x2(vg, vf);
+                    uint32_t zz[8];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // sigmoid(g) = 0.5 tanh(g/2) + 0.5: the gate pre-activations are formed already halved
+                        const float g0 = fmaf(__uint_as_float(vg[4 * k]), hs, 0.5f * pg[k].x), g1 = fmaf(__uint_as_float(vg[4 * k + 1]), hs, 0.5f * pg[k].y);
+                        const float g2 = fmaf(__uint_as_float(vg[4 * k + 2]), hs, 0.5f * pg[k].z), g3 = fmaf(__uint_as_float(vg[4 * k + 3]), hs, 0.5f * pg[k].w);
+                        const float f0 = fmaf(__uint_as_float(vf[4 * k]), args.gscale, pf[k].x), f1 = fmaf(__uint_as_float(vf[4 * k + 1]), args.gscale, pf[k].y);
+                        const float f2 = fmaf(__uint_as_float(vf[4 * k + 2]), args.gscale, pf[k].z), f3 = fmaf(__uint_as_float(vf[4 * k + 3]), args.gscale, pf[k].w);
+                        zz[2 * k] = pack_half2_nc(gate_half(g0, f0), gate_half(g1, f1));
+                        zz[2 * k + 1] = pack_half2_nc(gate_half(g2, f2), gate_half(g3, f3));
+                    }
+                    // hand the boxes back only now: the arithmetic above could not issue before the ld.shared data had arrived.
+                    // (Signalling right behind the ld.shared instructions let the TMA refill overtake loads still queued
+                    // behind this warp's stores -- a rare 32-row corruption.)
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(&edone_bar[sg]); mbar_arrive(&edone_bar[sf]); }
+                    if (row_ok) stg256(zrow + cg, zz);
+                }
+                z_pending = true;
+                z_tile = op.n;
+#ifdef B200_PUBLISH_NOW
+                publish_z();
+#endif
+                // R(n) directly follows the second gate op of the last row tile: it cannot wait for a deferred signal
+                if (j + 1 < n_ops && layer_op(j + 1, cnt).kind == 1 && layer_op(j + 1, cnt).n == op.n) publish_z();
+            } else {
+                // ---- residual: x <- (x + W_res z + b) / sqrt(2)  (net.py:76-78); fp16 / e4m3 of (x + d_next) feed the next layer's conv
+                const bool has_next = args.xa16_out != nullptr;
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    const int cl = grp * 128 + c * 16;
+                    const int q = q_op + 2 * c + grp;
+                    const int sx = q % S::kEStages;
+                    const uint32_t box = smem_e + sx * S::kEBoxBytes;
+                    uint32_t v[16];
+                    __syncwarp();
+                    tmem_ld16(tacc + cl, v);
+                    mbar_wait_tr(&efull_bar[sx], (q / S::kEStages) & 1, tr, w_e);
+                    float4 x[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) x[k] = lds128(box + xo[k]);
+#ifndef B200_PUBLISH_NOW
+                    if (c == 1 && z_pending) publish_z();
+#endif
+                    tmem_ld_wait16(v);
+                    uint32_t xs[16], h16[8], h8[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 bb = lds128(vec_s + (cl + 4 * k) * 4), dd = lds128(vec_s + (256 + cl + 4 * k) * 4);
+                        const float y0 = (x[k].x + fmaf(__uint_as_float(v[4 * k]), args.rscale, bb.x)) * rs2;
+                        const float y1 = (x[k].y + fmaf(__uint_as_float(v[4 * k + 1]), args.rscale, bb.y)) * rs2;
+                        const float y2 = (x[k].z + fmaf(__uint_as_float(v[4 * k + 2]), args.rscale, bb.z)) * rs2;
+                        const float y3 = (x[k].w + fmaf(__uint_as_float(v[4 * k + 3]), args.rscale, bb.w)) * rs2;
+                        xs[4 * k] = __float_as_uint(y0); xs[4 * k + 1] = __float_as_uint(y1); xs[4 * k + 2] = __float_as_uint(y2); xs[4 * k + 3] = __float_as_uint(y3);
+                        h16[2 * k] = pack_half2_sat(y0 + dd.x, y1 + dd.y);     // saturating: an out-of-range activation must not become inf
+                        h16[2 * k + 1] = pack_half2_sat(y2 + dd.z, y3 + dd.w);
+                        h8[k] = pack_e4m3x4(y0 + dd.x, y1 + dd.y, y2 + dd.z, y3 + dd.w);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&edone_bar[sx]);   // after the arithmetic that consumed the box (see the gate loop)
+                    if (row_ok) {
+                        // one row = 64 contiguous bytes of x (two full sectors), 32 of the fp16 and 16 of the e4m3 conv input
+                        stg256(args.x_out + row * C + cl, reinterpret_cast<const uint32_t(&)[8]>(xs[0]));
+                        stg256(args.x_out + row * C + cl + 8, reinterpret_cast<const uint32_t(&)[8]>(xs[8]));
+                        if (has_next) {
+                            stg256(args.xa16_out + row * C + cl, h16);
+                            *reinterpret_cast<uint4*>(args.xa8_out + row * C + cl) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty_remote0 + acc * 8);
+            if (tr) { if (op.kind == 0) t_gate += clock64() - t_op; else t_res += clock64() - t_op; }
+        }
+        if (z_pending) publish_z();
         if (tr) {
-            unsigned long long* t = args.trace + blockIdx.x * 16;
-            t[7] = clock64() - t_begin; t[8] = w_f; t[11] = t_gate; t[12] = t_res;
+            unsigned long long* tt = args.trace + blockIdx.x * 16;
+            tt[7] = clock64() - t_begin; tt[8] = w_f; tt[11] = t_gate; tt[12] = t_res; tt[14] = w_e;
         }
     }
 

@@ -138,7 +138,13 @@ struct DiffusionPlan::Workspace {
     int B = 0, T = 0;
     DevBuf cp;   // f32 [L][rows][2C]: conditioner projection + biases of every layer (step-invariant)
     DevBuf xt, xin_hi, xin_lo, cond_hi, cond_lo, xres, xa_hi, xa_lo, z_hi, z_lo, s_hi, s_lo, h_hi, h_lo, mel, mel2ph, eps;
+    // fused layer kernel: a layer writes the NEXT layer's conv input while neighbouring tiles still read halo rows of its own
+    // input, so the conv input ping-pongs between two buffers (layer l reads [l & 1]: xa_hi / xa8 are [0], these are [1])
+    DevBuf xa8, xa16_b, xa8_b;   // xa8: e4m3 copy of the conv input (A operand of the fp8 correction MMAs)
+    CUtensorMap m_xa16_b, m_xa8_b;
     CUtensorMap m_xin[2], m_cond[2], m_xa[2], m_z[2], m_s[2], m_h[2];
+    CUtensorMap m_xa8, m_x;          // fused layer kernel: 8-bit conv input, fp32 residual stream (16 x 128 boxes)
+    std::vector<CUtensorMap> m_cp;   // ... and the conditioner projection of every layer
     cudaGraphExec_t graph = nullptr;
     bool graph_has_mask = false;
     ~Workspace() {
@@ -337,6 +343,17 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
     mk(w->m_z, w->z_hi, w->z_lo, cfg.residual_layers * C);
     mk(w->m_s, w->s_hi, w->s_lo, C);
     mk(w->m_h, w->h_hi, w->h_lo, C);
+    if (use_fused) {
+        w->xa8.alloc(rows * C);
+        w->m_xa8 = make_act8_tmap(w->xa8.p, B, T, C, kXaBoxRows);
+        w->xa16_b.alloc(rows * C * 2);
+        w->xa8_b.alloc(rows * C);
+        w->m_xa16_b = make_act_tmap(w->xa16_b.p, B, T, C, 0, kXaBoxRows);
+        w->m_xa8_b = make_act8_tmap(w->xa8_b.p, B, T, C, kXaBoxRows);
+        w->m_x = make_f32_tmap(w->xres.p, B, T, C);
+        for (int l = 0; l < cfg.residual_layers; ++l)
+            w->m_cp.push_back(make_f32_tmap(w->cp.as<float>() + static_cast<size_t>(l) * rows * 2 * C, B, T, 2 * C));
+    }
     auto& ref = *w;
     ws[key] = std::move(w);
     return ref;
@@ -409,20 +426,36 @@ ConvGemmArgs DiffusionPlan::resskip_args(Workspace& w, int l, const float* lut_t
 }
 
 // one whole ResidualBlock: gate GEMM of both channel halves + residual GEMM per 256-row tile (diffnet_layer.cuh)
-static LayerArgs fused_args(const ConvGemmArgs& g, const ConvGemmArgs& r, int dilation, int z_col0) {
+LayerArgs DiffusionPlan::fused_args(Workspace& w, int l, const float* lut_t) {
+    const int C = cfg.residual_channels, L = cfg.residual_layers;
+    Layer& ly = layers[l];
     LayerArgs a{};
-    a.xa = g.amap[0];
-    a.z = r.amap[0];
-    a.wg[0] = g.wmap[0]; a.wg[1] = g.wmap[1];
-    a.wr[0] = r.wmap[0]; a.wr[1] = r.wmap[1];
-    a.B = g.B; a.T = g.L;
-    a.tiles_per_batch = (g.L + 2 * kTileM - 1) / (2 * kTileM);
+    a.xa16 = (l & 1) ? w.m_xa16_b : w.m_xa[0];
+    a.xa8 = (l & 1) ? w.m_xa8_b : w.m_xa8;
+    a.z = w.m_z[0];
+    CUtensorMap unused;
+    ly.g1.maps(128, a.wg16, unused);
+    a.wg8 = ly.g1.map8();
+    ly.g2.maps(128, a.wr[0], a.wr[1]);
+    a.cp = w.m_cp[l];
+    a.x = w.m_x;
+    a.B = w.B;
+    a.T = w.T;
+    a.tiles_per_batch = (w.T + 2 * kTileM - 1) / (2 * kTileM);
     a.n_row_tiles = a.B * a.tiles_per_batch;
-    a.dilation = dilation;
-    a.a_rows = g.a_rows;
-    a.z_col0 = z_col0;
-    a.gate = g.epi;
-    a.res = r.epi;
+    a.dilation = ly.dilation;
+    a.a_rows = kXaBoxRows;
+    a.z_col0 = l * C;
+    a.z_pitch = L * C;
+    a.z_out = w.z_hi.as<__half>();
+    a.x_out = w.xres.as<float>();
+    a.xa16_out = (l + 1 < L) ? ((l & 1) ? w.xa_hi.as<__half>() : w.xa16_b.as<__half>()) : nullptr;
+    a.xa8_out = (l + 1 < L) ? ((l & 1) ? w.xa8.as<uint8_t>() : w.xa8_b.as<uint8_t>()) : nullptr;
+    a.bias_r = ly.g2_bias.as<float>();
+    a.dvec = (l + 1 < L) ? lut_t + static_cast<size_t>(l + 1) * C : nullptr;
+    a.gscale = ly.g1.acc_scale;
+    a.rscale = ly.g2.acc_scale;
+    if (const char* ab = std::getenv("BSG_ABLATE")) a.flags = std::atoi(ab);   // timing experiments only (wrong results)
     return a;
 }
 
@@ -460,7 +493,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
     auto run = [&](int n) {
         for (int i = 0; i < n; ++i) {
             const int l = i % L;
-            if (which == 3) launch_diffnet_layer(fused_args(gate_args(w, l), resskip_args(w, l, lut.as<float>()), layers[l].dilation, l * cfg.residual_channels), st);
+            if (which == 3) launch_diffnet_layer(fused_args(w, l, lut.as<float>()), st);
             else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
             else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
             else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
@@ -485,7 +518,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
         ConvGemmArgs a = which == 0 ? gate_args(w, 1) : (which == 1 ? resskip_args(w, 1, lut.as<float>()) : skipsum_args(w));
         a.trace = tb.as<unsigned long long>();
         if (which == 3) {
-            LayerArgs la = fused_args(gate_args(w, 1), resskip_args(w, 1, lut.as<float>()), layers[1].dilation, cfg.residual_channels);
+            LayerArgs la = fused_args(w, 1, lut.as<float>());
             la.trace = tb.as<unsigned long long>();
             launch_diffnet_layer(la, st);
         } else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, a, st, gate_mode);
@@ -509,8 +542,8 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
                          which, s[0] / n_mma, s[10] / n_mma, s[1] / n_mma, s[2] / n_mma, s[3] / n_mma, s[4] / n_cta, s[5] / n_cta, s[6] / n_cta,
                          s[7] / n_cta, s[8] / n_cta);
         if (which == 3 && n_cta)
-            std::fprintf(stderr, "TRACE fused layer: producer waits for z %.0f clk | epilogue warp busy in gate ops %.0f, in residual ops %.0f (row tiles %.2f)\n",
-                         s[9] / n_cta, s[11] / n_cta, s[12] / n_cta, n_mma ? s[10] / n_mma : 0.0);
+            std::fprintf(stderr, "TRACE fused layer: producer waits for z %.0f clk | epilogue warp busy in gate ops %.0f, in residual ops %.0f, of which waiting for cp/x boxes %.0f | box producer waits for consumers %.0f (row tiles %.2f)\n",
+                         s[9] / n_cta, s[11] / n_cta, s[12] / n_cta, s[14] / n_cta, s[13] / n_cta, n_mma ? s[10] / n_mma : 0.0);
     }
     return ms / static_cast<float>(reps);
 }
@@ -536,12 +569,14 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         a.epi.out_fp16 = terms == 2;
         a.epi.dvec = lut_t;
         a.epi.out_pitch = C;
+        a.epi.out8 = use_fused ? w.xa8.as<uint8_t>() : nullptr;
         launch_conv_gemm(256, terms_side, EPI_INPROJ, a, st);
         ++launches, ++g_launch_count;
     }
+    static const int fuse_layers = [] { const char* e = std::getenv("BSG_FUSE_LAYERS"); return e ? std::atoi(e) : 1 << 30; }();   // debugging: even count
     for (int l = 0; l < L; ++l) {
-        if (use_fused) {
-            launch_diffnet_layer(fused_args(gate_args(w, l), resskip_args(w, l, lut_t), layers[l].dilation, l * C), st);
+        if (use_fused && l < fuse_layers) {
+            launch_diffnet_layer(fused_args(w, l, lut_t), st);
             ++launches, ++g_launch_count;
             continue;
         }

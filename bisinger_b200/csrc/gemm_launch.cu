@@ -20,7 +20,8 @@ EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 
-CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool bytes) {
+CUtensorMap make_tmap_ex(const void* base, int kind, int swizzle, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box) {
     CUtensorMap m;
     cuuint64_t gdim[5];
     cuuint64_t gstr[4];
@@ -29,11 +30,15 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     B200_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base must be 16-byte aligned");
     for (int i = 0; i + 1 < rank; ++i) B200_CHECK(gstr[i] % 16 == 0, "tensor map strides must be multiples of 16 bytes");
-    CUresult r = get_encode_tiled()(&m, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                                    gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapDataType dt = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    const CUtensorMapSwizzle sw = swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = get_encode_tiled()(&m, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bx, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
     return m;
+}
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool bytes) {
+    return make_tmap_ex(base, bytes ? 1 : 0, 128, rank, dims, strides_bytes, box);
 }
 
 int device_sm_count() {
@@ -113,20 +118,19 @@ void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
 
 // One fused DiffNet layer (diffnet_layer.cuh): CTA pairs over the 256-row tiles, persistent.
 void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream) {
-    using S = GemmSmem<256, 2, true>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(diffnet_layer_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes); });
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(diffnet_layer_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayerSmem::kTotal); });
     B200_CUDA(attr_err);
     static int sms = 0;
     if (sms == 0) sms = device_sm_count();
     if (args.n_row_tiles <= 0) return;
-    B200_CHECK(args.a_rows >= kTileM && args.a_rows <= S::kASlotRows && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
+    B200_CHECK(args.a_rows >= kTileM && args.a_rows * 128 <= LayerSmem::kASlotBytes && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
     const int pairs = sms / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * (args.n_row_tiles < pairs ? args.n_row_tiles : pairs));
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = kLayerSmemBytes;
+    cfg.blockDim = dim3(kLayerThreads);
+    cfg.dynamicSmemBytes = LayerSmem::kTotal;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;

@@ -48,6 +48,7 @@ private:
     ConvGemmArgs gate_args(Workspace& w, int l);
     ConvGemmArgs resskip_args(Workspace& w, int l, const float* lut_t);
     ConvGemmArgs skipsum_args(Workspace& w);
+    struct LayerArgs fused_args(Workspace& w, int l, const float* lut_t);
     void enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail, cudaStream_t st);
 
     std::vector<Layer> layers;

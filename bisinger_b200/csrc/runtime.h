@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -96,6 +97,22 @@ EncodeTiledFn get_encode_tiled();
 CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                            bool bytes = false);
 
+// general form: kind 0 = 16-bit, 1 = 8-bit, 2 = fp32 elements; swizzle 128 or 64 (bytes)
+CUtensorMap make_tmap_ex(const void* base, int kind, int swizzle, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+// 8-bit activations [B][L][C], box = 128 channels (128 bytes) x box_rows rows
+inline CUtensorMap make_act8_tmap(const void* base, int B, int L, int C, int box_rows) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(C) * L};
+    const uint32_t box[3] = {128, static_cast<uint32_t>(box_rows), 1};
+    return make_tmap_ex(base, 1, 128, 3, dims, strides, box);
+}
+// fp32 rows [B][L][C] read / written by the epilogue through shared memory: box = 16 columns (64 bytes, SWIZZLE_64B) x 128 rows
+inline CUtensorMap make_f32_tmap(const void* base, int B, int L, int C) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(C) * 4, static_cast<uint64_t>(C) * 4 * L};
+    const uint32_t box[3] = {16, 128, 1};
+    return make_tmap_ex(base, 2, 64, 3, dims, strides, box);
+}
 // activations [B][L][C] (channels-last), box = 64 channels x box_rows rows (the halo tile of one k-block)
 inline CUtensorMap make_act_tmap(const void* base, int B, int L, int C, int row_pitch_elems = 0, int box_rows = kTileM) {
     if (row_pitch_elems == 0) row_pitch_elems = C;
@@ -166,6 +183,19 @@ inline float f16_bits_to_f32(uint16_t b) {
 // Packed (hi, lo) weight matrix on the device: bf16 pair (bf16 / bf16x3 modes) or fp16 pair pre-scaled by 2^p (fp16x2)
 struct PackedW {
     DevBuf hi, lo;
+    DevBuf lo8;            // fp16x2 packing only: e5m2(w * 2^p - hi), the weight-correction operand of the fp8 MMAs
+    CUtensorMap tm8;       // box = 128 K-columns (bytes) x 128 rows
+    bool tm8_ok = false;
+    const CUtensorMap& map8() {
+        if (!tm8_ok) {
+            const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+            const uint64_t strides[1] = {static_cast<uint64_t>(K)};
+            const uint32_t box[2] = {128, 128};
+            tm8 = make_tmap_ex(lo8.p, 1, 128, 2, dims, strides, box);
+            tm8_ok = true;
+        }
+        return tm8;
+    }
     int N = 0, K = 0;
     float acc_scale = 1.0f;   // 2^-p: what the epilogue multiplies the accumulators with
     CUtensorMap tm[2];     // cached TMA descriptors (hi, lo) for box = 64 x tm_ntile
@@ -203,11 +233,16 @@ struct PackedW {
             }
             const float up = std::ldexp(1.0f, p);
             acc_scale = std::ldexp(1.0f, -p);
+            std::vector<uint8_t> l8(w.size());
             for (size_t i = 0; i < w.size(); ++i) {
                 const float v = w[i] * up;
                 h[i] = f32_to_f16_bits(v);
-                l[i] = f32_to_f16_bits(v - f16_bits_to_f32(h[i]));
+                const float rem = v - f16_bits_to_f32(h[i]);
+                l[i] = f32_to_f16_bits(rem);
+                l8[i] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(rem, __NV_SATFINITE, __NV_E5M2));
             }
+            upload(lo8, l8);
+            tm8_ok = false;
         }
         upload(hi, h);
         upload(lo, l);
