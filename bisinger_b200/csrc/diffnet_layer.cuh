@@ -5,8 +5,8 @@
 //                        epilogue: + conditioner projection, sigmoid * tanh -> z (fp16, the all-layer z matrix)
 //     R(n)             : acc[256 x 256] = z[rows, this layer's columns] * W_res^T                               (K = 256)
 //                        epilogue: x = (x + acc + b) / sqrt2 -> x f32 ; fp16 / e4m3 of (x + d_next) -> next layer's conv input
-// issued in the order  G(0,0) G(0,1) | G(1,0) R(0) G(1,1) | G(2,0) R(1) G(2,1) | ... | R(last)  so that the gate epilogue of
-// tile n (which R(n) depends on) overlaps the first gate GEMM of tile n+1.  TMEM holds two 256-column accumulators that
+// issued in the order  G(0,0) G(0,1) | G(1,0) G(1,1) R(0) | G(2,0) G(2,1) R(1) | ... | R(last)  so that the gate epilogues of
+// tile n (which R(n) depends on) overlap the gate GEMMs of tile n+1.  TMEM holds two 256-column accumulators that
 // alternate op by op.  R(n) reads the z rows the same CTA has just written: they go to global memory anyway (the skip sum
 // of the step is one K = L*C GEMM over that matrix) and come back through L2 by TMA; the epilogue warps order their stores
 // before the async-proxy reads with fence.proxy.async + an mbarrier the TMA producer waits on.
@@ -18,7 +18,8 @@
 // good to a few bits: what it removes is the SYSTEMATIC fp16 weight-rounding error that would add up over the 100 steps.
 // The residual GEMM keeps two fp16 MMAs per product (its z operand has no 8-bit copy).
 //
-// Epilogue: the fp32 streams the epilogue consumes (conditioner projection cp, residual stream x) move by TMA through a ring of [128 rows x 16 columns] shared-memory boxes (SWIZZLE_64B) fed by a second producer warp,
+// Epilogue: the streams the epilogue consumes (conditioner projection cp in fp32; the fp16 conv input, which doubles as the
+// residual stream) move by TMA through a ring of [128 rows x 16 columns] shared-memory boxes (SWIZZLE_64B) fed by a second producer warp,
 // and every epilogue thread works on ONE accumulator row exactly as tcgen05.ld delivers it -- no shared-memory transposes,
 // no global loads in the epilogue warps, 32-byte (full-sector) row stores for the 16-/8-bit outputs.  The register/LSU
 // epilogue of conv_gemm.cuh needed 15-20k cycles per op here and paced the kernel (profiles/r01_g, r01_h).
@@ -38,7 +39,7 @@ struct LayerArgs {
     CUtensorMap wg8;       // e5m2 correction of the same, box = 128 x 128
     CUtensorMap wr[2];     // residual half of the output projection fp16 hi / lo [C][C], box = 64 x 128
     CUtensorMap cp;        // conditioner projection + biases f32 [B][T][2C] (packed column order), box = 16 x 128, SWIZZLE_64B
-    CUtensorMap x;         // residual stream f32 [B][T][C], box = 16 x 128, SWIZZLE_64B (loaded and stored)
+    CUtensorMap xe;        // the conv input fp16 [B][T][C] once more, as the epilogue reads it: box = 32 channels x 128 rows, SWIZZLE_64B
     int B, T;
     int tiles_per_batch;   // ceil(T / 256)
     int n_row_tiles;       // B * tiles_per_batch
@@ -47,12 +48,12 @@ struct LayerArgs {
     int z_col0;            // first column of this layer in the z matrix
     int z_pitch;           // elements per row of the z matrix
     __half* z_out;         // z matrix base
-    float* x_out;          // residual stream (same buffer the x boxes are loaded from)
     __half* xa16_out;      // next layer's conv input (null after the last layer); NOT the buffer behind xa16 / xa8: other tiles
                            // still read halo rows of this layer's input while this tile's rows are written
     uint8_t* xa8_out;
     const float* bias_r;   // [C] residual bias
     const float* dvec;     // [C] next layer's step embedding (null after the last layer)
+    const float* dcur;     // [C] this layer's step embedding: the residual stream is carried as fp16(x + d), x = that - d
     float gscale, rscale;  // 2^-p of the gate / residual weight packing
     int flags;             // timing ablations (bit 0: no gate math)
     unsigned long long* trace;
@@ -65,8 +66,15 @@ struct LayerOp {
 __device__ __forceinline__ LayerOp layer_op(int j, int cnt) {
     if (j < 2) return LayerOp{0, 0, j};
     const int q = (j - 2) / 3, r = (j - 2) % 3;
+#ifdef B200_ORDER_GRG
     if (q == cnt - 1 || r == 1) return LayerOp{1, q, 0};
     return LayerOp{0, q + 1, r == 0 ? 0 : 1};
+#else
+    // G(q+1,0) G(q+1,1) R(q): the residual GEMM of a tile comes TWO gate GEMMs after the gate epilogue it depends on, so the
+    // operand producer never waits for z (with G R G it stalled ~10k cycles per row tile and starved the MMA issuer)
+    if (q == cnt - 1 || r == 2) return LayerOp{1, q, 0};
+    return LayerOp{0, q + 1, r};
+#endif
 }
 
 #ifndef B200_GATE_MATH
@@ -133,7 +141,7 @@ struct LayerSmem {
     static_assert(kOffW % 1024 == 0 && kOffE % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 };
 constexpr int kLayerThreads = 32 * 11;
-constexpr int kBoxesPerOp = 16;
+constexpr int kGateBoxes = 16, kResBoxes = 8;
 
 // byte offset of 16-byte chunk k (4 fp32 columns) of row r in a SWIZZLE_64B box
 __device__ __forceinline__ uint32_t ebox_off(int r, int k) { return static_cast<uint32_t>(r * 64 + ((k ^ ((r >> 1) & 3)) << 4)); }
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
     const uint32_t smem_a = smem_u32(smem);
     const uint32_t smem_w = smem_a + S::kOffW;
     const uint32_t smem_e = smem_a + S::kOffE;
-    float* vec = reinterpret_cast<float*>(smem + S::kOffVec);        // [0,256) residual bias, [256,512) next step embedding
+    float* vec = reinterpret_cast<float*>(smem + S::kOffVec);        // [0,256) residual bias - this layer's step embedding, [256,512) next step embedding
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
     uint64_t* afull_bar = bars;
     uint64_t* aempty_bar = afull_bar + S::kAStages;
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
     if (warp == 0) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {   // per-column vectors of the residual epilogue (weights / LUT: not written by the previous kernel)
         const int c = threadIdx.x - 64;
-        vec[c] = args.bias_r[c];
+        vec[c] = args.bias_r[c] - args.dcur[c];            // x = fp16 conv input - d_cur, then + residual bias
         vec[256 + c] = args.dvec ? args.dvec[c] : 0.0f;
     }
     tc_fence_before();
@@ -356,30 +364,23 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             t[0] = clock64() - t_begin; t[1] = w_t; t[2] = w_a; t[3] = w_b; t[10] = cnt;
         }
     } else if (warp == 10 && lane == 0) {
-        // ================= epilogue-operand producer: cp / x boxes in, updated x boxes out =================
-        // box q of this CTA: op j = q / 16, i = q % 16.  gate op: chunk c = i / 4, column group g = (i / 2) % 2, i % 2 = gate / filter
-        // columns of cp; residual op: chunk c = i / 2, group g = i % 2 of x.  Slot = q % kEStages.
-        const int n_boxes = n_ops * kBoxesPerOp;
+        // ================= epilogue-operand producer: cp boxes (gate ops) / conv-input boxes (residual ops) =================
+        // gate op, 16 boxes of 16 fp32 columns of cp: box i -> chunk c = i / 4, column group g = (i / 2) % 2, i % 2 = gate / filter
+        // columns.  residual op, 8 boxes of 32 fp16 channels of the conv input: box i -> chunk c = i / 2, group g = i % 2.
         long long w_e = 0;
-        auto box_coords = [&](int q, int& kind, int& col, int& row, int& b) {
-            const int j = q / kBoxesPerOp, i = q % kBoxesPerOp;
+        int q = 0;
+        for (int j = 0; j < n_ops; ++j) {
             const LayerOp op = layer_op(j, cnt);
             const int m = worker + op.n * n_workers;
-            b = m / args.tiles_per_batch;
-            row = (m % args.tiles_per_batch) * kTileRows + rank * kTileM;
-            kind = op.kind;
-            if (kind == 0) col = op.h * 256 + ((i >> 1) & 1) * 64 + (i >> 2) * 16 + (i & 1) * 128;
-            else col = (i & 1) * 128 + (i >> 1) * 16;
-        };
-        for (int q = 0; q < n_boxes; ++q) {
-            const int s = q % S::kEStages;
-            const uint32_t dst = smem_e + s * S::kEBoxBytes;
-            if (q >= S::kEStages) mbar_wait_tr(&edone_bar[s], ((q / S::kEStages) - 1) & 1, tr_on, w_e);   // previous occupant consumed by its four warps
-            if (q < n_boxes) {
-                int kind, col, row, b;
-                box_coords(q, kind, col, row, b);
+            const int b = m / args.tiles_per_batch;
+            const int row = (m % args.tiles_per_batch) * kTileRows + rank * kTileM;
+            const int nb = op.kind == 0 ? kGateBoxes : kResBoxes;
+            for (int i = 0; i < nb; ++i, ++q) {
+                const int s = q % S::kEStages;
+                if (q >= S::kEStages) mbar_wait_tr(&edone_bar[s], ((q / S::kEStages) - 1) & 1, tr_on, w_e);   // previous occupant consumed by its four warps
+                const int col = op.kind == 0 ? op.h * 256 + ((i >> 1) & 1) * 64 + (i >> 2) * 16 + (i & 1) * 128 : (i & 1) * 128 + (i >> 1) * 32;
                 mbar_arrive_expect_tx(&efull_bar[s], S::kEBoxBytes);
-                tma_load_3d_local(dst, kind == 0 ? &args.cp : &args.x, &efull_bar[s], col, row, b);
+                tma_load_3d_local(smem_e + s * S::kEBoxBytes, op.kind == 0 ? &args.cp : &args.xe, &efull_bar[s], col, row, b);
             }
         }
         if (tr_on) args.trace[blockIdx.x * 16 + 13] = w_e;
@@ -398,6 +399,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
 #pragma unroll
         for (int k = 0; k < 4; ++k) xo[k] = ebox_off(r_box, k);
 
+        int q_base = 0;           // first box of the current op in this CTA's box sequence
         bool z_pending = false;   // z rows stored by the previous gate op, not yet fenced / signalled
         int z_tile = 0;           // ... and the local row tile they belong to
         auto publish_z = [&]() {
@@ -421,21 +423,18 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             tc_fence_after();
             const long long t_op = tr ? clock64() : 0;
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
-            const int q_op = j * kBoxesPerOp;
+            const int q_op = q_base;
+            q_base += op.kind == 0 ? kGateBoxes : kResBoxes;
             if (op.kind == 0) {
                 // ---- gate: z = sigmoid(acc_g + cp_g) * tanh(acc_f + cp_f)   (net.py:71-74)
                 // (loops kept rolled: with the four roles' code paths resident the unrolled epilogue stalled on instruction fetch)
                 const float hs = 0.5f * args.gscale;
                 __half* zrow = args.z_out + row * args.z_pitch + args.z_col0 + op.h * 128;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
+                // one 16-channel chunk; vg / vf: its gate / filter accumulator columns (already waited for)
+                auto gate_chunk = [&](int c, const uint32_t (&vg)[16], const uint32_t (&vf)[16]) {
                     const int cg = grp * 64 + c * 16;          // gate columns [cg, cg+16), filter columns +128
                     const int q = q_op + 4 * c + 2 * grp;      // boxes q (cp of the gate columns), q + 1 (filter columns)
                     const int sg = q % S::kEStages, sf = (q + 1) % S::kEStages;
-                    uint32_t vg[16], vf[16];
-                    __syncwarp();
-                    tmem_ld16(tacc + cg, vg);
-                    tmem_ld16(tacc + 128 + cg, vf);
                     mbar_wait_tr(&efull_bar[sg], (q / S::kEStages) & 1, tr, w_e);
                     mbar_wait_tr(&efull_bar[sf], ((q + 1) / S::kEStages) & 1, tr, w_e);
                     float4 pg[4], pf[4];
@@ -444,10 +443,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                         pg[k] = lds128(smem_e + sg * S::kEBoxBytes + xo[k]);
                         pf[k] = lds128(smem_e + sf * S::kEBoxBytes + xo[k]);
                     }
-#ifndef B200_PUBLISH_NOW
-                    if (c == 1 && z_pending) publish_z();   // the previous gate op's z rows (its stores have long drained)
-#endif
-                    tmem_ld_wait16x2(vg, vf);
                     uint32_t zz[8];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -463,8 +458,30 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                     // (Signalling right behind the ld.shared instructions let the TMA refill overtake loads still queued
                     // behind this warp's stores -- a rare 32-row corruption.)
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(&edone_bar[sg]); mbar_arrive(&edone_bar[sf]); }
+                    if (lane == 0) { mbar_arrive_relaxed(&edone_bar[sg]); mbar_arrive_relaxed(&edone_bar[sf]); }
                     if (row_ok) stg256(zrow + cg, zz);
+                };
+                // the accumulator columns of chunk c+1 are read from TMEM while chunk c is processed (under MMA load a
+                // tcgen05.ld round trip is ~1k cycles and was 40 % of this loop: profiles/r01_h)
+                uint32_t ag[16], af[16], bg[16], bf[16];
+                __syncwarp();
+                tmem_ld16(tacc + grp * 64, ag);
+                tmem_ld16(tacc + 128 + grp * 64, af);
+#pragma unroll 1
+                for (int c = 0; c < 4; c += 2) {
+                    tmem_ld_wait16x2(ag, af);
+                    __syncwarp();
+                    tmem_ld16(tacc + grp * 64 + (c + 1) * 16, bg);
+                    tmem_ld16(tacc + 128 + grp * 64 + (c + 1) * 16, bf);
+                    if (c == 2 && z_pending) publish_z();   // the previous gate op's z rows (their stores have long drained)
+                    gate_chunk(c, ag, af);
+                    tmem_ld_wait16x2(bg, bf);
+                    if (c + 2 < 4) {
+                        __syncwarp();
+                        tmem_ld16(tacc + grp * 64 + (c + 2) * 16, ag);
+                        tmem_ld16(tacc + 128 + grp * 64 + (c + 2) * 16, af);
+                    }
+                    gate_chunk(c + 1, bg, bf);
                 }
                 z_pending = true;
                 z_tile = op.n;
@@ -475,53 +492,75 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                 if (j + 1 < n_ops && layer_op(j + 1, cnt).kind == 1 && layer_op(j + 1, cnt).n == op.n) publish_z();
             } else {
                 // ---- residual: x <- (x + W_res z + b) / sqrt(2)  (net.py:76-78); fp16 / e4m3 of (x + d_next) feed the next layer's conv
+                // The residual stream is carried only as the fp16 conv input: x = fp16(x + d_cur) - d_cur (tools/precision_study.py
+                // "state fp16": 1.5-2.2e-3 vs 1.2-1.3e-3 max mel error).  No fp32 x is read or written: the epilogue streams the conv
+                // input once more (32-channel boxes) and stores only the next layer's fp16 / e4m3 conv input.
                 const bool has_next = args.xa16_out != nullptr;
-#pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    const int cl = grp * 128 + c * 16;
+                auto res_chunk = [&](int c, const uint32_t (&v)[32]) {   // 32 channels
+                    const int cl = grp * 128 + c * 32;
                     const int q = q_op + 2 * c + grp;
                     const int sx = q % S::kEStages;
                     const uint32_t box = smem_e + sx * S::kEBoxBytes;
-                    uint32_t v[16];
-                    __syncwarp();
-                    tmem_ld16(tacc + cl, v);
                     mbar_wait_tr(&efull_bar[sx], (q / S::kEStages) & 1, tr, w_e);
-                    float4 x[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) x[k] = lds128(box + xo[k]);
-#ifndef B200_PUBLISH_NOW
-                    if (c == 1 && z_pending) publish_z();
-#endif
-                    tmem_ld_wait16(v);
-                    uint32_t xs[16], h16[8], h8[4];
+                    uint4 xh[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float4 bb = lds128(vec_s + (cl + 4 * k) * 4), dd = lds128(vec_s + (256 + cl + 4 * k) * 4);
-                        const float y0 = (x[k].x + fmaf(__uint_as_float(v[4 * k]), args.rscale, bb.x)) * rs2;
-                        const float y1 = (x[k].y + fmaf(__uint_as_float(v[4 * k + 1]), args.rscale, bb.y)) * rs2;
-                        const float y2 = (x[k].z + fmaf(__uint_as_float(v[4 * k + 2]), args.rscale, bb.z)) * rs2;
-                        const float y3 = (x[k].w + fmaf(__uint_as_float(v[4 * k + 3]), args.rscale, bb.w)) * rs2;
-                        xs[4 * k] = __float_as_uint(y0); xs[4 * k + 1] = __float_as_uint(y1); xs[4 * k + 2] = __float_as_uint(y2); xs[4 * k + 3] = __float_as_uint(y3);
-                        h16[2 * k] = pack_half2_sat(y0 + dd.x, y1 + dd.y);     // saturating: an out-of-range activation must not become inf
-                        h16[2 * k + 1] = pack_half2_sat(y2 + dd.z, y3 + dd.w);
-                        h8[k] = pack_e4m3x4(y0 + dd.x, y1 + dd.y, y2 + dd.z, y3 + dd.w);
+                        const float4 t4 = lds128(box + xo[k]);   // 8 fp16 channels
+                        xh[k] = make_uint4(__float_as_uint(t4.x), __float_as_uint(t4.y), __float_as_uint(t4.z), __float_as_uint(t4.w));
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&edone_bar[sx]);   // after the arithmetic that consumed the box (see the gate loop)
-                    if (row_ok) {
-                        // one row = 64 contiguous bytes of x (two full sectors), 32 of the fp16 and 16 of the e4m3 conv input
-                        stg256(args.x_out + row * C + cl, reinterpret_cast<const uint32_t(&)[8]>(xs[0]));
-                        stg256(args.x_out + row * C + cl + 8, reinterpret_cast<const uint32_t(&)[8]>(xs[8]));
-                        if (has_next) {
-                            stg256(args.xa16_out + row * C + cl, h16);
-                            *reinterpret_cast<uint4*>(args.xa8_out + row * C + cl) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+                    uint32_t h16[16], h8[8];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t pk[4] = {xh[k].x, xh[k].y, xh[k].z, xh[k].w};
+                        float y[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 xf = __half22float2(*reinterpret_cast<const __half2*>(&pk[e]));
+                            y[2 * e] = xf.x; y[2 * e + 1] = xf.y;
+                        }
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int c4 = cl + 8 * k + 4 * hh;
+                            const float4 bb = lds128(vec_s + c4 * 4), dd = lds128(vec_s + (256 + c4) * 4);
+                            const float y0 = (y[4 * hh] + fmaf(__uint_as_float(v[8 * k + 4 * hh]), args.rscale, bb.x)) * rs2 + dd.x;
+                            const float y1 = (y[4 * hh + 1] + fmaf(__uint_as_float(v[8 * k + 4 * hh + 1]), args.rscale, bb.y)) * rs2 + dd.y;
+                            const float y2 = (y[4 * hh + 2] + fmaf(__uint_as_float(v[8 * k + 4 * hh + 2]), args.rscale, bb.z)) * rs2 + dd.z;
+                            const float y3 = (y[4 * hh + 3] + fmaf(__uint_as_float(v[8 * k + 4 * hh + 3]), args.rscale, bb.w)) * rs2 + dd.w;
+                            h16[4 * k + 2 * hh] = pack_half2_sat(y0, y1);          // saturating: an out-of-range activation must not become inf
+                            h16[4 * k + 2 * hh + 1] = pack_half2_sat(y2, y3);
+                            h8[2 * k + hh] = pack_e4m3x4(y0, y1, y2, y3);
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_relaxed(&edone_bar[sx]);   // after the arithmetic that consumed the box (see the gate loop)
+                    if (row_ok && has_next) {
+                        // one row = 64 contiguous bytes of the fp16 and 32 of the e4m3 conv input: full 32-byte sectors
+                        stg256(args.xa16_out + row * C + cl, reinterpret_cast<const uint32_t(&)[8]>(h16[0]));
+                        stg256(args.xa16_out + row * C + cl + 16, reinterpret_cast<const uint32_t(&)[8]>(h16[8]));
+                        stg256(args.xa8_out + row * C + cl, h8);
+                    }
+                };
+                uint32_t va[32], vb[32];
+                __syncwarp();
+                tmem_ld32(tacc + grp * 128, va);
+#pragma unroll 1
+                for (int c = 0; c < 4; c += 2) {
+                    tmem_ld_wait32(va);
+                    __syncwarp();
+                    tmem_ld32(tacc + grp * 128 + (c + 1) * 32, vb);
+                    if (c == 2 && z_pending) publish_z();
+                    res_chunk(c, va);
+                    tmem_ld_wait32(vb);
+                    if (c + 2 < 4) {
+                        __syncwarp();
+                        tmem_ld32(tacc + grp * 128 + (c + 2) * 32, va);
+                    }
+                    res_chunk(c + 1, vb);
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(tempty_remote0 + acc * 8);
+            if (lane == 0) mbar_arrive_remote_relaxed(tempty_remote0 + acc * 8);   // TMEM reads ordered by tcgen05.wait::ld + fence
             if (tr) { if (op.kind == 0) t_gate += clock64() - t_op; else t_res += clock64() - t_op; }
         }
         if (z_pending) publish_z();

@@ -143,7 +143,7 @@ struct DiffusionPlan::Workspace {
     DevBuf xa8, xa16_b, xa8_b;   // xa8: e4m3 copy of the conv input (A operand of the fp8 correction MMAs)
     CUtensorMap m_xa16_b, m_xa8_b;
     CUtensorMap m_xin[2], m_cond[2], m_xa[2], m_z[2], m_s[2], m_h[2];
-    CUtensorMap m_xa8, m_x;          // fused layer kernel: 8-bit conv input, fp32 residual stream (16 x 128 boxes)
+    CUtensorMap m_xa8, m_xe[2];      // fused layer kernel: 8-bit conv input; the fp16 conv input buffers as the epilogue reads them
     std::vector<CUtensorMap> m_cp;   // ... and the conditioner projection of every layer
     cudaGraphExec_t graph = nullptr;
     bool graph_has_mask = false;
@@ -350,7 +350,8 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
         w->xa8_b.alloc(rows * C);
         w->m_xa16_b = make_act_tmap(w->xa16_b.p, B, T, C, 0, kXaBoxRows);
         w->m_xa8_b = make_act8_tmap(w->xa8_b.p, B, T, C, kXaBoxRows);
-        w->m_x = make_f32_tmap(w->xres.p, B, T, C);
+        w->m_xe[1] = make_epi16_tmap(w->xa16_b.p, B, T, C);
+        w->m_xe[0] = make_epi16_tmap(w->xa_hi.p, B, T, C);
         for (int l = 0; l < cfg.residual_layers; ++l)
             w->m_cp.push_back(make_f32_tmap(w->cp.as<float>() + static_cast<size_t>(l) * rows * 2 * C, B, T, 2 * C));
     }
@@ -438,7 +439,7 @@ LayerArgs DiffusionPlan::fused_args(Workspace& w, int l, const float* lut_t) {
     a.wg8 = ly.g1.map8();
     ly.g2.maps(128, a.wr[0], a.wr[1]);
     a.cp = w.m_cp[l];
-    a.x = w.m_x;
+    a.xe = w.m_xe[l & 1];
     a.B = w.B;
     a.T = w.T;
     a.tiles_per_batch = (w.T + 2 * kTileM - 1) / (2 * kTileM);
@@ -448,11 +449,11 @@ LayerArgs DiffusionPlan::fused_args(Workspace& w, int l, const float* lut_t) {
     a.z_col0 = l * C;
     a.z_pitch = L * C;
     a.z_out = w.z_hi.as<__half>();
-    a.x_out = w.xres.as<float>();
     a.xa16_out = (l + 1 < L) ? ((l & 1) ? w.xa_hi.as<__half>() : w.xa16_b.as<__half>()) : nullptr;
     a.xa8_out = (l + 1 < L) ? ((l & 1) ? w.xa8.as<uint8_t>() : w.xa8_b.as<uint8_t>()) : nullptr;
     a.bias_r = ly.g2_bias.as<float>();
     a.dvec = (l + 1 < L) ? lut_t + static_cast<size_t>(l + 1) * C : nullptr;
+    a.dcur = lut_t + static_cast<size_t>(l) * C;
     a.gscale = ly.g1.acc_scale;
     a.rscale = ly.g2.acc_scale;
     if (const char* ab = std::getenv("BSG_ABLATE")) a.flags = std::atoi(ab);   // timing experiments only (wrong results)

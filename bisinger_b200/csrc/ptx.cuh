@@ -28,6 +28,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrivals that publish no memory (a TMEM accumulator or a shared-memory box has been READ): relaxed, so that the
+// arrive does not wait for the thread's outstanding global stores to drain (the default .release did: profiles/r01_h)
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -153,6 +158,15 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
                  :
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&a)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]),
+                   "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]),
+                   "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]), "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]),
+                   "+r"(a[30]), "+r"(a[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait16x2(uint32_t (&a)[16], uint32_t (&b)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]),
@@ -178,6 +192,9 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_saddr, uint32_t ra
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
     return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_saddr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_saddr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_saddr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_saddr) : "memory");

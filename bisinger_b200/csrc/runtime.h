@@ -113,6 +113,13 @@ inline CUtensorMap make_f32_tmap(const void* base, int B, int L, int C) {
     const uint32_t box[3] = {16, 128, 1};
     return make_tmap_ex(base, 2, 64, 3, dims, strides, box);
 }
+// 16-bit rows [B][L][C] as the fused layer kernel's epilogue reads them: box = 32 channels (64 bytes, SWIZZLE_64B) x 128 rows
+inline CUtensorMap make_epi16_tmap(const void* base, int B, int L, int C) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * 2 * L};
+    const uint32_t box[3] = {32, 128, 1};
+    return make_tmap_ex(base, 0, 64, 3, dims, strides, box);
+}
 // activations [B][L][C] (channels-last), box = 64 channels x box_rows rows (the halo tile of one k-block)
 inline CUtensorMap make_act_tmap(const void* base, int B, int L, int C, int row_pitch_elems = 0, int box_rows = kTileM) {
     if (row_pitch_elems == 0) row_pitch_elems = C;

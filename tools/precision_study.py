@@ -51,7 +51,10 @@ def diffnet(p, spec, t, cond, S, cp_cache):
             if "cp" in S.per:   # storage type of the hoisted conditioner projection
                 cp_cache[i] = r(cp_cache[i] + p[pre + "dilated_conv.bias"][None, :, None], S.per["cp"]) - p[pre + "dilated_conv.bias"][None, :, None]
         xa = x + d[:, :, None]
-        if S.state16:
+        if S.state16 == "fp16":     # the residual stream is carried ONLY as the fp16 conv input: x = fp16(x + d) - d
+            xa = r(xa, torch.float16)
+            x = xa - d[:, :, None]
+        elif S.state16:
             h, l = split(xa, torch.bfloat16)
             xa = h + l
             x = xa - d[:, :, None]     # the state is re-derived from the stored operand
@@ -115,6 +118,7 @@ if __name__ == "__main__":
     schemes += [Scheme("cur but gate e5m2corr + cp fp16", hf, 1, 2, per={**side, "gate": W52, "cp": hf}),
                 Scheme("cur but cp fp16", hf, 1, 2, per={**side, "cp": hf}),
                 Scheme("cur but cp bf16", hf, 1, 2, per={**side, "cp": bf})]
+    schemes += [Scheme("cur + state fp16 (x carried as fp16(x+d))", hf, 1, 2, state16="fp16", per={**side, "gate": W52})]
     sel = sys.argv[1:]
     for seed, (B, T) in ((7, (2, 40)), (8, (1, 96))):
         sd = synth.diffnet_state(1234)
