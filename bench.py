@@ -28,12 +28,14 @@ BATCH, FRAMES = 32, 1875                      # cfg3: 32 phrases x 10 s
 FLOPS_DIFFNET_FRAME_STEP = 26_427_392         # SURVEY.md §8d (2*MAC, what the reference computes)
 FLOPS_GATE_GEMM_FRAME = 2 * (3 * 256) * 512           # dilated conv k=3 256->512 per frame per layer (the step-invariant
 #   conditioner 1x1 is hoisted out of the K loop and evaluated once per batch: SURVEY.md §8d allows exactly this)
+FLOPS_RES_GEMM_FRAME = 2 * 256 * 256                  # residual half of the 1x1 output projection per frame per layer
 FLOPS_COND_ONCE_FRAME = 20 * 2 * 256 * 512            # 5 242 880 per frame, once
 FLOPS_DIFFNET_FRAME_STEP_HOISTED = FLOPS_DIFFNET_FRAME_STEP - FLOPS_COND_ONCE_FRAME   # 21 184 512
 FLOPS_HIFIGAN_FRAME = 375_734_272
 CONTRACTION_NOTE = {
-    "fp16x2": " (per-layer GEMMs: fp16 activations x fp16 hi/lo-split weights, 2 tensor-core MMAs per product, fp32 accumulate; "
-              "once-per-step GEMMs bf16x3; vocoder bf16)",
+    "fp16x2": " (per-layer GEMMs, one fused kernel per ResidualBlock: fp16 activations x fp16 weights + a weight-rounding correction "
+              "term -- e4m3 x e5m2 on the fp8 pipe in the dilated-conv GEMM, a second fp16 MMA in the residual / skip-sum GEMMs -- "
+              "fp32 accumulate; once-per-step GEMMs bf16x3; vocoder bf16)",
     "bf16x3": " (3 tensor-core MMAs per product: hi*hi + lo*hi + hi*lo)",
     "bf16": " (single bf16 MMA per product; fails the 100-step mel tolerance on random-init weights)",
 }
@@ -204,24 +206,48 @@ def run_ours(args):
     if rank == 0:
         peaks = read_peaks()
         reps = 200
-        k_ms = gd.plan.time_kernel(0, B, T, reps)
-        gate_flops = FLOPS_GATE_GEMM_FRAME * B * T
-        achieved = gate_flops / (k_ms * 1e-3) / 1e12
-        line["roofline"] = {
-            "bound": "tensor", "kernel": "conv_gemm_kernel<256,%d,EPI_GATE,pair> (dilated-conv GEMM k=3 256->512, conditioner add + sigmoid*tanh gate epilogue)" % MMAS_PER_PRODUCT[args.precision],
-            "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops"], 4),
-            "traffic": None, "avg_launch_ms": round(k_ms, 4), "algorithmic_flops_per_launch": gate_flops,
-            "issued_mma_flops_per_algorithmic_flop": MMAS_PER_PRODUCT[args.precision],
-            "peak_source": peaks["source"] + ", of measured",
-            "share_of_step": round(20 * K_STEP * k_ms / (ms / args.steps), 3),
-        }
-        r_ms = gd.plan.time_kernel(1, B, T, reps)
+        fused = args.precision == "fp16x2"
+        try:
+            k_ms = gd.plan.time_kernel(3, B, T, reps) if fused else None
+        except RuntimeError:
+            fused, k_ms = False, None
+        if fused:
+            # dominant kernel: one fused ResidualBlock (dilated-conv gate GEMM of both channel halves + residual GEMM + both epilogues)
+            layer_flops = (FLOPS_GATE_GEMM_FRAME + FLOPS_RES_GEMM_FRAME) * B * T
+            achieved = layer_flops / (k_ms * 1e-3) / 1e12
+            line["roofline"] = {
+                "bound": "tensor", "kernel": "diffnet_layer_kernel (fused ResidualBlock: dilated-conv GEMM k=3 256->512 with fp16 + fp8-correction MMAs, "
+                                             "gate epilogue, residual GEMM 256->256, residual epilogue)",
+                "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops"], 4),
+                "traffic": None, "avg_launch_ms": round(k_ms, 4), "algorithmic_flops_per_launch": layer_flops,
+                "issued_mma_flops_per_algorithmic_flop": 2,
+                "issued_note": "per product one fp16 MMA + one correction MMA; the gate GEMM's correction runs at the fp8 rate (2x) => 1.5 fp16-MMA "
+                               "equivalents there; the kernel is bound by operand bytes into the SM (~1.3 MB per 256-row tile and CTA), see DESIGN.md",
+                "peak_source": peaks["source"] + ", of measured",
+                "share_of_step": round(20 * K_STEP * k_ms / (ms / args.steps), 3),
+            }
+            r_ms = 0.0
+        else:
+            k_ms = gd.plan.time_kernel(0, B, T, reps)
+            gate_flops = FLOPS_GATE_GEMM_FRAME * B * T
+            achieved = gate_flops / (k_ms * 1e-3) / 1e12
+            line["roofline"] = {
+                "bound": "tensor", "kernel": "conv_gemm_kernel<256,%d,EPI_GATE,pair> (dilated-conv GEMM k=3 256->512, conditioner add + sigmoid*tanh gate epilogue)" % MMAS_PER_PRODUCT[args.precision],
+                "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops"], 4),
+                "traffic": None, "avg_launch_ms": round(k_ms, 4), "algorithmic_flops_per_launch": gate_flops,
+                "issued_mma_flops_per_algorithmic_flop": MMAS_PER_PRODUCT[args.precision],
+                "peak_source": peaks["source"] + ", of measured",
+                "share_of_step": round(20 * K_STEP * k_ms / (ms / args.steps), 3),
+            }
+            r_ms = gd.plan.time_kernel(1, B, T, reps)
+        s_ms = gd.plan.time_kernel(2, B, T, 50)
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record(stream); mel_t = gd.sample(cond_d, mel_d, seed=99); e1.record(stream)
         gen(mel_t.transpose(1, 2).contiguous(), f0_d, seed=99); e2.record(stream)
         torch.cuda.synchronize(dev)
         line["breakdown_ms"] = {"sampler": round(e0.elapsed_time(e1), 2), "vocoder": round(e1.elapsed_time(e2), 2),
-                                "gate_gemm_launch": round(k_ms, 4), "resskip_gemm_launch": round(r_ms, 4),
+                                ("fused_layer_launch" if fused else "gate_gemm_launch"): round(k_ms, 4), "resskip_gemm_launch": round(r_ms, 4),
+                                "skipsum_gemm_launch": round(s_ms, 4),
                                 "layer_gemms_share_of_sampler": round(20 * K_STEP * (k_ms + r_ms) / e0.elapsed_time(e1), 3)}
         line["pipeline_algorithmic_tflops"] = round((FLOPS_DIFFNET_FRAME_STEP_HOISTED * K_STEP + FLOPS_COND_ONCE_FRAME + FLOPS_HIFIGAN_FRAME) * B * T * world * args.steps / (ms * 1e-3) / 1e12, 1)
         if world == 1 and not args.no_cpu_baseline:

@@ -106,6 +106,11 @@ struct ConvGemmArgs {
     int a_rows;            // rows of the A halo box (multiple of 8, 128 + max_shift - min_shift rounded up)
     TapSet taps;
     EpiParams epi;
+    int k_steps;           // MMAs (16 channels each) per 64-channel k-block; 0 = 4.  Fewer when Cin < 64 (the rest of the block is zero)
+    int w_resident;        // 1: all n_taps * n_kb weight tiles fit the weight ring: they are loaded ONCE per CTA and stay in shared
+                           //    memory for all its tiles (single-CTA tiles only).  Small-channel convolutions issue so little MMA work
+                           //    per weight tile that streaming the weights per tile left the kernel bound by TMA round trips
+                           //    (~150 cycles per MMA whatever N: profiles/r01_i)
     unsigned long long* trace;   // optional [grid][16] cycle counters of the three roles (tools/gpu_probe.py tracetarget), or null
 };
 
@@ -284,8 +289,9 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, int Lrows, uint
     // column range of this warp
     constexpr int kSplit = (N_TILE % 64 == 0) ? 2 : 1;
     constexpr int kColsPerGrp = N_TILE / kSplit;
-    if (EPI != EPI_POSTERIOR && kSplit == 1 && grp != 0) return;
-    const int c_begin = grp * kColsPerGrp;
+    // kSplit == 1 (narrow tiles): the two warp groups do not split the columns, they alternate TILES (see the kernel's
+    // epilogue loop); the posterior epilogue alternates 16-channel chunks instead
+    const int c_begin = kSplit == 1 ? 0 : grp * kColsPerGrp;
     (void)rows_left; (void)c_begin; (void)row_w; (void)lp; (void)sc;
 
     if constexpr (EPI == EPI_F32) {
@@ -580,12 +586,11 @@ __device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int 
     const int b = m / args.tiles_per_batch;
     const int t0 = (m % args.tiles_per_batch) * tile_rows + row_in_tile;
     constexpr int kSplit = (N_TILE % 64 == 0) ? 2 : 1;
-    if (kSplit == 1 && grp != 0) return;
     constexpr int kCols = N_TILE / kSplit;
     constexpr int kLinesPerRow = (kCols * 4 + 127) / 128;
     const float* src0 = nullptr;
     const float* src1 = nullptr;
-    int col = grp * kCols;
+    int col = kSplit == 1 ? 0 : grp * kCols;
     if constexpr (EPI == EPI_RES_SKIP) {
         src0 = e.f32_a;
         col += n_tile * N_TILE;
@@ -628,9 +633,9 @@ struct GemmSmem {
     static constexpr int kBSlotBytes = kBParts * kBPartBytes;
     static constexpr int kAStages = TERMS == 3 ? 2 : (TERMS == 2 ? B200_ASTAGES2 : 3);
     static constexpr int kBStagesRaw = (kSmemBudget - kAStages * kASlotBytes) / kBSlotBytes;
-    static constexpr int kBStages = kBStagesRaw > 6 ? 6 : kBStagesRaw;
+    static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;   // deep enough to hold a small convolution's whole weight set
     static constexpr int kOperandBytes = kAStages * kASlotBytes + kBStages * kBSlotBytes;
-    static constexpr int kBarBytes = 256;
+    static constexpr int kBarBytes = 512;
     static constexpr int kXposeBytes = kEpiWarps * kStageFloatsPerWarp * 4;   // one 16x36 fp32 transpose tile per epilogue warp
     static constexpr int kTotal = kOperandBytes + kBarBytes + kXposeBytes + 1024;  // +1024 for manual alignment
     static_assert(kBStages >= 2, "need at least a double-buffered weight ring");
@@ -663,6 +668,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     constexpr int kTmemCols = tmem_cols_for(2 * N_TILE);
     constexpr uint32_t kIdesc = umma_idesc_f16(PAIR ? 2 * kTileM : kTileM, N_TILE, /*fp16=*/TERMS == 2);
     constexpr int kTileRows = PAIR ? 2 * kTileM : kTileM;
+    // Narrow tiles (N_TILE = 32: the last HiFi-GAN stage) are bound by the epilogue's latency chain, not by its width: instead of
+    // idling, the second group of four epilogue warps takes every other tile (accumulator buffer = tile parity = group).
+    constexpr bool kAltTiles = (N_TILE % 64 != 0) && EPI != EPI_POSTERIOR;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -696,7 +704,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     if (threadIdx.x == 32) {
         for (int s = 0; s < S::kAStages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); }
         for (int s = 0; s < S::kBStages; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], MC ? 2 : 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * kEpiWarps : kEpiWarps); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], (PAIR ? 2 * kEpiWarps : kEpiWarps) / (kAltTiles ? 2 : 1)); }
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -725,6 +733,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         const bool tr = args.trace != nullptr;
         long long w_a = 0, w_b = 0;
         const long long t_begin = tr ? clock64() : 0;
+        const bool wres = !PAIR && args.w_resident != 0;
+        if (wres) {
+            // the whole weight set of the convolution, slot = kb * n_taps + tap (n_tiles_n == 1: checked on the host)
+            for (int kb = 0; kb < ts.n_kb; ++kb)
+                for (int tp = 0; tp < ts.n_taps; ++tp) {
+                    const int slot = kb * ts.n_taps + tp;
+                    mbar_arrive_expect_tx(&bfull_bar[slot], b_bytes);
+                    tma_load_2d(smem_b + slot * S::kBSlotBytes, &args.wmap[0], &bfull_bar[slot], ts.w_col0[tp] + kb * kBlockK, args.w_row0);
+                    if (TERMS >= 2) tma_load_2d(smem_b + slot * S::kBSlotBytes + S::kBPartBytes, &args.wmap[1], &bfull_bar[slot], ts.w_col0[tp] + kb * kBlockK, args.w_row0);
+                }
+        }
         for (int unit = worker; unit < n_units; unit += n_workers) {
             const int tile = B200_UNIT_TO_TILE(unit);
             const int n_tile = tile % args.n_tiles_n;
@@ -749,7 +768,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 }
                 if (++as == S::kAStages) { as = 0; aph ^= 1; }
                 // ... and one weight tile per tap
-                for (int tp = 0; tp < ts.n_taps; ++tp) {
+                for (int tp = 0; tp < (wres ? 0 : ts.n_taps); ++tp) {
                     mbar_wait_tr(&bempty_bar[bs], bph ^ 1, tr, w_b);
                     uint8_t* sb = smem_b + bs * S::kBSlotBytes;
                     const int wc = ts.w_col0[tp] + kb * kBlockK;
@@ -785,6 +804,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         const bool tr = args.trace != nullptr;
         long long w_t = 0, w_a = 0, w_b = 0;
         const long long t_begin = tr ? clock64() : 0;
+        const bool wres = !PAIR && args.w_resident != 0;
+        const int k_steps = args.k_steps > 0 ? args.k_steps : kBlockK / 16;
+        if (wres) {
+            for (int slot = 0; slot < ts.n_kb * ts.n_taps; ++slot) mbar_wait_tr(&bfull_bar[slot], 0, tr, w_b);
+            tc_fence_after();
+        }
         for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
             const int acc = it & 1;
             mbar_wait_tr(&tempty_bar[acc], ((it >> 1) & 1) ^ 1, tr, w_t);
@@ -796,14 +821,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 tc_fence_after();
                 const uint32_t a_slot = smem_u32(smem_a + as * S::kASlotBytes);
                 for (int tp = 0; tp < ts.n_taps; ++tp) {
-                    mbar_wait_tr(&bfull_bar[bs], bph, tr, w_b);
-                    tc_fence_after();
+                    if (!wres) {
+                        mbar_wait_tr(&bfull_bar[bs], bph, tr, w_b);
+                        tc_fence_after();
+                    }
                     const uint32_t a_hi = a_slot + ts.row_off[tp] * (kBlockK * 2);   // tap = row offset into the halo tile
                     const uint32_t a_lo = a_hi + S::kAPartBytes;
-                    const uint32_t b_hi = smem_u32(smem_b + bs * S::kBSlotBytes);
+                    const uint32_t b_hi = smem_u32(smem_b + (wres ? kb * ts.n_taps + tp : bs) * S::kBSlotBytes);
                     const uint32_t b_lo = b_hi + S::kBPartBytes;
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
+                        if (k >= k_steps) break;
                         const uint64_t da = umma_smem_desc<128>(a_hi + k * 32);
                         const uint64_t db = umma_smem_desc<128>(b_hi + k * 32);
                         if constexpr (PAIR) {
@@ -817,6 +845,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                         }
                         accumulate = 1;
                     }
+                    if (wres) continue;
                     // free the weight slot (in both CTAs; MC: one of the two arrivals in all four) when these MMAs retire
                     if constexpr (PAIR) umma_commit_pair(&bempty_bar[bs], MC ? static_cast<uint16_t>(0xF) : pair_mask); else umma_commit(&bempty_bar[bs]);
                     if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
@@ -844,6 +873,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
             const int tile = B200_UNIT_TO_TILE(unit);
             const int acc = it & 1;
+            if (kAltTiles && acc != ((warp - 2) >> 2)) continue;
             const int n_tile = tile % args.n_tiles_n;
             const int m = tile / args.n_tiles_n;
             const int b = m / args.tiles_per_batch;
@@ -854,7 +884,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             float* stage = xpose + (warp - 2) * kStageFloatsPerWarp;
             const int grp = (warp - 2) >> 2;
             if constexpr (EPI == EPI_RES_SKIP || EPI == EPI_BIAS_ACT || EPI == EPI_GATE) {
-                const int nu = unit + n_workers;
+                const int nu = unit + (kAltTiles ? 2 : 1) * n_workers;   // this group's next tile
                 if (nu < n_units && B200_UNIT_TO_TILE(nu) < args.num_tiles)
                     prefetch_rmw_tile<N_TILE, EPI>(args, B200_UNIT_TO_TILE(nu), kTileRows, rank * kTileM + quad * 32, grp, lane);
             }

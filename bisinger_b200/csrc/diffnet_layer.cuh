@@ -123,7 +123,10 @@ struct LayerSmem {
     static constexpr int kASlotBytes = 144 * 128;              // halo tile: 144 rows x 128 B (64 fp16 or 128 e4m3 channels)
     static constexpr int kAStages = 3;
     static constexpr int kWSlotBytes = 128 * 128;              // weight tile: 128 N rows x 128 B
-    static constexpr int kWStages = 6;
+#ifndef B200_WSTAGES
+#define B200_WSTAGES 6
+#endif
+    static constexpr int kWStages = B200_WSTAGES;
     static constexpr int kEBoxBytes = 128 * 16 * 4;            // epilogue box: 128 rows x 16 fp32
 #ifndef B200_ESTAGES
 #define B200_ESTAGES 9
@@ -189,7 +192,12 @@ __device__ __forceinline__ void tma_store_3d(const void* desc, uint32_t smem_src
                  : "memory");
 }
 
-template <int VARIANT>   // (a template only so that the header can be included from several translation units)
+// MC = 1: clusters of FOUR CTAs = two pairs working on two consecutive row tiles with the same weights; every weight tile is
+// read from L2 once per cluster (each CTA loads a quarter of the N rows and multicasts it to the CTA of the same rank in
+// the other pair).  At ~1.3 MB of L2->SM traffic per row tile and CTA, more than half of it weights, the 2-CTA kernel runs
+// into the L2->SM throughput limit (profiles/r01_h); only 33 such clusters fit on a B200, but 128 row-tile pairs over 33
+// clusters are the same 4 rounds as 256 row tiles over 74 pairs.
+template <int MC>
 __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const __grid_constant__ LayerArgs args) {
     using S = LayerSmem;
     constexpr int C = 256;
@@ -217,15 +225,25 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int rank = static_cast<int>(cluster_ctarank());
-    const int worker = static_cast<int>(blockIdx.x >> 1);
-    const int n_workers = static_cast<int>(gridDim.x >> 1);
-    const int cnt = (args.n_row_tiles - worker + n_workers - 1) / n_workers;   // row tiles of this CTA pair
+    const int crank = static_cast<int>(cluster_ctarank());
+    const int rank = crank & 1;                      // rank in the CTA pair (0 = leader: issues the MMAs)
+    const int pidx = MC ? (crank >> 1) : 0;          // which pair of the cluster
+    const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pidx));
+    constexpr int kClusterCtas = MC ? 4 : 2;
+    constexpr int kPairs = MC ? 2 : 1;
+    const int cluster_id = static_cast<int>(blockIdx.x) / kClusterCtas;
+    const int n_clusters = static_cast<int>(gridDim.x) / kClusterCtas;
+    // local row tile n of this pair is global row tile kPairs * (cluster_id + n * n_clusters) + pidx; with MC the odd one of the
+    // last unit may not exist: its loads are zero-filled by the TMA unit (batch index out of range) and nothing is stored
+    const int n_units = (args.n_row_tiles + kPairs - 1) / kPairs;
+    const int cnt = (n_units - cluster_id + n_clusters - 1) / n_clusters;
     const int n_ops = 3 * cnt;
+    const int worker = kPairs * cluster_id + pidx;   // first row tile of this pair
+    const int n_workers = kPairs * n_clusters;       // row-tile stride
 
     if (threadIdx.x == 32) {
         for (int s = 0; s < S::kAStages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); }
-        for (int s = 0; s < S::kWStages; ++s) { mbar_init(&wfull_bar[s], 1); mbar_init(&wempty_bar[s], 1); }
+        for (int s = 0; s < S::kWStages; ++s) { mbar_init(&wfull_bar[s], 1); mbar_init(&wempty_bar[s], MC ? 2 : 1); }
         for (int s = 0; s < S::kEStages; ++s) { mbar_init(&efull_bar[s], 1); mbar_init(&edone_bar[s], 4); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * kEpiWarps); }
         // z rows of local row tile n published: both gate epilogues, every epilogue warp of THIS CTA.  Two barriers (n & 1):
@@ -262,10 +280,14 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             tma_load_3d_pair(reinterpret_cast<void*>(smem + as * S::kASlotBytes), map, &afull_bar[as], c0, row, b);
             if (++as == S::kAStages) { as = 0; aph ^= 1; }
         };
-        auto load_w = [&](const CUtensorMap* map, int c0, int row) {
+        auto load_w = [&](const CUtensorMap* map, int c0, int row) {   // row: first of this CTA's 128 weight rows
             mbar_wait_tr(&wempty_bar[ws], wph ^ 1, tr_on, w_b);
             if (rank == 0) mbar_arrive_expect_tx(&wfull_bar[ws], S::kWSlotBytes * 2);
-            tma_load_2d_pair(reinterpret_cast<void*>(smem + S::kOffW + ws * S::kWSlotBytes), map, &wfull_bar[ws], c0, row);
+            uint8_t* dst = smem + S::kOffW + ws * S::kWSlotBytes;
+            if (MC)   // this CTA's half of those rows, into the same slot of the same-rank CTA of both pairs
+                tma_load_2d_pair_mc(dst + pidx * (S::kWSlotBytes / 2), map, &wfull_bar[ws], c0, row + pidx * 64, static_cast<uint16_t>(5u << rank));
+            else
+                tma_load_2d_pair(dst, map, &wfull_bar[ws], c0, row);
             if (++ws == S::kWStages) { ws = 0; wph ^= 1; }
         };
         const uint32_t halo_bytes = static_cast<uint32_t>(args.a_rows) * 128;
@@ -311,14 +333,16 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             mbar_wait_tr(&wfull_bar[ws], wph, tr_on, w_b);
             tc_fence_after();
             const uint32_t b_op = smem_w + ws * S::kWSlotBytes;
+            const bool skip = (eight && (args.flags & 2)) || (!eight && (args.flags & 4));   // timing ablations (wrong results)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint64_t da = umma_smem_desc<128>(a_op + k * 32), db = umma_smem_desc<128>(b_op + k * 32);
+                if (skip && accumulate) continue;
                 if (eight) umma_f8_pair(tacc, da, db, kIdesc8, accumulate);
                 else umma_f16_pair(tacc, da, db, kIdesc16, accumulate);
                 accumulate = 1;
             }
-            umma_commit_pair(&wempty_bar[ws]);
+            umma_commit_pair(&wempty_bar[ws], MC ? static_cast<uint16_t>(0xF) : pair_mask);   // MC: one of two arrivals in all four CTAs
             if (++ws == S::kWStages) { ws = 0; wph ^= 1; }
         };
         auto wait_a = [&]() {
@@ -327,7 +351,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             return smem_a + as * S::kASlotBytes;
         };
         auto free_a = [&]() {
-            umma_commit_pair(&aempty_bar[as]);
+            umma_commit_pair(&aempty_bar[as], pair_mask);
             if (++as == S::kAStages) { as = 0; aph ^= 1; }
         };
         const uint32_t tap_stride = static_cast<uint32_t>(args.dilation) * 128;   // taps = rows 0, d, 2d of the halo tile
@@ -357,7 +381,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                     free_a();
                 }
             }
-            umma_commit_pair(&tfull_bar[acc]);
+            umma_commit_pair(&tfull_bar[acc], pair_mask);
         }
         if (tr_on) {
             unsigned long long* t = args.trace + blockIdx.x * 16;
@@ -389,7 +413,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
         const int quad = warp & 3;
         const int grp = (warp - 2) >> 2;
         const int r_box = quad * 32 + lane;                 // row of this thread in the CTA's 128-row boxes
-        const uint32_t tempty_remote0 = map_to_cta(smem_u32(&tempty_bar[0]), 0);
+        const uint32_t tempty_remote0 = map_to_cta(smem_u32(&tempty_bar[0]), static_cast<uint32_t>(crank & ~1));
         const bool tr = tr_on && warp == 2 && lane == 0;
         long long w_f = 0, w_e = 0, t_gate = 0, t_res = 0;
         const long long t_begin = tr ? clock64() : 0;
@@ -417,7 +441,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             const int m = worker + op.n * n_workers;
             const int b = m / args.tiles_per_batch;
             const int t = (m % args.tiles_per_batch) * kTileRows + rank * kTileM + r_box;   // this thread's row in the batch item
-            const bool row_ok = t < args.T;
+            const bool row_ok = t < args.T && b < args.B;
             const long long row = static_cast<long long>(b) * args.T + t;
             mbar_wait_tr(&tfull_bar[acc], (j >> 1) & 1, tr, w_f);
             tc_fence_after();

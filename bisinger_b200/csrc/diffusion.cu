@@ -292,7 +292,8 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     // one fused kernel per ResidualBlock (diffnet_layer.cuh) in the fp16x2 mode; BSG_NO_FUSE=1 keeps the two-launch path
     use_fused = use_pair && terms == 2;
     if (const char* nf = std::getenv("BSG_NO_FUSE")) use_fused = use_fused && !(nf[0] == '1');
-    if (use_fused) { LayerArgs la{}; launch_diffnet_layer(la, nullptr); }
+    if (const char* mc = std::getenv("BSG_LAYER_MC")) fused_mc = mc[0] == '1';
+    if (use_fused) { LayerArgs la{}; launch_diffnet_layer(la, nullptr, fused_mc); }
     if (gate_mode == 2) launch_conv_gemm(256, terms, EPI_GATE, none, nullptr, 2);
     if (skip_mode == 2) launch_conv_gemm(kSkipTilePair, terms, EPI_RELU_BF16, none, nullptr, 2);
 }
@@ -435,9 +436,10 @@ LayerArgs DiffusionPlan::fused_args(Workspace& w, int l, const float* lut_t) {
     a.xa8 = (l & 1) ? w.m_xa8_b : w.m_xa8;
     a.z = w.m_z[0];
     CUtensorMap unused;
-    ly.g1.maps(128, a.wg16, unused);
-    a.wg8 = ly.g1.map8();
-    ly.g2.maps(128, a.wr[0], a.wr[1]);
+    const int wbox = fused_mc ? 64 : 128;   // weight rows one CTA loads per tile (multicast: half of its 128)
+    ly.g1.maps(wbox, a.wg16, unused);
+    a.wg8 = ly.g1.map8(wbox);
+    ly.g2.maps(wbox, a.wr[0], a.wr[1]);
     a.cp = w.m_cp[l];
     a.xe = w.m_xe[l & 1];
     a.B = w.B;
@@ -494,7 +496,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
     auto run = [&](int n) {
         for (int i = 0; i < n; ++i) {
             const int l = i % L;
-            if (which == 3) launch_diffnet_layer(fused_args(w, l, lut.as<float>()), st);
+            if (which == 3) launch_diffnet_layer(fused_args(w, l, lut.as<float>()), st, fused_mc);
             else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
             else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
             else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
@@ -521,7 +523,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
         if (which == 3) {
             LayerArgs la = fused_args(w, 1, lut.as<float>());
             la.trace = tb.as<unsigned long long>();
-            launch_diffnet_layer(la, st);
+            launch_diffnet_layer(la, st, fused_mc);
         } else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, a, st, gate_mode);
         else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, a, st);
         else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, a, st, skip_mode);
@@ -577,7 +579,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
     static const int fuse_layers = [] { const char* e = std::getenv("BSG_FUSE_LAYERS"); return e ? std::atoi(e) : 1 << 30; }();   // debugging: even count
     for (int l = 0; l < L; ++l) {
         if (use_fused && l < fuse_layers) {
-            launch_diffnet_layer(fused_args(w, l, lut_t), st);
+            launch_diffnet_layer(fused_args(w, l, lut_t), st, fused_mc);
             ++launches, ++g_launch_count;
             continue;
         }

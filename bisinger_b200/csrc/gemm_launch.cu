@@ -116,19 +116,41 @@ void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
 
 }  // namespace
 
-// One fused DiffNet layer (diffnet_layer.cuh): CTA pairs over the 256-row tiles, persistent.
-void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream) {
+// One fused DiffNet layer (diffnet_layer.cuh): persistent CTA pairs over the 256-row tiles, or (mc) clusters of two pairs
+// with multicast weight tiles (weight tensor maps must then have 64-row boxes).
+template <int MC>
+static void launch_layer_inst(const LayerArgs& args, cudaStream_t stream) {
+    auto kern = diffnet_layer_kernel<MC>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(diffnet_layer_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayerSmem::kTotal); });
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LayerSmem::kTotal); });
     B200_CUDA(attr_err);
     static int sms = 0;
     if (sms == 0) sms = device_sm_count();
+    constexpr int kCtas = MC ? 4 : 2;
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        if (MC) {
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(4 * 64);
+            q.blockDim = dim3(kLayerThreads);
+            q.dynamicSmemBytes = LayerSmem::kTotal;
+            cudaLaunchAttribute qa;
+            qa.id = cudaLaunchAttributeClusterDimension;
+            qa.val.clusterDim.x = 4; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
+            q.attrs = &qa;
+            q.numAttrs = 1;
+            B200_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q));
+            B200_CHECK(max_clusters > 0, "no 4-CTA cluster of the fused layer kernel fits on this device");
+        } else {
+            max_clusters = sms / 2;
+        }
+    }
     if (args.n_row_tiles <= 0) return;
     B200_CHECK(args.a_rows >= kTileM && args.a_rows * 128 <= LayerSmem::kASlotBytes && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
-    const int pairs = sms / 2;
+    const int units = MC ? (args.n_row_tiles + 1) / 2 : args.n_row_tiles;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * (args.n_row_tiles < pairs ? args.n_row_tiles : pairs));
+    cfg.gridDim = dim3(kCtas * (units < max_clusters ? units : max_clusters));
     cfg.blockDim = dim3(kLayerThreads);
     cfg.dynamicSmemBytes = LayerSmem::kTotal;
     cfg.stream = stream;
@@ -140,14 +162,29 @@ void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream) {
         ++na;
     }
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.x = kCtas;
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = 1;
     ++na;
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    B200_CUDA(cudaLaunchKernelEx(&cfg, diffnet_layer_kernel<0>, args));
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
     B200_CUDA(cudaGetLastError());
+}
+void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream, bool mc) {
+    if (mc) launch_layer_inst<1>(args, stream);
+    else launch_layer_inst<0>(args, stream);
+}
+
+int conv_gemm_weight_slots(int n_tile, int terms) {
+    if (terms != 1) return 0;
+    switch (n_tile) {
+        case 32: return GemmSmem<32, 1, false>::kBStages;
+        case 64: return GemmSmem<64, 1, false>::kBStages;
+        case 128: return GemmSmem<128, 1, false>::kBStages;
+        case 256: return GemmSmem<256, 1, false>::kBStages;
+        default: return 0;
+    }
 }
 
 #define B200_CASE(NT, TM, EP) \

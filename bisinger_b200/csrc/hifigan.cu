@@ -412,6 +412,8 @@ void HifiganPlan::forward(const float* mel, const float* f0, const float* rand_i
         a.amap[0] = make_act_tmap(a_ptr, B, Lrows, cv.cin, a_pitch, rows_box);
         a.amap[1] = a.amap[0];
         cv.w.maps(nt, a.wmap[0], a.wmap[1]);
+        a.k_steps = cv.cin >= kBlockK ? 0 : (cv.cin + 15) / 16;
+        a.w_resident = (a.n_tiles_n == 1 && static_cast<int>(shifts.size()) * (cp / kBlockK) <= conv_gemm_weight_slots(nt, 1)) ? 1 : 0;
         a.epi = epi;
         a.epi.bias = cv.bias.as<float>();
         launch_conv_gemm(nt, 1, EPI_BIAS_ACT, a, st);

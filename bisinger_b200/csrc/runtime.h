@@ -138,6 +138,9 @@ inline CUtensorMap make_w_tmap(const void* base, int N, int K, int n_tile, int r
 }
 
 int device_sm_count();
+// weight-ring slots of the single-CTA conv_gemm instantiation (n_tile, terms): a convolution with n_taps * n_kb <= this many
+// weight tiles may keep them resident (ConvGemmArgs::w_resident)
+int conv_gemm_weight_slots(int n_tile, int terms);
 
 // Launch one instantiation of conv_gemm_kernel (defined in gemm_launch.cu)
 // pair = 1: 2-CTA clusters on 256-row tiles (tcgen05 cta_group::2); the weight tensor map box must then be n_tile/2 rows
@@ -146,7 +149,7 @@ void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, 
 
 // One fused DiffNet layer (diffnet_layer.cuh); args.n_row_tiles == 0 only sets the kernel attributes up
 struct LayerArgs;
-void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream);
+void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream, bool mc = false);
 
 // fills the tile-geometry fields of args from (B, L, N_total, n_tile)
 inline void set_geometry(ConvGemmArgs& a, int B, int L, int n_total, int n_tile, bool pair = false) {
@@ -193,13 +196,15 @@ struct PackedW {
     DevBuf lo8;            // fp16x2 packing only: e5m2(w * 2^p - hi), the weight-correction operand of the fp8 MMAs
     CUtensorMap tm8;       // box = 128 K-columns (bytes) x 128 rows
     bool tm8_ok = false;
-    const CUtensorMap& map8() {
-        if (!tm8_ok) {
+    int tm8_rows = 0;
+    const CUtensorMap& map8(int box_rows = 128) {
+        if (!tm8_ok || tm8_rows != box_rows) {
             const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
             const uint64_t strides[1] = {static_cast<uint64_t>(K)};
-            const uint32_t box[2] = {128, 128};
+            const uint32_t box[2] = {128, static_cast<uint32_t>(box_rows)};
             tm8 = make_tmap_ex(lo8.p, 1, 128, 2, dims, strides, box);
             tm8_ok = true;
+            tm8_rows = box_rows;
         }
         return tm8;
     }
