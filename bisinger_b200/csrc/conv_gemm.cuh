@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                     const uint32_t b_lo = b_hi + S::kBPartBytes;
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        if (k >= k_steps) break;
+                        if (k >= k_steps) continue;   // (no break: the four steps stay unrolled, the skipped ones are predicated off)
                         const uint64_t da = umma_smem_desc<128>(a_hi + k * 32);
                         const uint64_t db = umma_smem_desc<128>(b_hi + k * 32);
                         if constexpr (PAIR) {

@@ -31,31 +31,37 @@
 
 namespace b200 {
 
-struct LayerArgs {
-    CUtensorMap xa16;      // conv input fp16 [B][T][C], box = 64 channels x a_rows rows
-    CUtensorMap xa8;       // conv input e4m3 [B][T][C], box = 128 channels x a_rows rows
-    CUtensorMap z;         // all-layer gated activations fp16 [B][T][L*C], box = 64 x 128
-    CUtensorMap wg16;      // dilated-conv weights fp16(W 2^p) [2C (gate/filter permuted)][3C], box = 64 x 128
-    CUtensorMap wg8;       // e5m2 correction of the same, box = 128 x 128
-    CUtensorMap wr[2];     // residual half of the output projection fp16 hi / lo [C][C], box = 64 x 128
+// per-layer parameters, in global memory (tensor maps must be 64-byte aligned)
+struct alignas(128) LayerParams {
+    CUtensorMap wg16;      // dilated-conv weights fp16(W 2^p) [2C (gate/filter permuted)][3C], box = 64 x 128 (64 with multicast)
+    CUtensorMap wg8;       // e5m2 correction of the same, box = 128 x 128 (64)
+    CUtensorMap wr[2];     // residual half of the output projection fp16 hi / lo [C][C], box = 64 x 128 (64)
     CUtensorMap cp;        // conditioner projection + biases f32 [B][T][2C] (packed column order), box = 16 x 128, SWIZZLE_64B
-    CUtensorMap xe;        // the conv input fp16 [B][T][C] once more, as the epilogue reads it: box = 32 channels x 128 rows, SWIZZLE_64B
+    const float* bias_r;   // [C] residual bias
+    float gscale, rscale;  // 2^-p of the gate / residual weight packing
+    int dilation;
+    int pad_;
+};
+
+struct LayerArgs {
+    CUtensorMap xa16[2];   // conv input fp16 [B][T][C], box = 64 channels x a_rows rows; layer l reads [l & 1] and writes the other
+    CUtensorMap xa8[2];    // conv input e4m3 [B][T][C], box = 128 channels x a_rows rows
+    CUtensorMap xe[2];     // the fp16 conv input once more, as the epilogue reads it: box = 32 channels x 128 rows, SWIZZLE_64B
+    CUtensorMap z;         // all-layer gated activations fp16 [B][T][L*C], box = 64 x 128
+    const LayerParams* tab;   // [total layers]
+    int layer0, n_layers;  // layers [layer0, layer0 + n_layers) run in this launch; total_layers: the last one writes no conv input
+    int total_layers;
     int B, T;
     int tiles_per_batch;   // ceil(T / 256)
     int n_row_tiles;       // B * tiles_per_batch
-    int dilation;
     int a_rows;            // rows of the xa halo boxes (128 + 2 * max dilation, multiple of 8)
-    int z_col0;            // first column of this layer in the z matrix
-    int z_pitch;           // elements per row of the z matrix
+    int z_pitch;           // elements per row of the z matrix (layer l owns columns [l*C, (l+1)*C))
     __half* z_out;         // z matrix base
-    __half* xa16_out;      // next layer's conv input (null after the last layer); NOT the buffer behind xa16 / xa8: other tiles
-                           // still read halo rows of this layer's input while this tile's rows are written
-    uint8_t* xa8_out;
-    const float* bias_r;   // [C] residual bias
-    const float* dvec;     // [C] next layer's step embedding (null after the last layer)
-    const float* dcur;     // [C] this layer's step embedding: the residual stream is carried as fp16(x + d), x = that - d
-    float gscale, rscale;  // 2^-p of the gate / residual weight packing
-    int flags;             // timing ablations (bit 0: no gate math)
+    __half* xa16_out[2];   // conv input buffers as plain pointers (layer l writes [(l + 1) & 1])
+    uint8_t* xa8_out[2];
+    const float* lut_t;    // [total layers][C] step embeddings d_l of this diffusion step
+    int* flags;            // n_layers > 1: [total layers][n_row_tiles] completion counters, zero before the launch
+    int flags_ablate;      // timing ablations (bit 1: no fp8 MMAs, bit 2: no fp16 MMAs)
     unsigned long long* trace;
 };
 
@@ -253,11 +259,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {   // per-column vectors of the residual epilogue (weights / LUT: not written by the previous kernel)
-        const int c = threadIdx.x - 64;
-        vec[c] = args.bias_r[c] - args.dcur[c];            // x = fp16 conv input - d_cur, then + residual bias
-        vec[256 + c] = args.dvec ? args.dvec[c] : 0.0f;
-    }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -267,6 +268,29 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const bool tr_on = args.trace != nullptr;
+    const int layer_end = args.layer0 + args.n_layers;
+    // Several layers in one launch: row tile m of layer l reads conv-input rows that the row tiles m-1, m, m+1 (of the same
+    // batch item) of layer l-1 wrote IN THIS LAUNCH, possibly on other SMs.  Each of their 16 epilogue warps fences its
+    // stores and bumps flags[l-1][tile]; a TMA-issuing thread polls (acquire) and orders the generic-proxy writes before
+    // its async-proxy reads.  Pairs therefore run ahead into the next layer wherever their inputs are ready: the partial
+    // last round of a layer (256 row tiles over 74 pairs) overlaps the next layer instead of idling.
+    auto wait_inputs = [&](int l, int m, long long& acc_wait) {
+        if (args.flags == nullptr || l == args.layer0) return;
+        const long long t0w = tr_on ? clock64() : 0;
+        const int ti = m % args.tiles_per_batch;
+        const int lo = ti > 0 ? m - 1 : m, hi = (ti + 1 < args.tiles_per_batch) ? m + 1 : m;
+        const int* f = args.flags + static_cast<size_t>(l - 1) * args.n_row_tiles;
+        for (int mm = lo; mm <= hi; ++mm) {
+            int v;
+            unsigned spins = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(f + mm) : "memory");
+                if (v < 2 * kEpiWarps && (++spins & 15) == 0) __nanosleep(64);
+            } while (v < 2 * kEpiWarps);
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (tr_on) acc_wait += clock64() - t0w;
+    };
 
     if (warp == 0 && lane == 0) {
         // ================= operand producer (one per CTA) =================
@@ -291,31 +315,40 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             if (++ws == S::kWStages) { ws = 0; wph ^= 1; }
         };
         const uint32_t halo_bytes = static_cast<uint32_t>(args.a_rows) * 128;
-        for (int j = 0; j < n_ops; ++j) {
-            const LayerOp op = layer_op(j, cnt);
-            const int m = worker + op.n * n_workers;
-            const int b = m / args.tiles_per_batch;
-            const int t0 = (m % args.tiles_per_batch) * kTileRows + rank * kTileM;
-            if (op.kind == 0) {
-                const int wrow = op.h * 256 + rank * 128;
-                for (int k8 = 0; k8 < 2; ++k8) {
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const int kb = 2 * k8 + kk;
-                        load_a(&args.xa16, halo_bytes, kb * 64, t0 - args.dilation, b);
-                        for (int tp = 0; tp < 3; ++tp) load_w(&args.wg16, tp * C + kb * 64, wrow);
+        long long w_dep = 0;
+        int ng0 = 0;   // local row tiles finished in earlier layers (z barrier parity runs on across layers)
+        for (int l = args.layer0; l < layer_end; ++l, ng0 += cnt) {
+            const LayerParams& lp = args.tab[l];
+            const int dil = lp.dilation;
+            for (int j = 0; j < n_ops; ++j) {
+                const LayerOp op = layer_op(j, cnt);
+                const int m = worker + op.n * n_workers;
+                const int b = m / args.tiles_per_batch;
+                const int t0 = (m % args.tiles_per_batch) * kTileRows + rank * kTileM;
+                if (op.kind == 0) {
+                    if (op.h == 0) wait_inputs(l, m, w_dep);
+                    const int wrow = op.h * 256 + rank * 128;
+                    for (int k8 = 0; k8 < 2; ++k8) {
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const int kb = 2 * k8 + kk;
+                            load_a(&args.xa16[l & 1], halo_bytes, kb * 64, t0 - dil, b);
+                            for (int tp = 0; tp < 3; ++tp) load_w(&lp.wg16, tp * C + kb * 64, wrow);
+                        }
+                        load_a(&args.xa8[l & 1], halo_bytes, k8 * 128, t0 - dil, b);
+                        for (int tp = 0; tp < 3; ++tp) load_w(&lp.wg8, tp * C + k8 * 128, wrow);
                     }
-                    load_a(&args.xa8, halo_bytes, k8 * 128, t0 - args.dilation, b);
-                    for (int tp = 0; tp < 3; ++tp) load_w(&args.wg8, tp * C + k8 * 128, wrow);
-                }
-            } else {
-                mbar_wait_tr(&zfull_bar[op.n & 1], static_cast<uint32_t>((op.n >> 1) & 1), tr_on, w_z);   // this CTA's z rows of tile n are in global memory
-                for (int kb = 0; kb < 4; ++kb) {
-                    load_a(&args.z, kTileM * 128, args.z_col0 + kb * 64, t0, b);
-                    load_w(&args.wr[0], kb * 64, rank * 128);
-                    load_w(&args.wr[1], kb * 64, rank * 128);
+                } else {
+                    const int ng = ng0 + op.n;
+                    mbar_wait_tr(&zfull_bar[ng & 1], static_cast<uint32_t>((ng >> 1) & 1), tr_on, w_z);   // this CTA's z rows of the tile are in global memory
+                    for (int kb = 0; kb < 4; ++kb) {
+                        load_a(&args.z, kTileM * 128, l * C + kb * 64, t0, b);
+                        load_w(&lp.wr[0], kb * 64, rank * 128);
+                        load_w(&lp.wr[1], kb * 64, rank * 128);
+                    }
                 }
             }
         }
+        if (tr_on) args.trace[blockIdx.x * 16 + 15] = w_dep;
         if (tr_on) {
             unsigned long long* t = args.trace + blockIdx.x * 16;
             t[4] = clock64() - t_begin; t[5] = w_a; t[6] = w_b; t[9] = w_z;
@@ -333,7 +366,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             mbar_wait_tr(&wfull_bar[ws], wph, tr_on, w_b);
             tc_fence_after();
             const uint32_t b_op = smem_w + ws * S::kWSlotBytes;
-            const bool skip = (eight && (args.flags & 2)) || (!eight && (args.flags & 4));   // timing ablations (wrong results)
+            const bool skip = (eight && (args.flags_ablate & 2)) || (!eight && (args.flags_ablate & 4));   // timing ablations (wrong results)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint64_t da = umma_smem_desc<128>(a_op + k * 32), db = umma_smem_desc<128>(b_op + k * 32);
@@ -354,34 +387,37 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             umma_commit_pair(&aempty_bar[as], pair_mask);
             if (++as == S::kAStages) { as = 0; aph ^= 1; }
         };
-        const uint32_t tap_stride = static_cast<uint32_t>(args.dilation) * 128;   // taps = rows 0, d, 2d of the halo tile
-        for (int j = 0; j < n_ops; ++j) {
-            const int kind = layer_op(j, cnt).kind;
-            const int acc = j & 1;
-            mbar_wait_tr(&tempty_bar[acc], ((j >> 1) & 1) ^ 1, tr_on, w_t);
-            tc_fence_after();
-            tacc = tmem_base + acc * 256;
-            accumulate = 0;
-            if (kind == 0) {
-                for (int k8 = 0; k8 < 2; ++k8) {
-                    for (int kk = 0; kk < 2; ++kk) {
+        int jg = 0;   // ops issued so far: accumulator buffer = jg & 1, across layers
+        for (int l = args.layer0; l < layer_end; ++l) {
+            const uint32_t tap_stride = static_cast<uint32_t>(args.tab[l].dilation) * 128;   // taps = rows 0, d, 2d of the halo tile
+            for (int j = 0; j < n_ops; ++j, ++jg) {
+                const int kind = layer_op(j, cnt).kind;
+                const int acc = jg & 1;
+                mbar_wait_tr(&tempty_bar[acc], ((jg >> 1) & 1) ^ 1, tr_on, w_t);
+                tc_fence_after();
+                tacc = tmem_base + acc * 256;
+                accumulate = 0;
+                if (kind == 0) {
+                    for (int k8 = 0; k8 < 2; ++k8) {
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint32_t a_slot = wait_a();
+                            for (int tp = 0; tp < 3; ++tp) mma_slot(a_slot + tp * tap_stride, false);
+                            free_a();
+                        }
                         const uint32_t a_slot = wait_a();
-                        for (int tp = 0; tp < 3; ++tp) mma_slot(a_slot + tp * tap_stride, false);
+                        for (int tp = 0; tp < 3; ++tp) mma_slot(a_slot + tp * tap_stride, true);
                         free_a();
                     }
-                    const uint32_t a_slot = wait_a();
-                    for (int tp = 0; tp < 3; ++tp) mma_slot(a_slot + tp * tap_stride, true);
-                    free_a();
+                } else {
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint32_t a_slot = wait_a();
+                        mma_slot(a_slot, false);
+                        mma_slot(a_slot, false);
+                        free_a();
+                    }
                 }
-            } else {
-                for (int kb = 0; kb < 4; ++kb) {
-                    const uint32_t a_slot = wait_a();
-                    mma_slot(a_slot, false);
-                    mma_slot(a_slot, false);
-                    free_a();
-                }
+                umma_commit_pair(&tfull_bar[acc], pair_mask);
             }
-            umma_commit_pair(&tfull_bar[acc], pair_mask);
         }
         if (tr_on) {
             unsigned long long* t = args.trace + blockIdx.x * 16;
@@ -391,20 +427,24 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
         // ================= epilogue-operand producer: cp boxes (gate ops) / conv-input boxes (residual ops) =================
         // gate op, 16 boxes of 16 fp32 columns of cp: box i -> chunk c = i / 4, column group g = (i / 2) % 2, i % 2 = gate / filter
         // columns.  residual op, 8 boxes of 32 fp16 channels of the conv input: box i -> chunk c = i / 2, group g = i % 2.
-        long long w_e = 0;
+        long long w_e = 0, w_dep = 0;
         int q = 0;
-        for (int j = 0; j < n_ops; ++j) {
-            const LayerOp op = layer_op(j, cnt);
-            const int m = worker + op.n * n_workers;
-            const int b = m / args.tiles_per_batch;
-            const int row = (m % args.tiles_per_batch) * kTileRows + rank * kTileM;
-            const int nb = op.kind == 0 ? kGateBoxes : kResBoxes;
-            for (int i = 0; i < nb; ++i, ++q) {
-                const int s = q % S::kEStages;
-                if (q >= S::kEStages) mbar_wait_tr(&edone_bar[s], ((q / S::kEStages) - 1) & 1, tr_on, w_e);   // previous occupant consumed by its four warps
-                const int col = op.kind == 0 ? op.h * 256 + ((i >> 1) & 1) * 64 + (i >> 2) * 16 + (i & 1) * 128 : (i & 1) * 128 + (i >> 1) * 32;
-                mbar_arrive_expect_tx(&efull_bar[s], S::kEBoxBytes);
-                tma_load_3d_local(smem_e + s * S::kEBoxBytes, op.kind == 0 ? &args.cp : &args.xe, &efull_bar[s], col, row, b);
+        for (int l = args.layer0; l < layer_end; ++l) {
+            const LayerParams& lp = args.tab[l];
+            for (int j = 0; j < n_ops; ++j) {
+                const LayerOp op = layer_op(j, cnt);
+                const int m = worker + op.n * n_workers;
+                const int b = m / args.tiles_per_batch;
+                const int row = (m % args.tiles_per_batch) * kTileRows + rank * kTileM;
+                const int nb = op.kind == 0 ? kGateBoxes : kResBoxes;
+                if (op.kind == 1) wait_inputs(l, m, w_dep);   // the boxes of a residual op are rows of this layer's conv input
+                for (int i = 0; i < nb; ++i, ++q) {
+                    const int s = q % S::kEStages;
+                    if (q >= S::kEStages) mbar_wait_tr(&edone_bar[s], ((q / S::kEStages) - 1) & 1, tr_on, w_e);   // previous occupant consumed by its four warps
+                    const int col = op.kind == 0 ? op.h * 256 + ((i >> 1) & 1) * 64 + (i >> 2) * 16 + (i & 1) * 128 : (i & 1) * 128 + (i >> 1) * 32;
+                    mbar_arrive_expect_tx(&efull_bar[s], S::kEBoxBytes);
+                    tma_load_3d_local(smem_e + s * S::kEBoxBytes, op.kind == 0 ? &lp.cp : &args.xe[l & 1], &efull_bar[s], col, row, b);
+                }
             }
         }
         if (tr_on) args.trace[blockIdx.x * 16 + 13] = w_e;
@@ -435,15 +475,30 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             if (lane == 0) mbar_arrive(&zfull_bar[z_tile & 1]);
             z_pending = false;
         };
-        for (int j = 0; j < n_ops; ++j) {
+        int jg = 0, ng0 = 0;      // ops / local row tiles of earlier layers (accumulator and z-barrier parities run on across layers)
+        for (int l = args.layer0; l < layer_end; ++l, ng0 += cnt) {
+          const LayerParams& lpar = args.tab[l];
+          const float gscale = lpar.gscale, rscale = lpar.rscale;
+          const bool has_next = l + 1 < args.total_layers;
+          __half* const xa16_out = args.xa16_out[(l + 1) & 1];
+          uint8_t* const xa8_out = args.xa8_out[(l + 1) & 1];
+          {   // per-column vectors of this layer's residual epilogue: vec[0,256) = residual bias - d_l (the residual stream is
+              // fp16(x + d_l)), vec[256,512) = d_{l+1}.  All epilogue warps are past the previous layer's last use.
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              const int c = threadIdx.x - 64;
+              vec[c] = lpar.bias_r[c] - args.lut_t[static_cast<size_t>(l) * C + c];
+              vec[256 + c] = has_next ? args.lut_t[static_cast<size_t>(l + 1) * C + c] : 0.0f;
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+          }
+          for (int j = 0; j < n_ops; ++j, ++jg) {
             const LayerOp op = layer_op(j, cnt);
-            const int acc = j & 1;
+            const int acc = jg & 1;
             const int m = worker + op.n * n_workers;
             const int b = m / args.tiles_per_batch;
             const int t = (m % args.tiles_per_batch) * kTileRows + rank * kTileM + r_box;   // this thread's row in the batch item
             const bool row_ok = t < args.T && b < args.B;
             const long long row = static_cast<long long>(b) * args.T + t;
-            mbar_wait_tr(&tfull_bar[acc], (j >> 1) & 1, tr, w_f);
+            mbar_wait_tr(&tfull_bar[acc], (jg >> 1) & 1, tr, w_f);
             tc_fence_after();
             const long long t_op = tr ? clock64() : 0;
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
@@ -452,8 +507,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             if (op.kind == 0) {
                 // ---- gate: z = sigmoid(acc_g + cp_g) * tanh(acc_f + cp_f)   (net.py:71-74)
                 // (loops kept rolled: with the four roles' code paths resident the unrolled epilogue stalled on instruction fetch)
-                const float hs = 0.5f * args.gscale;
-                __half* zrow = args.z_out + row * args.z_pitch + args.z_col0 + op.h * 128;
+                const float hs = 0.5f * gscale;
+                __half* zrow = args.z_out + row * args.z_pitch + l * C + op.h * 128;
                 // one 16-channel chunk; vg / vf: its gate / filter accumulator columns (already waited for)
                 auto gate_chunk = [&](int c, const uint32_t (&vg)[16], const uint32_t (&vf)[16]) {
                     const int cg = grp * 64 + c * 16;          // gate columns [cg, cg+16), filter columns +128
@@ -473,8 +528,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                         // sigmoid(g) = 0.5 tanh(g/2) + 0.5: the gate pre-activations are formed already halved
                         const float g0 = fmaf(__uint_as_float(vg[4 * k]), hs, 0.5f * pg[k].x), g1 = fmaf(__uint_as_float(vg[4 * k + 1]), hs, 0.5f * pg[k].y);
                         const float g2 = fmaf(__uint_as_float(vg[4 * k + 2]), hs, 0.5f * pg[k].z), g3 = fmaf(__uint_as_float(vg[4 * k + 3]), hs, 0.5f * pg[k].w);
-                        const float f0 = fmaf(__uint_as_float(vf[4 * k]), args.gscale, pf[k].x), f1 = fmaf(__uint_as_float(vf[4 * k + 1]), args.gscale, pf[k].y);
-                        const float f2 = fmaf(__uint_as_float(vf[4 * k + 2]), args.gscale, pf[k].z), f3 = fmaf(__uint_as_float(vf[4 * k + 3]), args.gscale, pf[k].w);
+                        const float f0 = fmaf(__uint_as_float(vf[4 * k]), gscale, pf[k].x), f1 = fmaf(__uint_as_float(vf[4 * k + 1]), gscale, pf[k].y);
+                        const float f2 = fmaf(__uint_as_float(vf[4 * k + 2]), gscale, pf[k].z), f3 = fmaf(__uint_as_float(vf[4 * k + 3]), gscale, pf[k].w);
                         zz[2 * k] = pack_half2_nc(gate_half(g0, f0), gate_half(g1, f1));
                         zz[2 * k + 1] = pack_half2_nc(gate_half(g2, f2), gate_half(g3, f3));
                     }
@@ -508,7 +563,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                     gate_chunk(c + 1, bg, bf);
                 }
                 z_pending = true;
-                z_tile = op.n;
+                z_tile = ng0 + op.n;
 #ifdef B200_PUBLISH_NOW
                 publish_z();
 #endif
@@ -519,7 +574,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                 // The residual stream is carried only as the fp16 conv input: x = fp16(x + d_cur) - d_cur (tools/precision_study.py
                 // "state fp16": 1.5-2.2e-3 vs 1.2-1.3e-3 max mel error).  No fp32 x is read or written: the epilogue streams the conv
                 // input once more (32-channel boxes) and stores only the next layer's fp16 / e4m3 conv input.
-                const bool has_next = args.xa16_out != nullptr;
                 auto res_chunk = [&](int c, const uint32_t (&v)[32]) {   // 32 channels
                     const int cl = grp * 128 + c * 32;
                     const int q = q_op + 2 * c + grp;
@@ -546,10 +600,10 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                         for (int hh = 0; hh < 2; ++hh) {
                             const int c4 = cl + 8 * k + 4 * hh;
                             const float4 bb = lds128(vec_s + c4 * 4), dd = lds128(vec_s + (256 + c4) * 4);
-                            const float y0 = (y[4 * hh] + fmaf(__uint_as_float(v[8 * k + 4 * hh]), args.rscale, bb.x)) * rs2 + dd.x;
-                            const float y1 = (y[4 * hh + 1] + fmaf(__uint_as_float(v[8 * k + 4 * hh + 1]), args.rscale, bb.y)) * rs2 + dd.y;
-                            const float y2 = (y[4 * hh + 2] + fmaf(__uint_as_float(v[8 * k + 4 * hh + 2]), args.rscale, bb.z)) * rs2 + dd.z;
-                            const float y3 = (y[4 * hh + 3] + fmaf(__uint_as_float(v[8 * k + 4 * hh + 3]), args.rscale, bb.w)) * rs2 + dd.w;
+                            const float y0 = (y[4 * hh] + fmaf(__uint_as_float(v[8 * k + 4 * hh]), rscale, bb.x)) * rs2 + dd.x;
+                            const float y1 = (y[4 * hh + 1] + fmaf(__uint_as_float(v[8 * k + 4 * hh + 1]), rscale, bb.y)) * rs2 + dd.y;
+                            const float y2 = (y[4 * hh + 2] + fmaf(__uint_as_float(v[8 * k + 4 * hh + 2]), rscale, bb.z)) * rs2 + dd.z;
+                            const float y3 = (y[4 * hh + 3] + fmaf(__uint_as_float(v[8 * k + 4 * hh + 3]), rscale, bb.w)) * rs2 + dd.w;
                             h16[4 * k + 2 * hh] = pack_half2_sat(y0, y1);          // saturating: an out-of-range activation must not become inf
                             h16[4 * k + 2 * hh + 1] = pack_half2_sat(y2, y3);
                             h8[2 * k + hh] = pack_e4m3x4(y0, y1, y2, y3);
@@ -559,9 +613,9 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                     if (lane == 0) mbar_arrive_relaxed(&edone_bar[sx]);   // after the arithmetic that consumed the box (see the gate loop)
                     if (row_ok && has_next) {
                         // one row = 64 contiguous bytes of the fp16 and 32 of the e4m3 conv input: full 32-byte sectors
-                        stg256(args.xa16_out + row * C + cl, reinterpret_cast<const uint32_t(&)[8]>(h16[0]));
-                        stg256(args.xa16_out + row * C + cl + 16, reinterpret_cast<const uint32_t(&)[8]>(h16[8]));
-                        stg256(args.xa8_out + row * C + cl, h8);
+                        stg256(xa16_out + row * C + cl, reinterpret_cast<const uint32_t(&)[8]>(h16[0]));
+                        stg256(xa16_out + row * C + cl + 16, reinterpret_cast<const uint32_t(&)[8]>(h16[8]));
+                        stg256(xa8_out + row * C + cl, h8);
                     }
                 };
                 uint32_t va[32], vb[32];
@@ -585,7 +639,15 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote_relaxed(tempty_remote0 + acc * 8);   // TMEM reads ordered by tcgen05.wait::ld + fence
+            if (op.kind == 1 && args.flags != nullptr && l + 1 < layer_end) {
+                // this warp's rows of the next layer's conv input are written: make them visible device-wide, then count the
+                // warp in (16 warps per row tile; readers: wait_inputs)
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(args.flags + static_cast<size_t>(l) * args.n_row_tiles + m) : "memory");
+            }
             if (tr) { if (op.kind == 0) t_gate += clock64() - t_op; else t_res += clock64() - t_op; }
+          }
         }
         if (z_pending) publish_z();
         if (tr) {

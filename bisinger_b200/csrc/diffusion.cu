@@ -144,7 +144,8 @@ struct DiffusionPlan::Workspace {
     CUtensorMap m_xa16_b, m_xa8_b;
     CUtensorMap m_xin[2], m_cond[2], m_xa[2], m_z[2], m_s[2], m_h[2];
     CUtensorMap m_xa8, m_xe[2];      // fused layer kernel: 8-bit conv input; the fp16 conv input buffers as the epilogue reads them
-    std::vector<CUtensorMap> m_cp;   // ... and the conditioner projection of every layer
+    DevBuf layer_tab;                // fused layer kernel: LayerParams[L] (weight / conditioner-projection tensor maps, scales) in device memory
+    DevBuf layer_flags;              // ... and the row-tile completion counters of a multi-layer launch [L][row tiles]
     cudaGraphExec_t graph = nullptr;
     bool graph_has_mask = false;
     ~Workspace() {
@@ -293,6 +294,7 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     use_fused = use_pair && terms == 2;
     if (const char* nf = std::getenv("BSG_NO_FUSE")) use_fused = use_fused && !(nf[0] == '1');
     if (const char* mc = std::getenv("BSG_LAYER_MC")) fused_mc = mc[0] == '1';
+    if (const char* sk = std::getenv("BSG_LAYER_STACK")) fused_stack = sk[0] == '1';
     if (use_fused) { LayerArgs la{}; launch_diffnet_layer(la, nullptr, fused_mc); }
     if (gate_mode == 2) launch_conv_gemm(256, terms, EPI_GATE, none, nullptr, 2);
     if (skip_mode == 2) launch_conv_gemm(kSkipTilePair, terms, EPI_RELU_BF16, none, nullptr, 2);
@@ -353,8 +355,26 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
         w->m_xa8_b = make_act8_tmap(w->xa8_b.p, B, T, C, kXaBoxRows);
         w->m_xe[1] = make_epi16_tmap(w->xa16_b.p, B, T, C);
         w->m_xe[0] = make_epi16_tmap(w->xa_hi.p, B, T, C);
-        for (int l = 0; l < cfg.residual_layers; ++l)
-            w->m_cp.push_back(make_f32_tmap(w->cp.as<float>() + static_cast<size_t>(l) * rows * 2 * C, B, T, 2 * C));
+        const int wbox = fused_mc ? 64 : 128;   // weight rows one CTA loads per tile (multicast: half of its 128)
+        std::vector<LayerParams> tab(cfg.residual_layers);
+        for (int l = 0; l < cfg.residual_layers; ++l) {
+            Layer& ly = layers[l];
+            LayerParams& lp = tab[l];
+            CUtensorMap unused;
+            ly.g1.maps(wbox, lp.wg16, unused);
+            lp.wg8 = ly.g1.map8(wbox);
+            ly.g2.maps(wbox, lp.wr[0], lp.wr[1]);
+            lp.cp = make_f32_tmap(w->cp.as<float>() + static_cast<size_t>(l) * rows * 2 * C, B, T, 2 * C);
+            lp.bias_r = ly.g2_bias.as<float>();
+            lp.gscale = ly.g1.acc_scale;
+            lp.rscale = ly.g2.acc_scale;
+            lp.dilation = ly.dilation;
+            lp.pad_ = 0;
+        }
+        w->layer_tab.alloc(tab.size() * sizeof(LayerParams));
+        B200_CUDA(cudaMemcpy(w->layer_tab.p, tab.data(), tab.size() * sizeof(LayerParams), cudaMemcpyHostToDevice));
+        const int n_row_tiles = B * ((T + 2 * kTileM - 1) / (2 * kTileM));
+        w->layer_flags.alloc(static_cast<size_t>(cfg.residual_layers) * n_row_tiles * sizeof(int));
     }
     auto& ref = *w;
     ws[key] = std::move(w);
@@ -427,38 +447,31 @@ ConvGemmArgs DiffusionPlan::resskip_args(Workspace& w, int l, const float* lut_t
     return a;
 }
 
-// one whole ResidualBlock: gate GEMM of both channel halves + residual GEMM per 256-row tile (diffnet_layer.cuh)
-LayerArgs DiffusionPlan::fused_args(Workspace& w, int l, const float* lut_t) {
+// ResidualBlocks [l0, l0 + n) in one launch of the fused layer kernel (diffnet_layer.cuh): per 256-row tile the gate GEMM of both
+// channel halves + the residual GEMM; n > 1: row-tile dataflow across the layers (zero w.layer_flags before the launch)
+LayerArgs DiffusionPlan::fused_args(Workspace& w, int l0, int n, const float* lut_t) {
     const int C = cfg.residual_channels, L = cfg.residual_layers;
-    Layer& ly = layers[l];
     LayerArgs a{};
-    a.xa16 = (l & 1) ? w.m_xa16_b : w.m_xa[0];
-    a.xa8 = (l & 1) ? w.m_xa8_b : w.m_xa8;
+    a.xa16[0] = w.m_xa[0]; a.xa16[1] = w.m_xa16_b;
+    a.xa8[0] = w.m_xa8; a.xa8[1] = w.m_xa8_b;
+    a.xe[0] = w.m_xe[0]; a.xe[1] = w.m_xe[1];
     a.z = w.m_z[0];
-    CUtensorMap unused;
-    const int wbox = fused_mc ? 64 : 128;   // weight rows one CTA loads per tile (multicast: half of its 128)
-    ly.g1.maps(wbox, a.wg16, unused);
-    a.wg8 = ly.g1.map8(wbox);
-    ly.g2.maps(wbox, a.wr[0], a.wr[1]);
-    a.cp = w.m_cp[l];
-    a.xe = w.m_xe[l & 1];
+    a.tab = w.layer_tab.as<LayerParams>();
+    a.layer0 = l0;
+    a.n_layers = n;
+    a.total_layers = L;
     a.B = w.B;
     a.T = w.T;
     a.tiles_per_batch = (w.T + 2 * kTileM - 1) / (2 * kTileM);
     a.n_row_tiles = a.B * a.tiles_per_batch;
-    a.dilation = ly.dilation;
     a.a_rows = kXaBoxRows;
-    a.z_col0 = l * C;
     a.z_pitch = L * C;
     a.z_out = w.z_hi.as<__half>();
-    a.xa16_out = (l + 1 < L) ? ((l & 1) ? w.xa_hi.as<__half>() : w.xa16_b.as<__half>()) : nullptr;
-    a.xa8_out = (l + 1 < L) ? ((l & 1) ? w.xa8.as<uint8_t>() : w.xa8_b.as<uint8_t>()) : nullptr;
-    a.bias_r = ly.g2_bias.as<float>();
-    a.dvec = (l + 1 < L) ? lut_t + static_cast<size_t>(l + 1) * C : nullptr;
-    a.dcur = lut_t + static_cast<size_t>(l) * C;
-    a.gscale = ly.g1.acc_scale;
-    a.rscale = ly.g2.acc_scale;
-    if (const char* ab = std::getenv("BSG_ABLATE")) a.flags = std::atoi(ab);   // timing experiments only (wrong results)
+    a.xa16_out[0] = w.xa_hi.as<__half>(); a.xa16_out[1] = w.xa16_b.as<__half>();
+    a.xa8_out[0] = w.xa8.as<uint8_t>(); a.xa8_out[1] = w.xa8_b.as<uint8_t>();
+    a.lut_t = lut_t;
+    a.flags = n > 1 ? w.layer_flags.as<int>() : nullptr;
+    if (const char* ab = std::getenv("BSG_ABLATE")) a.flags_ablate = std::atoi(ab);   // timing experiments only (wrong results)
     return a;
 }
 
@@ -496,7 +509,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
     auto run = [&](int n) {
         for (int i = 0; i < n; ++i) {
             const int l = i % L;
-            if (which == 3) launch_diffnet_layer(fused_args(w, l, lut.as<float>()), st, fused_mc);
+            if (which == 3) launch_diffnet_layer(fused_args(w, l, 1, lut.as<float>()), st, fused_mc);
             else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
             else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
             else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
@@ -521,7 +534,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
         ConvGemmArgs a = which == 0 ? gate_args(w, 1) : (which == 1 ? resskip_args(w, 1, lut.as<float>()) : skipsum_args(w));
         a.trace = tb.as<unsigned long long>();
         if (which == 3) {
-            LayerArgs la = fused_args(w, 1, lut.as<float>());
+            LayerArgs la = fused_args(w, 1, 1, lut.as<float>());
             la.trace = tb.as<unsigned long long>();
             launch_diffnet_layer(la, st, fused_mc);
         } else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, a, st, gate_mode);
@@ -576,17 +589,23 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         launch_conv_gemm(256, terms_side, EPI_INPROJ, a, st);
         ++launches, ++g_launch_count;
     }
-    static const int fuse_layers = [] { const char* e = std::getenv("BSG_FUSE_LAYERS"); return e ? std::atoi(e) : 1 << 30; }();   // debugging: even count
-    for (int l = 0; l < L; ++l) {
-        if (use_fused && l < fuse_layers) {
-            launch_diffnet_layer(fused_args(w, l, lut_t), st, fused_mc);
+    if (use_fused && fused_stack) {
+        // all ResidualBlocks in ONE launch: row tiles flow from layer to layer as soon as their three input tiles are done
+        B200_CUDA(cudaMemsetAsync(w.layer_flags.p, 0, w.layer_flags.bytes, st));
+        launch_diffnet_layer(fused_args(w, 0, L, lut_t), st, fused_mc);
+        ++launches, ++g_launch_count;
+    } else {
+        for (int l = 0; l < L; ++l) {
+            if (use_fused) {
+                launch_diffnet_layer(fused_args(w, l, 1, lut_t), st, fused_mc);
+                ++launches, ++g_launch_count;
+                continue;
+            }
+            launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
             ++launches, ++g_launch_count;
-            continue;
+            launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut_t), st);
+            ++launches, ++g_launch_count;
         }
-        launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
-        ++launches, ++g_launch_count;
-        launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut_t), st);
-        ++launches, ++g_launch_count;
     }
     {   // skip sum: sum_l (W_skip,l z_l + b_skip,l) / sqrt(L)  (net.py:77-78,126) as one K = L*C GEMM over the step's z matrix
         launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);

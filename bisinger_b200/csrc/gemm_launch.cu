@@ -147,6 +147,7 @@ static void launch_layer_inst(const LayerArgs& args, cudaStream_t stream) {
         }
     }
     if (args.n_row_tiles <= 0) return;
+    B200_CHECK(args.n_layers == 1 || args.flags != nullptr, "a multi-layer launch needs the row-tile completion counters");
     B200_CHECK(args.a_rows >= kTileM && args.a_rows * 128 <= LayerSmem::kASlotBytes && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
     const int units = MC ? (args.n_row_tiles + 1) / 2 : args.n_row_tiles;
     cudaLaunchConfig_t cfg{};

@@ -31,6 +31,7 @@ public:
     bool use_pair = true;    // 2-CTA (cta_group::2) tiles for the tensor-bound GEMMs (gate GEMM, skip-sum GEMM)
     bool use_fused = false;  // one fused kernel per ResidualBlock (fp16x2 mode)
     bool fused_mc = false;   // ... on 4-CTA clusters with multicast weight tiles
+    bool fused_stack = false;   // ... all layers of a step in one launch (row-tile dataflow between the layers)
     int gate_mode = 1, skip_mode = 1;   // launch_conv_gemm cluster mode of those two GEMMs: 0 single CTA, 1 pair, 2 two pairs + multicast weights
     unsigned long long launches = 0;
 
@@ -49,7 +50,7 @@ private:
     ConvGemmArgs gate_args(Workspace& w, int l);
     ConvGemmArgs resskip_args(Workspace& w, int l, const float* lut_t);
     ConvGemmArgs skipsum_args(Workspace& w);
-    struct LayerArgs fused_args(Workspace& w, int l, const float* lut_t);
+    struct LayerArgs fused_args(Workspace& w, int l0, int n, const float* lut_t);
     void enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail, cudaStream_t st);
 
     std::vector<Layer> layers;
