@@ -242,10 +242,14 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
     // local row tile n of this pair is global row tile kPairs * (cluster_id + n * n_clusters) + pidx; with MC the odd one of the
     // last unit may not exist: its loads are zero-filled by the TMA unit (batch index out of range) and nothing is stored
     const int n_units = (args.n_row_tiles + kPairs - 1) / kPairs;
-    const int cnt = (n_units - cluster_id + n_clusters - 1) / n_clusters;
-    const int n_ops = 3 * cnt;
-    const int worker = kPairs * cluster_id + pidx;   // first row tile of this pair
     const int n_workers = kPairs * n_clusters;       // row-tile stride
+    // The units are dealt round-robin to the clusters, so n_units % n_clusters of them own one unit more than the rest (256 row
+    // tiles over 74 pairs: 34 pairs with 4, 40 with 3).  In a multi-layer launch the deal rotates from layer to layer, so that
+    // over the layers every cluster gets the same share instead of the same clusters finishing last in every layer.
+    const int rot = args.n_layers > 1 ? n_units % n_clusters : 0;
+    auto layer_cluster = [&](int l) { return (cluster_id + (l - args.layer0) * rot) % n_clusters; };
+    auto layer_cnt = [&](int l) { return (n_units - layer_cluster(l) + n_clusters - 1) / n_clusters; };       // row tiles of this pair in layer l
+    auto layer_worker = [&](int l) { return kPairs * layer_cluster(l) + pidx; };                              // ... the first of them
 
     if (threadIdx.x == 32) {
         for (int s = 0; s < S::kAStages; ++s) { mbar_init(&afull_bar[s], 1); mbar_init(&aempty_bar[s], 1); }
@@ -317,9 +321,11 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
         const uint32_t halo_bytes = static_cast<uint32_t>(args.a_rows) * 128;
         long long w_dep = 0;
         int ng0 = 0;   // local row tiles finished in earlier layers (z barrier parity runs on across layers)
-        for (int l = args.layer0; l < layer_end; ++l, ng0 += cnt) {
+        for (int l = args.layer0, cnt = 0; l < layer_end; ++l, ng0 += cnt) {
             const LayerParams& lp = args.tab[l];
             const int dil = lp.dilation;
+            cnt = layer_cnt(l);
+            const int worker = layer_worker(l), n_ops = 3 * cnt;
             for (int j = 0; j < n_ops; ++j) {
                 const LayerOp op = layer_op(j, cnt);
                 const int m = worker + op.n * n_workers;
@@ -388,8 +394,11 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             if (++as == S::kAStages) { as = 0; aph ^= 1; }
         };
         int jg = 0;   // ops issued so far: accumulator buffer = jg & 1, across layers
+        int cnt_total = 0;
         for (int l = args.layer0; l < layer_end; ++l) {
             const uint32_t tap_stride = static_cast<uint32_t>(args.tab[l].dilation) * 128;   // taps = rows 0, d, 2d of the halo tile
+            const int cnt = layer_cnt(l), n_ops = 3 * cnt;
+            cnt_total += cnt;
             for (int j = 0; j < n_ops; ++j, ++jg) {
                 const int kind = layer_op(j, cnt).kind;
                 const int acc = jg & 1;
@@ -421,7 +430,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
         }
         if (tr_on) {
             unsigned long long* t = args.trace + blockIdx.x * 16;
-            t[0] = clock64() - t_begin; t[1] = w_t; t[2] = w_a; t[3] = w_b; t[10] = cnt;
+            t[0] = clock64() - t_begin; t[1] = w_t; t[2] = w_a; t[3] = w_b; t[10] = cnt_total;
         }
     } else if (warp == 10 && lane == 0) {
         // ================= epilogue-operand producer: cp boxes (gate ops) / conv-input boxes (residual ops) =================
@@ -431,6 +440,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
         int q = 0;
         for (int l = args.layer0; l < layer_end; ++l) {
             const LayerParams& lp = args.tab[l];
+            const int cnt = layer_cnt(l), worker = layer_worker(l), n_ops = 3 * cnt;
             for (int j = 0; j < n_ops; ++j) {
                 const LayerOp op = layer_op(j, cnt);
                 const int m = worker + op.n * n_workers;
@@ -476,8 +486,10 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             z_pending = false;
         };
         int jg = 0, ng0 = 0;      // ops / local row tiles of earlier layers (accumulator and z-barrier parities run on across layers)
-        for (int l = args.layer0; l < layer_end; ++l, ng0 += cnt) {
+        for (int l = args.layer0, cnt = 0; l < layer_end; ++l, ng0 += cnt) {
           const LayerParams& lpar = args.tab[l];
+          cnt = layer_cnt(l);
+          const int worker = layer_worker(l), n_ops = 3 * cnt;
           const float gscale = lpar.gscale, rscale = lpar.rscale;
           const bool has_next = l + 1 < args.total_layers;
           __half* const xa16_out = args.xa16_out[(l + 1) & 1];

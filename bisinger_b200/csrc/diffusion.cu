@@ -497,8 +497,8 @@ ConvGemmArgs DiffusionPlan::skipsum_args(Workspace& w) {
 // the layers (so weights change from launch to launch as in a real step).  which: 0 = gate GEMM, 1 = residual GEMM,
 // 2 = skip-sum GEMM.
 float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t st) {
-    B200_CHECK(which >= 0 && which <= 3, "unknown kernel id");
-    B200_CHECK(which != 3 || use_fused, "the fused layer kernel is not enabled in this plan");
+    B200_CHECK(which >= 0 && which <= 4, "unknown kernel id");   // 3 = one fused layer, 4 = all layers in one launch (time per layer)
+    B200_CHECK(which < 3 || use_fused, "the fused layer kernel is not enabled in this plan");
     B200_CHECK(reps > 0, "reps must be positive");
     B200_CUDA(cudaSetDevice(device));
     Workspace& w = workspace(B, T);
@@ -509,7 +509,11 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
     auto run = [&](int n) {
         for (int i = 0; i < n; ++i) {
             const int l = i % L;
-            if (which == 3) launch_diffnet_layer(fused_args(w, l, 1, lut.as<float>()), st, fused_mc);
+            if (which == 4) {
+                if (l != 0) continue;
+                B200_CUDA(cudaMemsetAsync(w.layer_flags.p, 0, w.layer_flags.bytes, st));
+                launch_diffnet_layer(fused_args(w, 0, L, lut.as<float>()), st, fused_mc);
+            } else if (which == 3) launch_diffnet_layer(fused_args(w, l, 1, lut.as<float>()), st, fused_mc);
             else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
             else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
             else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
@@ -533,8 +537,9 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
         B200_CUDA(cudaMemsetAsync(tb.p, 0, static_cast<size_t>(grid) * 16 * 8, st));
         ConvGemmArgs a = which == 0 ? gate_args(w, 1) : (which == 1 ? resskip_args(w, 1, lut.as<float>()) : skipsum_args(w));
         a.trace = tb.as<unsigned long long>();
-        if (which == 3) {
-            LayerArgs la = fused_args(w, 1, 1, lut.as<float>());
+        if (which >= 3) {
+            if (which == 4) B200_CUDA(cudaMemsetAsync(w.layer_flags.p, 0, w.layer_flags.bytes, st));
+            LayerArgs la = which == 4 ? fused_args(w, 0, L, lut.as<float>()) : fused_args(w, 1, 1, lut.as<float>());
             la.trace = tb.as<unsigned long long>();
             launch_diffnet_layer(la, st, fused_mc);
         } else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, a, st, gate_mode);
@@ -557,9 +562,9 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
                          "wait a-empty %.0f b-empty %.0f | epilogue warp total %.0f wait t-full %.0f\n",
                          which, s[0] / n_mma, s[10] / n_mma, s[1] / n_mma, s[2] / n_mma, s[3] / n_mma, s[4] / n_cta, s[5] / n_cta, s[6] / n_cta,
                          s[7] / n_cta, s[8] / n_cta);
-        if (which == 3 && n_cta)
-            std::fprintf(stderr, "TRACE fused layer: producer waits for z %.0f clk | epilogue warp busy in gate ops %.0f, in residual ops %.0f, of which waiting for cp/x boxes %.0f | box producer waits for consumers %.0f (row tiles %.2f)\n",
-                         s[9] / n_cta, s[11] / n_cta, s[12] / n_cta, s[14] / n_cta, s[13] / n_cta, n_mma ? s[10] / n_mma : 0.0);
+        if (which >= 3 && n_cta)
+            std::fprintf(stderr, "TRACE fused layer (waits for other tiles' rows: %.0f clk): producer waits for z %.0f clk | epilogue warp busy in gate ops %.0f, in residual ops %.0f, of which waiting for cp/x boxes %.0f | box producer waits for consumers %.0f (row tiles %.2f)\n",
+                         s[15] / n_cta, s[9] / n_cta, s[11] / n_cta, s[12] / n_cta, s[14] / n_cta, s[13] / n_cta, n_mma ? s[10] / n_mma : 0.0);
     }
     return ms / static_cast<float>(reps);
 }

@@ -31,7 +31,7 @@ public:
     bool use_pair = true;    // 2-CTA (cta_group::2) tiles for the tensor-bound GEMMs (gate GEMM, skip-sum GEMM)
     bool use_fused = false;  // one fused kernel per ResidualBlock (fp16x2 mode)
     bool fused_mc = false;   // ... on 4-CTA clusters with multicast weight tiles
-    bool fused_stack = false;   // ... all layers of a step in one launch (row-tile dataflow between the layers)
+    bool fused_stack = true;    // ... all layers of a step in one launch (row-tile dataflow between the layers); BSG_LAYER_STACK=0: one launch per layer
     int gate_mode = 1, skip_mode = 1;   // launch_conv_gemm cluster mode of those two GEMMs: 0 single CTA, 1 pair, 2 two pairs + multicast weights
     unsigned long long launches = 0;
 

@@ -206,7 +206,7 @@ def stage_proftarget():
     import torch
     sd, sched, plan, inp, O, synth = _diff_setup(1, 8, 100, os.environ.get("BSG_PREC", "fp16x2"))
     which = int(os.environ.get("BSG_WHICH", "1"))
-    print("kernel", which, "ms", plan.time_kernel(which, 32, 1875, 4))
+    print("kernel", which, "ms", plan.time_kernel(which, 32, 1875, int(os.environ.get("BSG_REPS", "4"))))
 
 
 def stage_mctest():
