@@ -47,7 +47,7 @@ class HifiganConfig(C.Structure):
 # every symbol include/bisinger_b200.h declares (tests check that the library exports all of them)
 EXPORTS = (
     "bsg_abi_version", "bsg_last_error", "bsg_kernel_launch_count",
-    "bsg_diffusion_plan_create", "bsg_diffusion_plan_destroy", "bsg_diffusion_sample", "bsg_diffnet_forward",
+    "bsg_diffusion_plan_create", "bsg_diffusion_plan_destroy", "bsg_diffusion_sample", "bsg_diffusion_sample_plms", "bsg_diffnet_forward",
     "bsg_diffusion_time_kernel",
     "bsg_hifigan_plan_create", "bsg_hifigan_plan_destroy", "bsg_hifigan_forward", "bsg_hifigan_source",
     "bsg_selftest_conv",
@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
     L.bsg_diffusion_plan_destroy.argtypes = [vp]
     L.bsg_diffusion_plan_destroy.restype = None
     L.bsg_diffusion_sample.argtypes = [vp, fp, fp, fp, fp, C.c_ulonglong, fp, ip, ip, fp, fp, vp]
+    L.bsg_diffusion_sample_plms.argtypes = [vp, fp, fp, fp, C.c_ulonglong, fp, C.POINTER(C.c_float), ip, ip, ip, fp, fp, vp]
     L.bsg_diffnet_forward.argtypes = [vp, fp, ip, fp, ip, ip, fp, vp]
     L.bsg_diffusion_time_kernel.argtypes = [vp, ip, ip, ip, ip, C.POINTER(C.c_float), vp]
     L.bsg_hifigan_plan_create.argtypes = [C.POINTER(HifiganConfig), C.POINTER(C.c_float), C.c_size_t, C.c_int, C.POINTER(vp)]

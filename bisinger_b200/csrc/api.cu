@@ -58,6 +58,16 @@ int bsg_diffusion_sample(bsg_diffusion_plan* plan, const float* cond, const floa
     });
 }
 
+int bsg_diffusion_sample_plms(bsg_diffusion_plan* plan, const float* cond, const float* fs2_mel, const float* start_noise,
+                              unsigned long long seed, const int64_t* mel2ph, const float* alphas_cumprod_host, int interval, int B,
+                              int T, float* mel_out, float* x_final, void* stream) {
+    return guarded([&] {
+        B200_CHECK(plan, "null plan");
+        plan->impl.sample_plms(cond, fs2_mel, start_noise, seed, mel2ph, alphas_cumprod_host, interval, B, T, mel_out, x_final,
+                               static_cast<cudaStream_t>(stream));
+    });
+}
+
 int bsg_diffnet_forward(bsg_diffusion_plan* plan, const float* spec, int t, const float* cond, int B, int T, float* eps_out,
                         void* stream) {
     return guarded([&] {

@@ -127,6 +127,40 @@ __global__ void init_x_kernel(int mode, const float* __restrict__ fs2_mel, const
     }
 }
 
+// One PLMS update (usr/diff/shallow_diffusion_tts.py:168-201).  prime = combination of the current and earlier noise predictions
+// (mode 0: e0; 1: (e0 + e1)/2 -- first iteration, e1 = prediction at the predictor point; 2: (3 e0 - e1)/2; 3: (23 e0 - 16 e1 + 5 e2)/12;
+// 4: (55 e0 - 59 e1 + 37 e2 - 9 e3)/24), x' = x + da * (cx * x - ce * prime)   (get_x_pred, :174-183; da, cx, ce from alphas_cumprod
+// in fp32 on the host, same operation order).  write_x = 0: predictor of the first iteration -- only the operand copy for the next
+// denoiser evaluation is written, x itself stays.  mel_out != null (last iteration): denorm_spec(x') * (mel2ph > 0) (:268-272).
+// One thread per (b, t); x, e* are [B][M][T].
+__global__ void plms_update_kernel(int mode, int write_x, float da, float cx, float ce, float* __restrict__ x, const float* __restrict__ e0,
+                                   const float* __restrict__ e1, const float* __restrict__ e2, const float* __restrict__ e3, int B, int T, int M,
+                                   __nv_bfloat16* __restrict__ xin_hi, __nv_bfloat16* __restrict__ xin_lo, float* __restrict__ mel_out,
+                                   const float* __restrict__ smin, const float* __restrict__ smax, const int64_t* __restrict__ mel2ph) {
+    const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= static_cast<long long>(B) * T) return;
+    const int b = static_cast<int>(r / T), t = static_cast<int>(r % T);
+    const float mask = (mel_out != nullptr && mel2ph != nullptr && !(mel2ph[r] > 0)) ? 0.0f : 1.0f;
+    for (int c = 0; c < M; ++c) {
+        const long long i = (static_cast<long long>(b) * M + c) * T + t;
+        const float a = e0[i];
+        float prime;
+        if (mode == 0) prime = a;
+        else if (mode == 1) prime = (a + e1[i]) / 2.0f;
+        else if (mode == 2) prime = (3.0f * a - e1[i]) / 2.0f;
+        else if (mode == 3) prime = (23.0f * a - 16.0f * e1[i] + 5.0f * e2[i]) / 12.0f;
+        else prime = (55.0f * a - 59.0f * e1[i] + 37.0f * e2[i] - 9.0f * e3[i]) / 24.0f;
+        const float xv = x[i];
+        const float xn = xv + da * (cx * xv - ce * prime);
+        if (write_x) x[i] = xn;
+        float hf; __nv_bfloat16 h, l;
+        split_bf16(xn, hf, h, l);
+        xin_hi[r * M + c] = h;
+        if (xin_lo) xin_lo[r * M + c] = l;
+        if (mel_out != nullptr) mel_out[r * M + c] = ((xn + 1.0f) / 2.0f * (smax[c] - smin[c]) + smin[c]) * mask;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
@@ -144,6 +178,7 @@ struct DiffusionPlan::Workspace {
     CUtensorMap m_xa16_b, m_xa8_b;
     CUtensorMap m_xin[2], m_cond[2], m_xa[2], m_z[2], m_s[2], m_h[2];
     CUtensorMap m_xa8, m_xe[2];      // fused layer kernel: 8-bit conv input; the fp16 conv input buffers as the epilogue reads them
+    DevBuf plms_eps[4];              // PLMS: the last four noise predictions [B][M][T]
     DevBuf layer_tab;                // fused layer kernel: LayerParams[L] (weight / conditioner-projection tensor maps, scales) in device memory
     DevBuf layer_flags;              // ... and the row-tile completion counters of a multi-layer launch [L][row tiles]
     cudaGraphExec_t graph = nullptr;
@@ -572,7 +607,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
 // One DiffNet evaluation at diffusion step t (net.py:107-130) followed by `tail`:
 //   tail == 0: posterior update of xt (p_sample), tail == 1: write eps to ws.eps
 void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, float* eps_out) {
     const int M = cfg.in_dims, H = cfg.hidden_size, C = cfg.residual_channels, L = cfg.residual_layers;
     const int B = w.B, T = w.T;
     const float* lut_t = lut.as<float>() + static_cast<size_t>(t) * L * C;
@@ -637,7 +672,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         set_taps(a, 0, 0, C / kBlockK, kOneTap, 1, 0);
         a.epi.bias = outproj_bias.as<float>();
         if (tail == 1) {
-            a.epi.f32_a = w.eps.as<float>();
+            a.epi.f32_a = eps_out ? eps_out : w.eps.as<float>();
             a.epi.flags = 1;
         } else {
             const StepCoef& sc = sched[t];
@@ -723,6 +758,79 @@ void DiffusionPlan::sample(const float* cond, const float* fs2_mel, const float*
         for (int k = 0; k < K; ++k)
             enqueue_step(w, K - 1 - k, k, step_noise ? step_noise + static_cast<size_t>(k) * per_step : nullptr, k == K - 1, use_mask, 0,
                          st);
+    }
+    B200_CUDA(cudaMemcpyAsync(mel_out, w.mel.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
+    if (x_final) B200_CUDA(cudaMemcpyAsync(x_final, w.xt.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
+}
+
+// PLMS / PNDM sampler: the infer branch with hparams['pndm_speedup'] = interval (shallow_diffusion_tts.py:168-201,258-264).
+// Deterministic after the start; K/interval iterations, one denoiser evaluation each plus one more in the first.
+void DiffusionPlan::sample_plms(const float* cond, const float* fs2_mel, const float* start_noise, unsigned long long seed,
+                                const int64_t* mel2ph, const float* alphas_cumprod, int interval, int B, int T, float* mel_out,
+                                float* x_final, cudaStream_t st) {
+    B200_CHECK(B > 0 && T > 0, "empty batch");
+    B200_CHECK(cond != nullptr && mel_out != nullptr && alphas_cumprod != nullptr, "cond, mel_out and alphas_cumprod are required");
+    B200_CHECK(interval >= 1 && interval <= cfg.k_step, "bad pndm_speedup interval");
+    B200_CUDA(cudaSetDevice(device));
+    Workspace& w = workspace(B, T);
+    const int M = cfg.in_dims, H = cfg.hidden_size, K = cfg.k_step;
+    const size_t rows = static_cast<size_t>(B) * T;
+    const bool lo = terms_side == 3;
+    if (w.plms_eps[0].p == nullptr)
+        for (auto& e : w.plms_eps) e.alloc(rows * M * 4);
+    B200_CUDA(cudaMemcpyAsync(d_seed.p, &seed, sizeof(seed), cudaMemcpyHostToDevice, st));
+    {
+        const size_t n = rows * H;
+        split_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256 + 1), 256, 0, st>>>(cond, w.cond_hi.as<__nv_bfloat16>(),
+                                                                                    lo ? w.cond_lo.as<__nv_bfloat16>() : nullptr, n);
+        ++launches, ++g_launch_count;
+        precompute_cond(w, st);
+        init_x_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(
+            fs2_mel ? 0 : 1, fs2_mel, start_noise, d_spec_min.as<float>(), d_spec_max.as<float>(), sched[K - 1].sqrt_ac, sched[K - 1].sqrt_1mac,
+            d_seed.as<unsigned long long>(), B, T, M, w.xt.as<float>(), w.xin_hi.as<__nv_bfloat16>(),
+            lo ? w.xin_lo.as<__nv_bfloat16>() : nullptr);
+        ++launches, ++g_launch_count;
+        B200_CUDA(cudaGetLastError());
+    }
+    if (mel2ph) B200_CUDA(cudaMemcpyAsync(w.mel2ph.p, mel2ph, rows * 8, cudaMemcpyDeviceToDevice, st));
+    // get_x_pred coefficients in fp32, same operation order as the reference (:175-180)
+    auto coef = [&](int t, float& da, float& cx, float& ce) {
+        const float a_t = alphas_cumprod[t], a_prev = alphas_cumprod[t - interval > 0 ? t - interval : 0];
+        const float a_t_sq = std::sqrt(a_t), a_prev_sq = std::sqrt(a_prev);
+        da = a_prev - a_t;
+        cx = 1.0f / (a_t_sq * (a_t_sq + a_prev_sq));
+        ce = 1.0f / (a_t_sq * (std::sqrt((1.0f - a_prev) * a_t) + std::sqrt((1.0f - a_t) * a_prev)));
+    };
+    auto update = [&](int mode, int write_x, int t, const float* e0, const float* e1, const float* e2, const float* e3, bool last) {
+        float da, cx, ce;
+        coef(t, da, cx, ce);
+        plms_update_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(
+            mode, write_x, da, cx, ce, w.xt.as<float>(), e0, e1, e2, e3, B, T, M, w.xin_hi.as<__nv_bfloat16>(),
+            lo ? w.xin_lo.as<__nv_bfloat16>() : nullptr, last ? w.mel.as<float>() : nullptr, d_spec_min.as<float>(), d_spec_max.as<float>(),
+            mel2ph ? w.mel2ph.as<int64_t>() : nullptr);
+        ++launches, ++g_launch_count;
+        B200_CUDA(cudaGetLastError());
+    };
+    int n_hist = 0, head = 0;   // ring of the last noise predictions: plms_eps[(head - j) & 3] = j-th most recent
+    const int t_first = ((K - 1) / interval) * interval;
+    for (int t = t_first, it = 0; t >= 0; t -= interval, ++it) {
+        head = (head + 1) & 3;
+        float* e0 = w.plms_eps[head].as<float>();
+        enqueue_step(w, t, it, nullptr, false, false, 1, st, e0);
+        const bool last = t - interval < 0;
+        const float* e1 = w.plms_eps[(head + 3) & 3].as<float>();
+        const float* e2 = w.plms_eps[(head + 2) & 3].as<float>();
+        const float* e3 = w.plms_eps[(head + 1) & 3].as<float>();
+        if (n_hist == 0) {
+            // first iteration (:188-191): predictor step, a second evaluation at max(t - interval, 0), average
+            update(0, 0, t, e0, nullptr, nullptr, nullptr, false);
+            float* ep = w.eps.as<float>();
+            enqueue_step(w, t - interval > 0 ? t - interval : 0, it, nullptr, false, false, 1, st, ep);
+            update(1, 1, t, e0, ep, nullptr, nullptr, last);
+        } else {
+            update(n_hist + 1 > 4 ? 4 : n_hist + 1, 1, t, e0, e1, e2, e3, last);
+        }
+        if (n_hist < 3) ++n_hist;
     }
     B200_CUDA(cudaMemcpyAsync(mel_out, w.mel.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
     if (x_final) B200_CUDA(cudaMemcpyAsync(x_final, w.xt.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));

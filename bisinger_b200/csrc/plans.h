@@ -20,6 +20,8 @@ public:
 
     void sample(const float* cond, const float* fs2_mel, const float* start_noise, const float* step_noise,
                 unsigned long long seed, const int64_t* mel2ph, int B, int T, float* mel_out, float* x_final, cudaStream_t st);
+    void sample_plms(const float* cond, const float* fs2_mel, const float* start_noise, unsigned long long seed, const int64_t* mel2ph,
+                     const float* alphas_cumprod, int interval, int B, int T, float* mel_out, float* x_final, cudaStream_t st);
     void denoise(const float* spec, int t, const float* cond, int B, int T, float* eps_out, cudaStream_t st);
     float time_kernel(int which, int B, int T, int reps, cudaStream_t st);
 
@@ -51,7 +53,8 @@ private:
     ConvGemmArgs resskip_args(Workspace& w, int l, const float* lut_t);
     ConvGemmArgs skipsum_args(Workspace& w);
     struct LayerArgs fused_args(Workspace& w, int l0, int n, const float* lut_t);
-    void enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail, cudaStream_t st);
+    void enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail, cudaStream_t st,
+                      float* eps_out = nullptr);
 
     std::vector<Layer> layers;
     PackedW inproj, skipproj, outproj, skipall;   // skipall: skip halves of all output projections, [C][L*C]

@@ -130,6 +130,8 @@ class DiffusionPlan:
                                  denoise_fn.dilation_cycle_length, self.timesteps, self.K_step, _lib.PRECISIONS[precision])
         w = denoise_fn.flat_weights()
         keep = [sched[f[0]].detach().to("cpu", torch.float32).contiguous() for f in _lib.Schedule._fields_]
+        ac = sched.get("alphas_cumprod") if isinstance(sched, dict) else None   # PLMS only (shallow_diffusion_tts.py:104,175-176)
+        self._alphas_cumprod = None if ac is None else ac.detach().to("cpu", torch.float32).contiguous()
         s = _lib.Schedule(*[_lib.fptr(t) for t in keep])
         smin = torch.zeros(M) if spec_min is None else torch.as_tensor(spec_min, dtype=torch.float32).reshape(-1).cpu().contiguous()
         smax = torch.ones(M) if spec_max is None else torch.as_tensor(spec_max, dtype=torch.float32).reshape(-1).cpu().contiguous()
@@ -186,6 +188,30 @@ class DiffusionPlan:
         _lib.check(_lib.lib().bsg_diffusion_sample(
             self._h, _lib.dev_ptr(cond), _lib.dev_ptr(fs2_mel), _lib.dev_ptr(start_noise), _lib.dev_ptr(step_noise),
             C.c_ulonglong(seed & (2 ** 64 - 1)), _lib.dev_ptr(mel2ph), B, T, _lib.dev_ptr(mel), _lib.dev_ptr(xf),
+            _lib.current_stream_ptr(dev)))
+        return (mel, xf) if return_x else mel
+
+
+    def sample_plms(self, cond_btH, fs2_mel=None, start_noise=None, interval: int = 5, seed: int = 0, mel2ph=None,
+                    return_x: bool = False):
+        """The PLMS / PNDM sampler (hparams['pndm_speedup'] = interval; shallow_diffusion_tts.py:168-201,258-264): K_step / interval
+        iterations, deterministic after the start.  Arguments as ``sample``; returns mel_out [B,T,M] (and x_0 [B,1,M,T])."""
+        if self._alphas_cumprod is None:
+            raise RuntimeError("sample_plms needs the 'alphas_cumprod' schedule buffer (pass it in sched=)")
+        dev = self.device
+        f32 = lambda t: None if t is None else t.to(dev, torch.float32).contiguous()
+        cond = f32(cond_btH)
+        B, T, H = cond.shape
+        if H != self.H:
+            raise RuntimeError(f"cond has {H} channels, plan expects {self.H}")
+        fs2_mel, start_noise = f32(fs2_mel), f32(start_noise)
+        if mel2ph is not None:
+            mel2ph = mel2ph.to(dev, torch.int64).contiguous()
+        mel = torch.empty((B, T, self.M), device=dev, dtype=torch.float32)
+        xf = torch.empty((B, 1, self.M, T), device=dev, dtype=torch.float32) if return_x else None
+        _lib.check(_lib.lib().bsg_diffusion_sample_plms(
+            self._h, _lib.dev_ptr(cond), _lib.dev_ptr(fs2_mel), _lib.dev_ptr(start_noise), C.c_ulonglong(seed & (2 ** 64 - 1)),
+            _lib.dev_ptr(mel2ph), _lib.fptr(self._alphas_cumprod), int(interval), B, T, _lib.dev_ptr(mel), _lib.dev_ptr(xf),
             _lib.current_stream_ptr(dev)))
         return (mel, xf) if return_x else mel
 
@@ -262,6 +288,7 @@ class B200GaussianDiffusion(nn.Module):
         """(Re)build the device plan from the *current* parameters and schedule buffers (call again after loading a
         checkpoint)."""
         sched = {f[0]: getattr(self, f[0]) for f in _lib.Schedule._fields_}
+        sched["alphas_cumprod"] = self.alphas_cumprod      # the PLMS sampler's get_x_pred (shallow_diffusion_tts.py:175-176)
         self._plan = DiffusionPlan(self.denoise_fn, sched, self.num_timesteps, self.K_step, self.spec_min.reshape(-1),
                                    self.spec_max.reshape(-1), self.precision)
         return self._plan
@@ -279,6 +306,9 @@ class B200GaussianDiffusion(nn.Module):
     @torch.no_grad()
     def sample(self, decoder_inp, fs2_mel, mel2ph=None, start_noise=None, step_noise=None, seed=0, return_x=False):
         gaussian = bool(self.hparams.get("gaussian_start"))
+        if self.hparams.get("pndm_speedup"):   # shallow_diffusion_tts.py:258-264
+            return self.plan.sample_plms(decoder_inp, None if gaussian else fs2_mel, start_noise, int(self.hparams["pndm_speedup"]), seed,
+                                         mel2ph, return_x)
         return self.plan.sample(decoder_inp, None if gaussian else fs2_mel, start_noise, step_noise, seed, mel2ph, return_x)
 
     def forward(self, txt_tokens, mel2ph=None, spk_embed=None, ref_mels=None, f0=None, uv=None, energy=None, infer=False,
@@ -286,8 +316,6 @@ class B200GaussianDiffusion(nn.Module):
         if not infer:
             raise NotImplementedError("B200GaussianDiffusion implements the inference branch only "
                                       "(training stays in the reference: shallow_diffusion_tts.py:237-242)")
-        if self.hparams.get("pndm_speedup"):
-            raise NotImplementedError("pndm_speedup (p_sample_plms) is not built yet; use the ancestral sampler")
         if self.fs2 is None:
             raise RuntimeError("no FastSpeech2 conditioner attached (pass fs2=...)")
         ret = self.fs2(txt_tokens, mel2ph, spk_embed, ref_mels, f0, uv, energy, skip_decoder=False, infer=True, **kwargs)

@@ -100,6 +100,15 @@ int bsg_diffusion_sample(bsg_diffusion_plan* plan, const float* cond, const floa
                          const float* step_noise, unsigned long long seed, const int64_t* mel2ph, int B, int T,
                          float* mel_out, float* x_final, void* stream);
 
+/* The same infer branch with hparams['pndm_speedup'] = interval: the PLMS / PNDM sampler (shallow_diffusion_tts.py:168-201
+ * p_sample_plms, :258-264 the loop over reversed(range(0, K_step, interval))).  Deterministic after the start: no per-step
+ * noise.  alphas_cumprod_host: host f32 [timesteps] = GaussianDiffusion.alphas_cumprod (:104).  The diffusion step is a scalar
+ * (the reference takes max() of a [B] tensor at :189 and therefore only runs for B = 1; any B is accepted here).
+ * Other arguments as bsg_diffusion_sample.                                                                        */
+int bsg_diffusion_sample_plms(bsg_diffusion_plan* plan, const float* cond, const float* fs2_mel, const float* start_noise,
+                              unsigned long long seed, const int64_t* mel2ph, const float* alphas_cumprod_host, int interval, int B,
+                              int T, float* mel_out, float* x_final, void* stream);
+
 /* One DiffNet evaluation eps = denoise_fn(x, t, cond) (usr/diff/net.py:107-130) -- the drop-in for
  * DiffNet.forward used by B200DiffNet and by the parity tests.
  *   spec device f32 [B][1][M][T], t = diffusion step (same for the whole batch, as at :267),

@@ -236,6 +236,56 @@ def diffusion_infer(p: Dict[str, Tensor], sched: Dict[str, Tensor], spec_min: Te
     return (out, x, trace) if return_trace else out
 
 
+def plms_x_pred(sched: Dict[str, Tensor], x: Tensor, noise_t: Tensor, t: int, interval: int) -> Tensor:
+    """get_x_pred of p_sample_plms, usr/diff/shallow_diffusion_tts.py:174-183 (fp32 buffers, fp32 arithmetic)."""
+    a_t = sched["alphas_cumprod"][t]
+    a_prev = sched["alphas_cumprod"][max(t - interval, 0)]
+    a_t_sq, a_prev_sq = a_t.sqrt(), a_prev.sqrt()
+    x_delta = (a_prev - a_t) * ((1 / (a_t_sq * (a_t_sq + a_prev_sq))) * x
+                                - 1 / (a_t_sq * (((1 - a_prev) * a_t).sqrt() + ((1 - a_t) * a_prev).sqrt())) * noise_t)
+    return x + x_delta
+
+
+def diffusion_infer_plms(p: Dict[str, Tensor], sched: Dict[str, Tensor], spec_min: Tensor, spec_max: Tensor,
+                         cond_btH: Tensor, K_step: int, interval: int, fs2_mel: Optional[Tensor] = None,
+                         start_noise: Optional[Tensor] = None, mel2ph: Optional[Tensor] = None,
+                         gaussian_start: bool = False, dilation_cycle: int = 4, operand: Optional[str] = None,
+                         return_x: bool = False):
+    """Infer branch of GaussianDiffusion.forward with hparams['pndm_speedup'] = interval: the PLMS / PNDM sampler,
+    usr/diff/shallow_diffusion_tts.py:168-201 (p_sample_plms) and :258-264 (the loop over reversed(range(0, K_step, interval))).
+    Deterministic after the start: no noise is drawn.  The reference evaluates max(t - interval, 0) on a [B] tensor, which only
+    works for B = 1; the step index is the same for all rows, so this restatement (and the CUDA path) take it
+    as a scalar and accept any B."""
+    cond = cond_btH.transpose(1, 2)
+    if gaussian_start:
+        x = start_noise
+    else:
+        xs = norm_spec(fs2_mel, spec_min, spec_max).transpose(1, 2)[:, None]
+        x = q_sample(sched, xs, K_step - 1, start_noise)
+    B = x.shape[0]
+    noise_list = []                                                      # deque(maxlen=4), :259
+    for t in reversed(range(0, K_step, interval)):
+        noise_pred = diffnet_forward(p, x, torch.full((B,), t, dtype=torch.long), cond, dilation_cycle, operand)
+        if len(noise_list) == 0:                                         # :188-191
+            x_pred = plms_x_pred(sched, x, noise_pred, t, interval)
+            noise_pred_prev = diffnet_forward(p, x_pred, torch.full((B,), max(t - interval, 0), dtype=torch.long), cond,
+                                              dilation_cycle, operand)
+            prime = (noise_pred + noise_pred_prev) / 2
+        elif len(noise_list) == 1:                                       # :192-193
+            prime = (3 * noise_pred - noise_list[-1]) / 2
+        elif len(noise_list) == 2:                                       # :194-195
+            prime = (23 * noise_pred - 16 * noise_list[-1] + 5 * noise_list[-2]) / 12
+        else:                                                            # :196-197
+            prime = (55 * noise_pred - 59 * noise_list[-1] + 37 * noise_list[-2] - 9 * noise_list[-3]) / 24
+        x = plms_x_pred(sched, x, prime, t, interval)                    # :199
+        noise_list.append(noise_pred)
+        noise_list = noise_list[-4:]
+    out = denorm_spec(x[:, 0].transpose(1, 2), spec_min, spec_max)
+    if mel2ph is not None:
+        out = out * (mel2ph > 0).float()[:, :, None]
+    return (out, x) if return_x else out
+
+
 # --------------------------------------------------------------------------------------
 # NSF harmonic source (modules/parallel_wavegan/models/source.py)
 # --------------------------------------------------------------------------------------

@@ -169,6 +169,29 @@ def test_layer_kernel_variants(dev, monkeypatch, env):
         assert torch.equal(var, base)
 
 
+@pytest.mark.parametrize("B,T,interval", [(1, 60, 5), (3, 300, 5), (2, 90, 10), (1, 40, 1)])
+def test_plms_sampler_vs_oracle(diff, dev, B, T, interval):
+    """PLMS / PNDM sampler (p_sample_plms, shallow_diffusion_tts.py:168-201): CUDA path vs the oracle (which is pinned to the executed
+    reference for B = 1); the first case is also a committed golden fixture of the reference itself."""
+    import os
+    sd, sched, plan = diff
+    seed = 61 if (B, T, interval) == (1, 60, 5) else 200 + T
+    inp = synth.kernel_inputs(seed, B, T, 1)
+    mel2ph = torch.ones(B, T, dtype=torch.long)
+    mel2ph[-1, T - 7:] = 0
+    with torch.no_grad():
+        ref = O.diffusion_infer_plms(sd, sched, torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX), inp["cond"], K_STEP, interval,
+                                     inp["fs2_mel"], inp["start_noise"], mel2ph=mel2ph)
+    mel = plan.sample_plms(inp["cond"].to(dev), inp["fs2_mel"].to(dev), inp["start_noise"].to(dev), interval=interval,
+                           mel2ph=mel2ph.to(dev)).cpu()
+    assert float((mel - ref).abs().max()) <= MEL_TOL
+    assert float(mel[-1, T - 7:].abs().max()) == 0.0
+    if (B, T, interval) == (1, 60, 5):
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "plms_golden.npz"))
+        unmasked = plan.sample_plms(inp["cond"].to(dev), inp["fs2_mel"].to(dev), inp["start_noise"].to(dev), interval=interval).cpu()
+        assert np.abs(unmasked.numpy() - g["mel.0"]).max() <= MEL_TOL
+
+
 def test_sampler_mel2ph_mask_and_gaussian_start(diff, dev):
     sd, sched, plan = diff
     B, T = 2, 90

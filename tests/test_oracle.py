@@ -123,3 +123,19 @@ def test_live_reference_matches_oracle(sd_diff):
         a = net(inp["start_noise"], t, inp["cond"].transpose(1, 2))
         b = O.diffnet_forward(sd_diff, inp["start_noise"], t, inp["cond"].transpose(1, 2))
     assert float((a - b).abs().max()) < 2e-5
+
+
+def test_plms_sampler_vs_golden(sd_diff):
+    """oracle.diffusion_infer_plms against the executed reference's p_sample_plms loop (oracle/make_golden_plms.py)."""
+    import os
+    from make_golden_plms import PLMS_CASES
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "plms_golden.npz"))
+    sched = O.schedule_buffers(O.linear_beta_schedule(K_STEP, MAX_BETA))
+    smin, smax = torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX)
+    for i, c in enumerate(PLMS_CASES):
+        inp = synth.kernel_inputs(c["seed"], c["B"], c["T"], 1)
+        with torch.no_grad():
+            mel, x0 = O.diffusion_infer_plms(sd_diff, sched, smin, smax, inp["cond"], K_STEP, c["interval"], inp["fs2_mel"],
+                                             inp["start_noise"], return_x=True)
+        assert np.abs(mel.numpy() - g[f"mel.{i}"]).max() < 1e-4
+        assert np.abs(x0.numpy() - g[f"x0.{i}"]).max() < 5e-5
