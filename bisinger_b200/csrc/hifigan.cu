@@ -17,6 +17,7 @@
 // delta with 0 <= delta*u + p + pad < k, written to columns [p*Cout, (p+1)*Cout) of the [rows_in][u*Cout] view of the
 // output (which is the same memory as [rows_in*u][Cout]).
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <memory>
 
@@ -327,6 +328,8 @@ HifiganPlan::HifiganPlan(const bsg_hifigan_config& c, const float* w, size_t n_w
     d_seed.alloc(sizeof(unsigned long long));
     ConvGemmArgs none{};
     for (int nt : {256, 128, 64, 32}) launch_conv_gemm(nt, 1, EPI_BIAS_ACT, none, nullptr);
+    if (const char* np = std::getenv("BSG_VOC_PAIR")) pair_mode = np[0] == '1';
+    if (pair_mode) for (int nt : {256, 128}) launch_conv_gemm(nt, 1, EPI_BIAS_ACT, none, nullptr, 1);
 }
 
 HifiganPlan::~HifiganPlan() = default;
@@ -406,17 +409,20 @@ void HifiganPlan::forward(const float* mel, const float* f0, const float* rand_i
     auto run_conv = [&](Conv& cv, const void* a_ptr, int a_pitch, int Lrows, const std::vector<int>& shifts, const EpiParams& epi) {
         ConvGemmArgs a{};
         const int nt = ntile_for(cv.cout);
-        set_geometry(a, B, Lrows, cv.cout, nt);
+        // wide stages on 2-CTA tiles (M = 256): a single CTA reads 12 KB (N = 256) / 8 KB (N = 128) of shared memory per MMA and is
+        // bound by that; a pair reads 8 / 6 KB per SM
+        const int pair = (pair_mode && nt >= 128 && static_cast<long long>(B) * Lrows >= 4096) ? 1 : 0;
+        set_geometry(a, B, Lrows, cv.cout, nt, pair != 0);
         const int cp = ((cv.cin + kBlockK - 1) / kBlockK) * kBlockK;
         const int rows_box = set_taps(a, 0, 0, cp / kBlockK, shifts.data(), static_cast<int>(shifts.size()), cp);
         a.amap[0] = make_act_tmap(a_ptr, B, Lrows, cv.cin, a_pitch, rows_box);
         a.amap[1] = a.amap[0];
-        cv.w.maps(nt, a.wmap[0], a.wmap[1]);
+        cv.w.maps(pair ? nt / 2 : nt, a.wmap[0], a.wmap[1]);
         a.k_steps = cv.cin >= kBlockK ? 0 : (cv.cin + 15) / 16;
-        a.w_resident = (a.n_tiles_n == 1 && static_cast<int>(shifts.size()) * (cp / kBlockK) <= conv_gemm_weight_slots(nt, 1)) ? 1 : 0;
+        a.w_resident = (!pair && a.n_tiles_n == 1 && static_cast<int>(shifts.size()) * (cp / kBlockK) <= conv_gemm_weight_slots(nt, 1)) ? 1 : 0;
         a.epi = epi;
         a.epi.bias = cv.bias.as<float>();
-        launch_conv_gemm(nt, 1, EPI_BIAS_ACT, a, st);
+        launch_conv_gemm(nt, 1, EPI_BIAS_ACT, a, st, pair);
         launches += 1, g_launch_count += 1;
     };
     auto same_shifts = [](int k, int dil) {

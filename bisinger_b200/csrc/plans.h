@@ -77,6 +77,7 @@ public:
     bsg_hifigan_config cfg;
     int device;
     int hop = 1;
+    bool pair_mode = true;   // 2-CTA tiles for the >= 128-channel stages (BSG_VOC_PAIR=0: single-CTA tiles everywhere)
     unsigned long long launches = 0;
 
 private:
