@@ -276,10 +276,29 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     auto b_out = take(p, M);
     inproj.pack(w_in, C, M);
     upload(inproj_bias, b_in);
-    skipall.pack(skip_w, C, L * C, f16);
-    upload(skipall_bias, skip_b);
-    skipproj.pack(w_skip, C, C);
-    upload(skipproj_bias, b_skip);
+    {
+        // skip_projection folded into the skip sum (no nonlinearity between them, net.py:126-128):
+        //   relu(W_sp (sum_l W_skip,l z_l + b_skip) / sqrt(L) + b_sp) = relu(((W_sp W_skip) z + W_sp b_skip + sqrt(L) b_sp) / sqrt(L))
+        // one K = L*C GEMM produces the head activation h directly; products in fp64 on the host
+        std::vector<float> fold(static_cast<size_t>(C) * L * C);
+        std::vector<float> fold_b(C);
+        std::vector<double> acc(static_cast<size_t>(L) * C);
+        const double sqrtL = std::sqrt(static_cast<double>(L));
+        for (int o2 = 0; o2 < C; ++o2) {
+            std::fill(acc.begin(), acc.end(), 0.0);
+            double ab = 0.0;
+            for (int o = 0; o < C; ++o) {
+                const double ws = w_skip[static_cast<size_t>(o2) * C + o];
+                const float* row = &skip_w[static_cast<size_t>(o) * L * C];
+                for (int k = 0; k < L * C; ++k) acc[k] += ws * row[k];
+                ab += ws * skip_b[o];
+            }
+            for (int k = 0; k < L * C; ++k) fold[static_cast<size_t>(o2) * L * C + k] = static_cast<float>(acc[k]);
+            fold_b[o2] = static_cast<float>(ab + sqrtL * b_skip[o2]);
+        }
+        skipall.pack(fold, C, L * C, f16);
+        upload(skipall_bias, fold_b);
+    }
     outproj.pack(w_out, M, C);
     upload(outproj_bias, b_out);
 
@@ -510,7 +529,8 @@ LayerArgs DiffusionPlan::fused_args(Workspace& w, int l0, int n, const float* lu
     return a;
 }
 
-// skip sum of all layers as one K = L*C GEMM over the step's z matrix (net.py:77-78,126), / sqrt(L), -> s (bf16 hi/lo)
+// skip sum of all layers + skip_projection + ReLU as one K = L*C GEMM over the step's z matrix (net.py:77-78,126-128; weights
+// pre-multiplied in the constructor) -> h (bf16 hi/lo), the A operand of the output projection
 ConvGemmArgs DiffusionPlan::skipsum_args(Workspace& w) {
     const int C = cfg.residual_channels, L = cfg.residual_layers;
     ConvGemmArgs a{};
@@ -520,10 +540,10 @@ ConvGemmArgs DiffusionPlan::skipsum_args(Workspace& w) {
     set_w(a, skipall, nt >> skip_mode);
     set_taps(a, 0, 0, L * C / kBlockK, kOneTap, 1, 0);
     a.epi.bias = skipall_bias.as<float>();
-    a.epi.out_hi = w.s_hi.as<__nv_bfloat16>();
-    a.epi.out_lo = w.s_lo.p ? w.s_lo.as<__nv_bfloat16>() : nullptr;
+    a.epi.out_hi = w.h_hi.as<__nv_bfloat16>();
+    a.epi.out_lo = w.h_lo.p ? w.h_lo.as<__nv_bfloat16>() : nullptr;
     a.epi.out_pitch = C;
-    a.epi.flags = 1;                                        // no ReLU
+    a.epi.flags = 0;                                        // ReLU (net.py:128)
     a.epi.c0 = 1.0f / std::sqrt(static_cast<float>(L));
     return a;
 }
@@ -647,21 +667,8 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
             ++launches, ++g_launch_count;
         }
     }
-    {   // skip sum: sum_l (W_skip,l z_l + b_skip,l) / sqrt(L)  (net.py:77-78,126) as one K = L*C GEMM over the step's z matrix
+    {   // skip sum sum_l (W_skip,l z_l + b_skip,l) / sqrt(L) (net.py:77-78,126) and skip_projection + ReLU (:127-128): one K = L*C GEMM
         launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
-        ++launches, ++g_launch_count;
-    }
-    {   // skip_projection + ReLU (net.py:127-128)
-        ConvGemmArgs a{};
-        set_geometry(a, B, T, C, 256);
-        a.amap[0] = w.m_s[0]; a.amap[1] = w.m_s[1];
-        set_w(a, skipproj, 256);
-        set_taps(a, 0, 0, C / kBlockK, kOneTap, 1, 0);
-        a.epi.bias = skipproj_bias.as<float>();
-        a.epi.out_hi = w.h_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.h_lo);
-        a.epi.out_pitch = C;
-        a.epi.c0 = 1.0f;
-        launch_conv_gemm(256, terms_side, EPI_RELU_BF16, a, st);
         ++launches, ++g_launch_count;
     }
     {   // output_projection (net.py:129) fused with the DDPM posterior update (shallow_diffusion_tts.py:149-166)

@@ -57,8 +57,8 @@ private:
                       float* eps_out = nullptr);
 
     std::vector<Layer> layers;
-    PackedW inproj, skipproj, outproj, skipall;   // skipall: skip halves of all output projections, [C][L*C]
-    DevBuf inproj_bias, skipproj_bias, outproj_bias, skipall_bias;
+    PackedW inproj, outproj, skipall;   // skipall: skip_projection x the skip halves of all output projections, [C][L*C]
+    DevBuf inproj_bias, outproj_bias, skipall_bias;
     DevBuf lut, d_spec_min, d_spec_max, d_seed;
     std::vector<StepCoef> sched;
     std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
