@@ -287,9 +287,20 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
         for (int mm = lo; mm <= hi; ++mm) {
             int v;
             unsigned spins = 0;
+            long long t_start = 0;
             do {
                 asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(f + mm) : "memory");
-                if (v < 2 * kEpiWarps && (++spins & 15) == 0) __nanosleep(64);
+                if (v < 2 * kEpiWarps && (++spins & 15) == 0) {
+                    __nanosleep(64);
+                    // bounded: the dataflow needs every CTA of the grid resident (one per SM, sized from the device's SM count);
+                    // if something else pins SMs for seconds, fail loudly instead of hanging the device
+                    const long long now = clock64();
+                    if (t_start == 0) t_start = now;
+                    if (now - t_start > 8000000000LL) {
+                        printf("diffnet_layer_kernel: block %d waited > 4 s for row tile %d of layer %d\n", blockIdx.x, mm, l - 1);
+                        __trap();
+                    }
+                }
             } while (v < 2 * kEpiWarps);
         }
         asm volatile("fence.proxy.async.global;" ::: "memory");
