@@ -625,7 +625,8 @@ __device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int 
 template <int N_TILE, int TERMS, bool PAIR = false>
 struct GemmSmem {
     static constexpr int kAParts = TERMS == 3 ? 2 : 1;                              // activations: hi/lo only in bf16x3
-    static constexpr int kBParts = TERMS >= 2 ? 2 : 1;                              // weights: hi/lo in bf16x3 and fp16x2
+    static constexpr int kBParts = (TERMS == 2 || TERMS == 3) ? 2 : 1;              // weights: hi/lo in bf16x3 and fp16x2 (TERMS 4: fp16 tiles and e5m2
+                                                                                    // correction tiles take turns in single-part slots)
     static constexpr int kASlotRows = TERMS == 1 ? 192 : 144;                       // halo tile capacity
     static constexpr int kAPartBytes = kASlotRows * kBlockK * 2;                    // one of hi / lo
     static constexpr int kBPartBytes = (PAIR ? N_TILE / 2 : N_TILE) * kBlockK * 2;       // PAIR: each CTA stages half of the N columns
@@ -666,7 +667,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     using S = GemmSmem<N_TILE, TERMS, PAIR>;
     static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128");
     constexpr int kTmemCols = tmem_cols_for(2 * N_TILE);
-    constexpr uint32_t kIdesc = umma_idesc_f16(PAIR ? 2 * kTileM : kTileM, N_TILE, /*fp16=*/TERMS == 2);
+    constexpr uint32_t kIdesc = umma_idesc_f16(PAIR ? 2 * kTileM : kTileM, N_TILE, /*fp16=*/TERMS == 2 || TERMS == 4);
+    // TERMS == 4 ("fp16 + fp8 correction", PAIR only): amap[0] / wmap[0] = fp16 activations / fp16(W 2^p) as in TERMS 2; after every second
+    // 64-channel k-block one 128-channel block of amap[1] = e4m3 activations x wmap[1] = e5m2(W 2^p - hi) on the fp8 pipe (K = 32 per
+    // MMA, twice the rate) into the same accumulator -- see diffnet_layer.cuh
+    constexpr uint32_t kIdesc8 = umma_idesc_f8(PAIR ? 2 * kTileM : kTileM, N_TILE, 0, 1);
+    static_assert(TERMS != 4 || (PAIR && !MC), "the fp8-correction mode is built for 2-CTA tiles");
     constexpr int kTileRows = PAIR ? 2 * kTileM : kTileM;
     // Narrow tiles (N_TILE = 32: the last HiFi-GAN stage) are bound by the epilogue's latency chain, not by its width: instead of
     // idling, the second group of four epilogue warps takes every other tile (accumulator buffer = tile parity = group).
@@ -741,7 +747,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                     const int slot = kb * ts.n_taps + tp;
                     mbar_arrive_expect_tx(&bfull_bar[slot], b_bytes);
                     tma_load_2d(smem_b + slot * S::kBSlotBytes, &args.wmap[0], &bfull_bar[slot], ts.w_col0[tp] + kb * kBlockK, args.w_row0);
-                    if (TERMS >= 2) tma_load_2d(smem_b + slot * S::kBSlotBytes + S::kBPartBytes, &args.wmap[1], &bfull_bar[slot], ts.w_col0[tp] + kb * kBlockK, args.w_row0);
+                    if (TERMS == 2 || TERMS == 3) tma_load_2d(smem_b + slot * S::kBSlotBytes + S::kBPartBytes, &args.wmap[1], &bfull_bar[slot], ts.w_col0[tp] + kb * kBlockK, args.w_row0);
                 }
         }
         for (int unit = worker; unit < n_units; unit += n_workers) {
@@ -778,17 +784,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                         const uint16_t mc_mask = static_cast<uint16_t>(5u << rank);
                         uint8_t* dq = sb + pidx * (S::kBPartBytes / 2);
                         tma_load_2d_pair_mc(dq, &args.wmap[0], &bfull_bar[bs], wc, wrow, mc_mask);
-                        if (TERMS >= 2) tma_load_2d_pair_mc(dq + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow, mc_mask);
+                        if (TERMS == 2 || TERMS == 3) tma_load_2d_pair_mc(dq + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow, mc_mask);
                     } else if constexpr (PAIR) {
                         if (rank == 0) mbar_arrive_expect_tx(&bfull_bar[bs], b_bytes);
                         tma_load_2d_pair(sb, &args.wmap[0], &bfull_bar[bs], wc, wrow);
-                        if (TERMS >= 2) tma_load_2d_pair(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
+                        if (TERMS == 2 || TERMS == 3) tma_load_2d_pair(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
                     } else {
                         mbar_arrive_expect_tx(&bfull_bar[bs], b_bytes);
                         tma_load_2d(sb, &args.wmap[0], &bfull_bar[bs], wc, wrow);
-                        if (TERMS >= 2) tma_load_2d(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
+                        if (TERMS == 2 || TERMS == 3) tma_load_2d(sb + S::kBPartBytes, &args.wmap[1], &bfull_bar[bs], wc, wrow);
                     }
                     if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
+                }
+                if constexpr (TERMS == 4) {
+                    if (kb & 1) {
+                        // the fp8 correction block of the 128 channels just covered: e4m3 activations (amap[1]) x e5m2 weight remainders (wmap[1])
+                        const int c8 = (kb >> 1) * 128;
+                        mbar_wait_tr(&aempty_bar[as], aph ^ 1, tr, w_a);
+                        if (rank == 0) mbar_arrive_expect_tx(&afull_bar[as], a_bytes);
+                        tma_load_3d_pair(smem_a + as * S::kASlotBytes, &args.amap[1], &afull_bar[as], ts.a_col0 + c8, ar, b);
+                        if (++as == S::kAStages) { as = 0; aph ^= 1; }
+                        for (int tp = 0; tp < ts.n_taps; ++tp) {
+                            mbar_wait_tr(&bempty_bar[bs], bph ^ 1, tr, w_b);
+                            if (rank == 0) mbar_arrive_expect_tx(&bfull_bar[bs], b_bytes);
+                            tma_load_2d_pair(smem_b + bs * S::kBSlotBytes, &args.wmap[1], &bfull_bar[bs], ts.w_col0[tp] + c8, wrow);
+                            if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
+                        }
+                    }
                 }
             }
         }
@@ -837,11 +859,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                         if constexpr (PAIR) {
                             umma_f16_pair(tacc, da, db, kIdesc, accumulate);
                             if (TERMS == 3) umma_f16_pair(tacc, umma_smem_desc<128>(a_lo + k * 32), db, kIdesc, 1);
-                            if (TERMS >= 2) umma_f16_pair(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
+                            if (TERMS == 2 || TERMS == 3) umma_f16_pair(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
                         } else {
                             umma_f16(tacc, da, db, kIdesc, accumulate);
                             if (TERMS == 3) umma_f16(tacc, umma_smem_desc<128>(a_lo + k * 32), db, kIdesc, 1);
-                            if (TERMS >= 2) umma_f16(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
+                            if (TERMS == 2 || TERMS == 3) umma_f16(tacc, da, umma_smem_desc<128>(b_lo + k * 32), kIdesc, 1);
                         }
                         accumulate = 1;
                     }
@@ -853,6 +875,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                 // free the halo tile after its last tap
                 if constexpr (PAIR) umma_commit_pair(&aempty_bar[as], pair_mask); else umma_commit(&aempty_bar[as]);
                 if (++as == S::kAStages) { as = 0; aph ^= 1; }
+                if constexpr (TERMS == 4) {
+                    if (kb & 1) {
+                        mbar_wait_tr(&afull_bar[as], aph, tr, w_a);
+                        tc_fence_after();
+                        const uint32_t a8 = smem_u32(smem_a + as * S::kASlotBytes);
+                        for (int tp = 0; tp < ts.n_taps; ++tp) {
+                            mbar_wait_tr(&bfull_bar[bs], bph, tr, w_b);
+                            tc_fence_after();
+                            const uint32_t a_op = a8 + ts.row_off[tp] * 128, b_op = smem_u32(smem_b + bs * S::kBSlotBytes);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f8_pair(tacc, umma_smem_desc<128>(a_op + k * 32), umma_smem_desc<128>(b_op + k * 32), kIdesc8, 1);
+                            umma_commit_pair(&bempty_bar[bs], pair_mask);
+                            if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
+                        }
+                        umma_commit_pair(&aempty_bar[as], pair_mask);
+                        if (++as == S::kAStages) { as = 0; aph ^= 1; }
+                    }
+                }
             }
             // accumulator complete -> epilogue (of both CTAs)
             if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc], pair_mask); else umma_commit(&tfull_bar[acc]);
@@ -890,8 +931,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             }
             // the fp16x2 per-layer GEMMs (gate, residual) feed fp16x2 consumers: fp16 operand output decided at compile time
             if (MC && b >= args.B) { /* the odd row tile of the last unit does not exist */ }
-            else if (args.L - t_warp >= 32) run_epilogue<N_TILE, EPI, true, TERMS == 2>(args.epi, args.L, tacc, b, t_warp, n_tile, grp, stage, lane);
-            else run_epilogue<N_TILE, EPI, false, TERMS == 2>(args.epi, args.L, tacc, b, t_warp, n_tile, grp, stage, lane);
+            else if (args.L - t_warp >= 32) run_epilogue<N_TILE, EPI, true, TERMS == 2 || TERMS == 4>(args.epi, args.L, tacc, b, t_warp, n_tile, grp, stage, lane);
+            else run_epilogue<N_TILE, EPI, false, TERMS == 2 || TERMS == 4>(args.epi, args.L, tacc, b, t_warp, n_tile, grp, stage, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

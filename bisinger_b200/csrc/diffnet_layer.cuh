@@ -57,6 +57,7 @@ struct LayerArgs {
     int a_rows;            // rows of the xa halo boxes (128 + 2 * max dilation, multiple of 8)
     int z_pitch;           // elements per row of the z matrix (layer l owns columns [l*C, (l+1)*C))
     __half* z_out;         // z matrix base
+    uint8_t* z8_out;       // e4m3 copy of z (same shape): A operand of the skip-sum GEMM's fp8 correction term; may be null
     __half* xa16_out[2];   // conv input buffers as plain pointers (layer l writes [(l + 1) & 1])
     uint8_t* xa8_out[2];
     const float* lut_t;    // [total layers][C] step embeddings d_l of this diffusion step
@@ -532,6 +533,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                 // (loops kept rolled: with the four roles' code paths resident the unrolled epilogue stalled on instruction fetch)
                 const float hs = 0.5f * gscale;
                 __half* zrow = args.z_out + row * args.z_pitch + l * C + op.h * 128;
+                uint8_t* z8row = args.z8_out ? args.z8_out + row * args.z_pitch + l * C + op.h * 128 : nullptr;
                 // one 16-channel chunk; vg / vf: its gate / filter accumulator columns (already waited for)
                 auto gate_chunk = [&](int c, const uint32_t (&vg)[16], const uint32_t (&vf)[16]) {
                     const int cg = grp * 64 + c * 16;          // gate columns [cg, cg+16), filter columns +128
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                         pg[k] = lds128(smem_e + sg * S::kEBoxBytes + xo[k]);
                         pf[k] = lds128(smem_e + sf * S::kEBoxBytes + xo[k]);
                     }
-                    uint32_t zz[8];
+                    uint32_t zz[8], z8[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         // sigmoid(g) = 0.5 tanh(g/2) + 0.5: the gate pre-activations are formed already halved
@@ -553,15 +555,20 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                         const float g2 = fmaf(__uint_as_float(vg[4 * k + 2]), hs, 0.5f * pg[k].z), g3 = fmaf(__uint_as_float(vg[4 * k + 3]), hs, 0.5f * pg[k].w);
                         const float f0 = fmaf(__uint_as_float(vf[4 * k]), gscale, pf[k].x), f1 = fmaf(__uint_as_float(vf[4 * k + 1]), gscale, pf[k].y);
                         const float f2 = fmaf(__uint_as_float(vf[4 * k + 2]), gscale, pf[k].z), f3 = fmaf(__uint_as_float(vf[4 * k + 3]), gscale, pf[k].w);
-                        zz[2 * k] = pack_half2_nc(gate_half(g0, f0), gate_half(g1, f1));
-                        zz[2 * k + 1] = pack_half2_nc(gate_half(g2, f2), gate_half(g3, f3));
+                        const float z0 = gate_half(g0, f0), z1 = gate_half(g1, f1), z2 = gate_half(g2, f2), z3 = gate_half(g3, f3);
+                        zz[2 * k] = pack_half2_nc(z0, z1);
+                        zz[2 * k + 1] = pack_half2_nc(z2, z3);
+                        z8[k] = pack_e4m3x4(z0, z1, z2, z3);
                     }
                     // hand the boxes back only now: the arithmetic above could not issue before the ld.shared data had arrived.
                     // (Signalling right behind the ld.shared instructions let the TMA refill overtake loads still queued
                     // behind this warp's stores -- a rare 32-row corruption.)
                     __syncwarp();
                     if (lane == 0) { mbar_arrive_relaxed(&edone_bar[sg]); mbar_arrive_relaxed(&edone_bar[sf]); }
-                    if (row_ok) stg256(zrow + cg, zz);
+                    if (row_ok) {
+                        stg256(zrow + cg, zz);
+                        if (z8row != nullptr) *reinterpret_cast<uint4*>(z8row + cg) = make_uint4(z8[0], z8[1], z8[2], z8[3]);
+                    }
                 };
                 // the accumulator columns of chunk c+1 are read from TMEM while chunk c is processed (under MMA load a
                 // tcgen05.ld round trip is ~1k cycles and was 40 % of this loop: profiles/r01_h)
