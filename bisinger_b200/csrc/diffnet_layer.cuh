@@ -1,10 +1,12 @@
-// One DiffNet ResidualBlock (usr/diff/net.py:58-78) as ONE persistent 2-CTA kernel.
+// The DiffNet ResidualBlocks (usr/diff/net.py:58-78) as ONE persistent 2-CTA kernel: one launch runs a range of layers
+// (normally all 20 of a diffusion step), row tiles flowing from layer to layer as soon as their inputs are complete.
 //
 // Per 256-row tile n (128 rows per CTA of the pair) three GEMM "ops" run on one producer / MMA / epilogue pipeline:
 //     G(n,0)  G(n,1)   : acc[256 x 256] = conv_dilated(xa)[:, gate | filter rows of channel half h]            (K = 3 x 256)
 //                        epilogue: + conditioner projection, sigmoid * tanh -> z (fp16, the all-layer z matrix)
 //     R(n)             : acc[256 x 256] = z[rows, this layer's columns] * W_res^T                               (K = 256)
-//                        epilogue: x = (x + acc + b) / sqrt2 -> x f32 ; fp16 / e4m3 of (x + d_next) -> next layer's conv input
+//                        epilogue: x = (x + acc + b) / sqrt2 with x = fp16 conv input - d_l (the residual stream is carried only
+//                        as the conv input) ; fp16 / e4m3 of (x + d_next) -> next layer's conv input
 // issued in the order  G(0,0) G(0,1) | G(1,0) G(1,1) R(0) | G(2,0) G(2,1) R(1) | ... | R(last)  so that the gate epilogues of
 // tile n (which R(n) depends on) overlap the gate GEMMs of tile n+1.  TMEM holds two 256-column accumulators that
 // alternate op by op.  R(n) reads the z rows the same CTA has just written: they go to global memory anyway (the skip sum
@@ -25,7 +27,11 @@
 // epilogue of conv_gemm.cuh needed 15-20k cycles per op here and paced the kernel (profiles/r01_g, r01_h).
 //
 // Warps: 0 = operand producer (TMA), 1 = MMA issuer (leader CTA), 2..9 = epilogue (TMEM lane quadrant = warp % 4, two
-// column groups), 10 = epilogue-operand producer (TMA loads of cp / x boxes, TMA stores of the updated x boxes).
+// column groups), 10 = epilogue-operand producer (TMA loads of the cp / conv-input boxes).
+//
+// Layers: row tile m of layer l reads halo rows of tiles m-1, m, m+1 of layer l-1; completion counters in global memory
+// (wait_inputs below) order that, the conv input ping-pongs between two buffers, and the deal of row tiles to CTA pairs rotates
+// per layer so that the uneven split (256 tiles over 74 pairs) averages out.
 #pragma once
 #include "conv_gemm.cuh"
 
