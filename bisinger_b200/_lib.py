@@ -44,12 +44,19 @@ class HifiganConfig(C.Structure):
     ]
 
 
+class PeConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n_mel_bins", "hidden_size", "prenet_layers", "conv_layers", "predictor_layers", "kernel_size",
+                                       "predictor_kernel", "predictor_hidden", "gn_group_size", "left_padding", "pitch_norm",
+                                       "use_uv")] + [("f0_mean", C.c_float), ("f0_std", C.c_float)]
+
+
 # every symbol include/bisinger_b200.h declares (tests check that the library exports all of them)
 EXPORTS = (
     "bsg_abi_version", "bsg_last_error", "bsg_kernel_launch_count",
     "bsg_diffusion_plan_create", "bsg_diffusion_plan_destroy", "bsg_diffusion_sample", "bsg_diffusion_sample_plms", "bsg_diffnet_forward",
     "bsg_diffusion_time_kernel",
     "bsg_hifigan_plan_create", "bsg_hifigan_plan_destroy", "bsg_hifigan_forward", "bsg_hifigan_source",
+    "bsg_pe_plan_create", "bsg_pe_plan_destroy", "bsg_pe_forward",
     "bsg_selftest_conv",
 )
 
@@ -83,6 +90,10 @@ def lib() -> C.CDLL:
     L.bsg_hifigan_plan_destroy.restype = None
     L.bsg_hifigan_forward.argtypes = [vp, fp, fp, fp, fp, C.c_ulonglong, ip, ip, fp, vp]
     L.bsg_hifigan_source.argtypes = [vp, fp, fp, fp, C.c_ulonglong, ip, ip, fp, vp]
+    L.bsg_pe_plan_create.argtypes = [C.POINTER(PeConfig), C.POINTER(C.c_float), C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.bsg_pe_plan_destroy.argtypes = [vp]
+    L.bsg_pe_plan_destroy.restype = None
+    L.bsg_pe_forward.argtypes = [vp, fp, ip, ip, fp, fp, vp]
     L.bsg_selftest_conv.argtypes = [fp, C.POINTER(C.c_float), C.POINTER(C.c_float), ip, ip, ip, ip, ip, C.POINTER(C.c_int),
                                     ip, ip, fp, vp]
     if L.bsg_abi_version() != 1:

@@ -34,6 +34,11 @@ struct bsg_hifigan_plan {
     template <class... A> explicit bsg_hifigan_plan(A&&... a) : impl(std::forward<A>(a)...) {}
 };
 
+struct bsg_pe_plan {
+    b200::PitchExtractorPlan impl;
+    template <class... A> explicit bsg_pe_plan(A&&... a) : impl(std::forward<A>(a)...) {}
+};
+
 extern "C" {
 
 int bsg_abi_version(void) { return BSG_ABI_VERSION; }
@@ -105,6 +110,21 @@ int bsg_hifigan_source(bsg_hifigan_plan* plan, const float* f0, const float* ran
     return guarded([&] {
         B200_CHECK(plan && f0 && har_source, "null argument");
         plan->impl.source(f0, rand_ini, src_noise, seed, B, T, har_source, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int bsg_pe_plan_create(const bsg_pe_config* cfg, const float* weights_host, size_t n_weights, int device, bsg_pe_plan** out) {
+    return guarded([&] {
+        B200_CHECK(cfg && weights_host && out, "null argument");
+        *out = new bsg_pe_plan(*cfg, weights_host, n_weights, device);
+    });
+}
+void bsg_pe_plan_destroy(bsg_pe_plan* plan) { delete plan; }
+
+int bsg_pe_forward(bsg_pe_plan* plan, const float* mel, int B, int T, float* pitch_pred, float* f0, void* stream) {
+    return guarded([&] {
+        B200_CHECK(plan && mel && pitch_pred && f0, "null argument");
+        plan->impl.forward(mel, B, T, pitch_pred, f0, static_cast<cudaStream_t>(stream));
     });
 }
 

@@ -217,6 +217,8 @@ void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, 
     // HiFi-GAN
     B200_PAIR(256, 1, EPI_BIAS_ACT) B200_PAIR(128, 1, EPI_BIAS_ACT)
     B200_CASE(256, 1, EPI_BIAS_ACT) B200_CASE(128, 1, EPI_BIAS_ACT) B200_CASE(64, 1, EPI_BIAS_ACT) B200_CASE(32, 1, EPI_BIAS_ACT)
+    // PitchExtractor (bf16x3)
+    B200_CASE(256, 3, EPI_BIAS_ACT) B200_PAIR(256, 3, EPI_BIAS_ACT)
     throw Error("conv_gemm: no instantiation for n_tile=" + std::to_string(n_tile) + " terms=" + std::to_string(terms) +
                 " epi=" + std::to_string(epi) + (pair == 2 ? " (pair, multicast)" : (pair ? " (pair)" : "")));
 }

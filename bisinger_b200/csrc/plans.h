@@ -108,4 +108,35 @@ private:
     std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
 };
 
+class PitchExtractorPlan {
+public:
+    PitchExtractorPlan(const bsg_pe_config& cfg, const float* weights, size_t n_weights, int device);
+    ~PitchExtractorPlan();
+    void forward(const float* mel, int B, int T, float* pitch_pred, float* f0, cudaStream_t st);
+
+    bsg_pe_config cfg;
+    int device;
+    bool pair_mode = true;   // 2-CTA tiles when the batch has >= 4096 rows (BSG_PE_PAIR=0: single-CTA tiles)
+    unsigned long long launches = 0;
+
+private:
+    struct Workspace;
+    struct Conv {
+        PackedW w;
+        DevBuf bias;
+        int cin = 0, cout = 0, k = 1;
+    };
+    struct Layer {           // convolution + the per-channel pair of its normalisation (scale/shift or gamma/beta)
+        Conv conv;
+        DevBuf p0, p1;
+    };
+    Workspace& workspace(int B, int T);
+
+    std::vector<Layer> prenet, encoder, predictor;
+    Conv prenet_out, enc_in, enc_out;
+    DevBuf pos_freq, lin;    // sinusoid frequencies [C/2]; final Linear weight [2][C] + bias [2]
+    float pos_alpha = 1.0f;
+    std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
+};
+
 }  // namespace b200

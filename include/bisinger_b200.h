@@ -42,6 +42,7 @@ extern "C" {
 
 typedef struct bsg_diffusion_plan bsg_diffusion_plan;
 typedef struct bsg_hifigan_plan bsg_hifigan_plan;
+typedef struct bsg_pe_plan bsg_pe_plan;
 
 int bsg_abi_version(void);
 const char* bsg_last_error(void);
@@ -172,6 +173,50 @@ int bsg_hifigan_forward(bsg_hifigan_plan* plan, const float* mel, const float* f
 /* NSF harmonic source only (hifigan.py:147-149): har_source device f32 [B][T*hop].  Exposed for parity tests. */
 int bsg_hifigan_source(bsg_hifigan_plan* plan, const float* f0, const float* rand_ini, const float* src_noise,
                        unsigned long long seed, int B, int T, float* har_source, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PitchExtractor: mel -> f0 between the sampler and the vocoder.
+ * Replaces  self.pe(mel_out)['f0_denorm_pred']   inference/m4singer/bisinger/a-lang-esm-style-ori-shift.py:629-630,
+ *           usr/diffsinger_task.py:107-113;  module: modules/fastspeech/pe.py:120-150 (eval mode).
+ * ------------------------------------------------------------------------------------------------ */
+#define BSG_PITCH_NORM_LOG 0      /* hparams['pitch_norm'] == 'log':      f0 = 2 ** pred       (utils/pitch_utils.py:66-67) */
+#define BSG_PITCH_NORM_STANDARD 1 /* 'standard':                          f0 = pred * f0_std + f0_mean          (:64-65)    */
+#define BSG_PITCH_NORM_NONE 2
+
+typedef struct {
+    int n_mel_bins;       /* PitchExtractor(n_mel_bins=80)                                                         */
+    int hidden_size;      /* 256 (pe.py:123)                                                                       */
+    int prenet_layers;    /* 3  (Prenet n_layers, pe.py:9)                                                         */
+    int conv_layers;      /* PitchExtractor(conv_layers=2): ConvStacks blocks, 0 = no mel_encoder (pe.py:128-130)  */
+    int predictor_layers; /* 5  (pe.py:133)                                                                        */
+    int kernel_size;      /* 5  (Prenet / ConvStacks kernel, pe.py:9,82)                                           */
+    int predictor_kernel; /* hparams['predictor_kernel'] (5)                                                       */
+    int predictor_hidden; /* hparams['predictor_hidden'] if > 0 else hidden_size                                   */
+    int gn_group_size;    /* 16: GroupNorm(n_chans // 16, n_chans) (pe.py:54)                                      */
+    int left_padding;     /* 0: hparams['ffn_padding'] == 'SAME'; 1: (k-1, 0) padding (tts_modules.py:212-214)     */
+    int pitch_norm;       /* BSG_PITCH_NORM_*                                                                      */
+    int use_uv;           /* hparams['pitch_type'] == 'frame' and hparams['use_uv'] (pe.py:146)                    */
+    float f0_mean, f0_std;
+} bsg_pe_config;
+
+/* weights_host: float32, in this order (names of the reference state_dict; BatchNorm folded by the caller):
+ *   for i < prenet_layers: mel_prenet.layers.i.0.{weight[C][Cin][k],bias[C]}, bn_scale[C], bn_shift[C]
+ *                          (scale = layers.i.2.weight / sqrt(running_var + 1e-5), shift = layers.i.2.bias - running_mean * scale)
+ *   mel_prenet.out_proj.{weight[C][C],bias[C]}
+ *   if conv_layers > 0: mel_encoder.in_proj.{weight,bias};
+ *                       for j < conv_layers: mel_encoder.conv.j.conv.conv.{weight[C][C][k],bias}, mel_encoder.conv.j.norm.{weight,bias};
+ *                       mel_encoder.out_proj.{weight,bias}
+ *   pitch_predictor.pos_embed_alpha[1], frequencies[C/2] = exp(arange(C/2) * -(ln 1e4 / (C/2 - 1)))  (common_layers.py:130-132)
+ *   for i < predictor_layers: pitch_predictor.conv.i.1.{weight[C][C][k],bias}, pitch_predictor.conv.i.3.{weight,bias}
+ *   pitch_predictor.linear.{weight[2][C],bias[2]}                                                                  */
+int bsg_pe_plan_create(const bsg_pe_config* cfg, const float* weights_host, size_t n_weights, int device, bsg_pe_plan** out);
+void bsg_pe_plan_destroy(bsg_pe_plan* plan);
+
+/* PitchExtractor.forward(mel_input) (pe.py:138-150).
+ *   mel        device f32 [B][T][n_mel_bins]  (the sampler's mel_out as it stands; all-zero frames are padding)
+ *   pitch_pred device f32 [B][T][2]           ret['pitch_pred']
+ *   f0         device f32 [B][T]              ret['f0_denorm_pred'] (Hz, 0 = unvoiced / padding)                   */
+int bsg_pe_forward(bsg_pe_plan* plan, const float* mel, int B, int T, float* pitch_pred, float* f0, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Kernel self-test: C[b][l][n] = bias[n] + sum_taps A[b][l+shift][:] . W[n][tap][:] through the same tcgen05

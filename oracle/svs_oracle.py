@@ -384,6 +384,97 @@ def hifigan_forward(p: Dict[str, Tensor], h: dict, mel: Tensor, f0: Optional[Ten
 
 
 # --------------------------------------------------------------------------------------
+# PitchExtractor: mel -> f0 between the sampler and the vocoder
+# --------------------------------------------------------------------------------------
+
+PE_HPARAMS = dict(predictor_hidden=-1, ffn_padding="SAME", predictor_kernel=5, pitch_type="frame", use_uv=True,
+                  pitch_norm="log", f0_mean=0.0, f0_std=1.0)   # configs/tts/fs2.yaml:13-14,23,33, configs/tts/base.yaml:64, usr/configs/base.yaml:2
+
+
+def pe_conv_layers(p: Dict[str, Tensor]) -> int:
+    n = 0
+    while f"mel_encoder.conv.{n}.conv.conv.weight" in p:
+        n += 1
+    return n
+
+
+def pe_positions(x0: Tensor) -> Tensor:
+    """utils/__init__.py:146-158 make_positions(tensor, padding_idx=0) on the float tensor xs[..., 0]
+    (modules/fastspeech/tts_modules.py:230): position = running count of non-zero entries, 0 where the entry is zero."""
+    mask = x0.ne(0).int()
+    return (torch.cumsum(mask, dim=1).type_as(mask) * mask).long()
+
+
+def pe_pos_table(n: int, dim: int) -> Tensor:
+    """modules/commons/common_layers.py:123-144 get_embedding(n, dim, padding_idx=0)."""
+    half = dim // 2
+    emb = math.log(10000) / (half - 1)
+    emb = torch.exp(torch.arange(half, dtype=torch.float) * -emb)
+    emb = torch.arange(n, dtype=torch.float).unsqueeze(1) * emb.unsqueeze(0)
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=1).view(n, -1)
+    emb[0, :] = 0
+    return emb
+
+
+def pe_forward(p: Dict[str, Tensor], mel: Tensor, hp: Optional[dict] = None) -> Dict[str, Tensor]:
+    """PitchExtractor.forward in eval mode (modules/fastspeech/pe.py:138-150): mel [B,T,80] ->
+    {'pitch_pred' [B,T,2], 'f0_denorm_pred' [B,T]}."""
+    hp = {**PE_HPARAMS, **(hp or {})}
+    # ---- Prenet (pe.py:24-42): 3 x [conv k5 -> ReLU -> BatchNorm1d(eval)] * nonpadding, Linear, * nonpadding
+    nonpad = 1 - mel.abs().sum(-1).eq(0).float()[:, None, :]          # [B,1,T]
+    x = mel.transpose(1, 2)
+    i = 0
+    while f"mel_prenet.layers.{i}.0.weight" in p:
+        pre = f"mel_prenet.layers.{i}."
+        k = p[pre + "0.weight"].shape[-1]
+        x = F.conv1d(x, p[pre + "0.weight"], p[pre + "0.bias"], padding=k // 2)
+        x = F.relu(x)
+        x = F.batch_norm(x, p[pre + "2.running_mean"], p[pre + "2.running_var"], p[pre + "2.weight"], p[pre + "2.bias"],
+                         training=False, eps=1e-5)
+        x = x * nonpad
+        i += 1
+    x = F.linear(x.transpose(1, 2), p["mel_prenet.out_proj.weight"], p["mel_prenet.out_proj.bias"])
+    x = x * nonpad.transpose(1, 2)
+    # ---- ConvStacks (pe.py:83-117), ConvBlock norm='gn' (:45-78): Linear, n x [x + ReLU(GroupNorm(C/16 groups)(conv k5))], Linear
+    n_enc = pe_conv_layers(p)
+    if n_enc > 0:
+        x = F.linear(x, p["mel_encoder.in_proj.weight"], p["mel_encoder.in_proj.bias"]).transpose(1, 2)
+        for j in range(n_enc):
+            pre = f"mel_encoder.conv.{j}."
+            w = p[pre + "conv.conv.weight"]
+            y = F.conv1d(x, w, p[pre + "conv.conv.bias"], padding=(w.shape[-1] - 1) // 2)    # ConvNorm, common_layers.py:56-58
+            y = F.group_norm(y, w.shape[0] // 16, p[pre + "norm.weight"], p[pre + "norm.bias"], eps=1e-5)
+            x = x + F.relu(y)
+        x = F.linear(x.transpose(1, 2), p["mel_encoder.out_proj.weight"], p["mel_encoder.out_proj.bias"])
+    # ---- PitchPredictor (tts_modules.py:224-237): + alpha * sinusoidal positions, 5 x [pad, conv k, ReLU, LayerNorm(C, eps 1e-12)], Linear -> 2
+    pos = pe_positions(x[..., 0])
+    table = pe_pos_table(max(4096, 1 + x.shape[1]), x.shape[-1])          # init_size=4096, grown to padding_idx+1+T (:151-158)
+    x = x + p["pitch_predictor.pos_embed_alpha"] * table[pos]
+    x = x.transpose(1, 2)
+    i = 0
+    while f"pitch_predictor.conv.{i}.1.weight" in p:
+        pre = f"pitch_predictor.conv.{i}."
+        k = p[pre + "1.weight"].shape[-1]
+        pad = ((k - 1) // 2, (k - 1) // 2) if hp["ffn_padding"] == "SAME" else (k - 1, 0)
+        x = F.conv1d(F.pad(x, pad), p[pre + "1.weight"], p[pre + "1.bias"])
+        x = F.relu(x)
+        x = F.layer_norm(x.transpose(1, 2), (x.shape[1],), p[pre + "3.weight"], p[pre + "3.bias"], eps=1e-12).transpose(1, 2)
+        i += 1
+    pred = F.linear(x.transpose(1, 2), p["pitch_predictor.linear.weight"], p["pitch_predictor.linear.bias"])
+    # ---- denorm_f0 (utils/pitch_utils.py:63-76) as called at pe.py:144-149
+    f0 = pred[:, :, 0]
+    if hp["pitch_norm"] == "standard":
+        f0 = f0 * hp["f0_std"] + hp["f0_mean"]
+    if hp["pitch_norm"] == "log":
+        f0 = 2 ** f0
+    f0 = f0.clone()
+    if hp["pitch_type"] == "frame" and hp["use_uv"]:
+        f0[pred[:, :, 1] > 0] = 0
+    f0[mel.abs().sum(-1) == 0] = 0
+    return {"pitch_pred": pred, "f0_denorm_pred": f0}
+
+
+# --------------------------------------------------------------------------------------
 # Metrics used by the parity tests
 # --------------------------------------------------------------------------------------
 

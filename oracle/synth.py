@@ -123,6 +123,59 @@ def hifigan_state(seed: int = 4321, h: dict | None = None) -> Dict[str, Tensor]:
     return sd
 
 
+def pe_state(seed: int = 777, conv_layers: int = 2, n_mel: int = 80, C: int = 256) -> Dict[str, Tensor]:
+    """State dict with the parameter/buffer names of PitchExtractor (modules/fastspeech/pe.py:120-136).  BatchNorm running
+    statistics and every affine are non-trivial so that each term of the eval-mode formulas matters; the last Linear is
+    scaled so that log2-f0 lands around 7..8.5 (130..360 Hz) with both signs of the uv logit."""
+    g = _gen(seed)
+    sd: Dict[str, Tensor] = {}
+
+    def conv(name, cout, cin, k):
+        sd[name + ".weight"] = _normal(g, (cout, cin, k), math.sqrt(2.0 / (cin * k)))
+        sd[name + ".bias"] = _uniform(g, (cout,), 1.0 / math.sqrt(cin * k))
+
+    def linear(name, cout, cin, gain=1.0):
+        sd[name + ".weight"] = _uniform(g, (cout, cin), gain * math.sqrt(6.0 / (cin + cout)))
+        sd[name + ".bias"] = _uniform(g, (cout,), 0.1)
+
+    def affine(name, n):
+        sd[name + ".weight"] = 1.0 + _uniform(g, (n,), 0.3)
+        sd[name + ".bias"] = _uniform(g, (n,), 0.2)
+
+    cin = n_mel
+    for i in range(3):
+        conv(f"mel_prenet.layers.{i}.0", C, cin, 5)
+        affine(f"mel_prenet.layers.{i}.2", C)
+        sd[f"mel_prenet.layers.{i}.2.running_mean"] = 0.3 + _uniform(g, (C,), 0.3)
+        sd[f"mel_prenet.layers.{i}.2.running_var"] = 0.5 + torch.rand((C,), generator=g)
+        sd[f"mel_prenet.layers.{i}.2.num_batches_tracked"] = torch.tensor(1000)
+        cin = C
+    linear("mel_prenet.out_proj", C, C)
+    for j in range(conv_layers):
+        conv(f"mel_encoder.conv.{j}.conv.conv", C, C, 5)
+        affine(f"mel_encoder.conv.{j}.norm", C)
+    if conv_layers > 0:
+        linear("mel_encoder.in_proj", C, C)
+        linear("mel_encoder.out_proj", C, C)
+    sd["pitch_predictor.pos_embed_alpha"] = torch.tensor([0.8])
+    for i in range(5):
+        conv(f"pitch_predictor.conv.{i}.1", C, C, 5)
+        affine(f"pitch_predictor.conv.{i}.3", C)
+    sd["pitch_predictor.linear.weight"] = _uniform(g, (2, C), 0.04)
+    sd["pitch_predictor.linear.bias"] = torch.tensor([7.8, 0.0])
+    sd["pitch_predictor.embed_positions._float_tensor"] = torch.zeros(1)
+    return sd
+
+
+def pe_inputs(seed: int, B: int, T: int, M: int = 80, pad_tail: int = 0) -> Tensor:
+    """Log-mel input [B,T,80] as vocoder_inputs draws it; the last `pad_tail` frames of every odd batch row are all-zero
+    padding frames (pe.py:30,145: padding = frames whose |mel| sums to 0)."""
+    mel = vocoder_inputs(seed, B, T, M=M)["mel"].transpose(1, 2).contiguous()
+    if pad_tail > 0:
+        mel[1::2, T - pad_tail:, :] = 0.0
+    return mel
+
+
 def kernel_inputs(seed: int, B: int, T: int, K: int, M: int = 80, H: int = 256) -> Dict[str, Tensor]:
     """Kernel-level sampler inputs: cond ~ N(0,1) [B,T,H], fs2_mel in the log-mel
     range, q_sample noise and per-step noise z_k ~ N(0,1)."""
