@@ -114,6 +114,14 @@ def build_models(dev, precision):
     return gd, gen, synth
 
 
+def build_pitch_extractor(dev, synth):
+    from bisinger_b200.pitch import B200PitchExtractor
+    pe = B200PitchExtractor().eval()
+    pe.load_state_dict(synth.pe_state(777, 2), strict=True)
+    pe.build_plan(dev)
+    return pe
+
+
 def host_inputs(synth, B, T, seed):
     import torch
     k = synth.kernel_inputs(seed, B, T, 1)
@@ -222,7 +230,10 @@ def run_ours(args):
                                              "dilated-conv GEMM k=3 256->512 with fp16 + fp8-correction MMAs, gate epilogue, residual GEMM 256->256, "
                                              "residual epilogue)",
                 "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops"], 4),
-                "traffic": None, "avg_launch_ms": round(k_ms * n_layers, 4), "algorithmic_flops_per_launch": layer_flops * n_layers,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 20-layer launch at cfg3 from the ncu --set full capture
+                # summarised in profiles/r01_h_fused_layer_kernel.txt (3.94 GB read + 1.48 GB written); other shapes: not captured
+                "traffic": 5.42e9 if (B, T) == (BATCH, FRAMES) else None,
+                "avg_launch_ms": round(k_ms * n_layers, 4), "algorithmic_flops_per_launch": layer_flops * n_layers,
                 "ms_per_layer": round(k_ms, 4),
                 "issued_mma_flops_per_algorithmic_flop": 2,
                 "issued_note": "per product one fp16 MMA + one correction MMA; the gate GEMM's correction runs at the fp8 rate (2x) => 1.5 fp16-MMA "
@@ -253,6 +264,15 @@ def run_ours(args):
                                 ("fused_layer_launch" if fused else "gate_gemm_launch"): round(k_ms, 4), "resskip_gemm_launch": round(r_ms, 4),
                                 "skipsum_gemm_launch": round(s_ms, 4),
                                 "layer_gemms_share_of_sampler": round(20 * K_STEP * (k_ms + r_ms) / e0.elapsed_time(e1), 3)}
+        # the stage the reference runs between the two when hparams['pe_enable'] (mel -> f0); reported beside the
+        # step, not part of it: the metric's workload feeds the vocoder a synthetic f0
+        pe = build_pitch_extractor(dev, synth)
+        for _ in range(2):
+            pe(mel_t)
+        e3, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e3.record(stream); pe(mel_t); e4.record(stream)
+        torch.cuda.synchronize(dev)
+        line["breakdown_ms"]["pitch_extractor_not_in_step"] = round(e3.elapsed_time(e4), 3)
         line["pipeline_algorithmic_tflops"] = round((FLOPS_DIFFNET_FRAME_STEP_HOISTED * K_STEP + FLOPS_COND_ONCE_FRAME + FLOPS_HIFIGAN_FRAME) * B * T * world * args.steps / (ms * 1e-3) / 1e12, 1)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(steps=1, warmup=1)

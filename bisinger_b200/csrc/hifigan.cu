@@ -199,6 +199,14 @@ int ntile_for(int cout) { return cout >= 256 ? 256 : cout; }
 struct HifiganPlan::Workspace {
     int B = 0, T = 0;
     DevBuf mel16, har, phase0, upin[2], X0, Xr, S, A0, Ar, Tb;
+    // graph path (no injected noise): plan-owned copies of the caller's buffers, so that the captured launches see fixed addresses
+    DevBuf in_mel, in_f0, out_wav;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [has_src]
+    unsigned long long graph_nodes[2] = {0, 0};
+    ~Workspace() {
+        for (auto& g : graph)
+            if (g) cudaGraphExecDestroy(g);
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -329,6 +337,7 @@ HifiganPlan::HifiganPlan(const bsg_hifigan_config& c, const float* w, size_t n_w
     ConvGemmArgs none{};
     for (int nt : {256, 128, 64, 32}) launch_conv_gemm(nt, 1, EPI_BIAS_ACT, none, nullptr);
     if (const char* np = std::getenv("BSG_VOC_PAIR")) pair_mode = np[0] == '1';
+    if (const char* ng = std::getenv("BSG_VOC_GRAPH")) use_graphs = ng[0] == '1';
     if (pair_mode) for (int nt : {256, 128}) launch_conv_gemm(nt, 1, EPI_BIAS_ACT, none, nullptr, 1);
 }
 
@@ -373,7 +382,6 @@ void HifiganPlan::run_source(Workspace& w, const float* f0, const float* rand_in
                              int T, cudaStream_t st) {
     const int dim = cfg.harmonic_num + 1;
     B200_CHECK(cfg.use_pitch_embed, "this generator was built without the NSF source (use_pitch_embed = 0)");
-    B200_CUDA(cudaMemcpyAsync(d_seed.p, &seed, sizeof(seed), cudaMemcpyHostToDevice, st));
     nsf_phase_kernel<<<(B * dim + 63) / 64, 64, 0, st>>>(f0, rand_ini, B, T, hop, dim, static_cast<float>(cfg.audio_sample_rate),
                                                          w.phase0.as<double>());
     const long long n = static_cast<long long>(B) * T * hop;
@@ -390,6 +398,7 @@ void HifiganPlan::source(const float* f0, const float* rand_ini, const float* sr
     B200_CHECK(B > 0 && T > 0, "empty batch");
     B200_CUDA(cudaSetDevice(device));
     Workspace& w = workspace(B, T);
+    B200_CUDA(cudaMemcpyAsync(d_seed.p, &seed, sizeof(seed), cudaMemcpyHostToDevice, st));
     run_source(w, f0, rand_ini, src_noise, seed, B, T, st);
     B200_CUDA(cudaMemcpyAsync(har, w.har.p, static_cast<size_t>(B) * T * hop * 4, cudaMemcpyDeviceToDevice, st));
 }
@@ -399,6 +408,49 @@ void HifiganPlan::forward(const float* mel, const float* f0, const float* rand_i
     B200_CHECK(B > 0 && T > 0, "empty batch");
     B200_CUDA(cudaSetDevice(device));
     Workspace& w = workspace(B, T);
+    const size_t BT = static_cast<size_t>(B) * T;
+    const int has_src = f0 != nullptr ? 1 : 0;
+    B200_CUDA(cudaMemcpyAsync(d_seed.p, &seed, sizeof(seed), cudaMemcpyHostToDevice, st));
+    if (!use_graphs || rand_ini != nullptr || src_noise != nullptr) {   // injected randomness (parity tests): plain launches
+        enqueue(w, mel, f0, rand_ini, src_noise, seed, B, T, wav, st);
+        return;
+    }
+    // production path: the ~110 launches of one forward are captured once per shape and replayed (no launch gaps at small batches)
+    w.in_mel.ensure(BT * cfg.num_mels * 4);
+    w.out_wav.ensure(BT * hop * 4);
+    if (has_src) w.in_f0.ensure(BT * 4);
+    B200_CUDA(cudaMemcpyAsync(w.in_mel.p, mel, BT * cfg.num_mels * 4, cudaMemcpyDeviceToDevice, st));
+    if (has_src) B200_CUDA(cudaMemcpyAsync(w.in_f0.p, f0, BT * 4, cudaMemcpyDeviceToDevice, st));
+    if (!w.graph[has_src]) {
+        cudaStream_t cs;
+        B200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t g = nullptr;
+        const unsigned long long before = launches;
+        B200_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        try {
+            enqueue(w, w.in_mel.as<float>(), has_src ? w.in_f0.as<float>() : nullptr, nullptr, nullptr, seed, B, T, w.out_wav.as<float>(), cs);
+        } catch (...) {
+            cudaStreamEndCapture(cs, &g);
+            if (g) cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            throw;
+        }
+        B200_CUDA(cudaStreamEndCapture(cs, &g));
+        w.graph_nodes[has_src] = launches - before;
+        launches = before;
+        g_launch_count -= w.graph_nodes[has_src];
+        B200_CUDA(cudaGraphInstantiate(&w.graph[has_src], g, 0));
+        cudaGraphDestroy(g);
+        cudaStreamDestroy(cs);
+    }
+    B200_CUDA(cudaGraphLaunch(w.graph[has_src], st));
+    launches += w.graph_nodes[has_src], g_launch_count += w.graph_nodes[has_src];
+    B200_CUDA(cudaMemcpyAsync(wav, w.out_wav.p, BT * hop * 4, cudaMemcpyDeviceToDevice, st));
+}
+
+// the launches of one forward pass on stream st (everything but the seed upload)
+void HifiganPlan::enqueue(Workspace& w, const float* mel, const float* f0, const float* rand_ini, const float* src_noise,
+                          unsigned long long seed, int B, int T, float* wav, cudaStream_t st) {
     const size_t BT = static_cast<size_t>(B) * T;
     const bool has_src = f0 != nullptr;
     if (has_src) run_source(w, f0, rand_ini, src_noise, seed, B, T, st);

@@ -264,6 +264,12 @@ __global__ void __launch_bounds__(256) pe_row_kernel(const RowArgs a) {
 struct PitchExtractorPlan::Workspace {
     int B = 0, T = 0, n_chunks = 0;
     DevBuf mel_hi, mel_lo, nonpad, Y, X, a_hi, a_lo, gn_part, gn_stats, pos;
+    DevBuf in_mel, out_pred, out_f0;   // plan-owned copies of the caller's buffers: the captured launches see fixed addresses
+    cudaGraphExec_t graph = nullptr;
+    unsigned long long graph_nodes = 0;
+    ~Workspace() {
+        if (graph) cudaGraphExecDestroy(graph);
+    }
 };
 
 static std::vector<float> take_n(const float*& p, const float* end, size_t n) {
@@ -329,6 +335,7 @@ PitchExtractorPlan::PitchExtractorPlan(const bsg_pe_config& c, const float* w, s
     ConvGemmArgs none{};
     launch_conv_gemm(256, 3, EPI_BIAS_ACT, none, nullptr);
     if (const char* np = std::getenv("BSG_PE_PAIR")) pair_mode = np[0] == '1';
+    if (const char* ng = std::getenv("BSG_PE_GRAPH")) use_graphs = ng[0] == '1';
     if (pair_mode) launch_conv_gemm(256, 3, EPI_BIAS_ACT, none, nullptr, 1);
 }
 
@@ -354,6 +361,9 @@ PitchExtractorPlan::Workspace& PitchExtractorPlan::workspace(int B, int T) {
     w->gn_part.alloc(static_cast<size_t>(B) * w->n_chunks * 16 * 2 * 8);
     w->gn_stats.alloc(static_cast<size_t>(B) * 16 * 2 * 4);
     w->pos.alloc(rows * 4);
+    w->in_mel.alloc(rows * cfg.n_mel_bins * 4);
+    w->out_pred.alloc(rows * 2 * 4);
+    w->out_f0.alloc(rows * 4);
     auto& ref = *w;
     ws[key] = std::move(w);
     return ref;
@@ -363,6 +373,42 @@ void PitchExtractorPlan::forward(const float* mel, int B, int T, float* pitch_pr
     B200_CHECK(B > 0 && T > 0, "empty batch");
     B200_CUDA(cudaSetDevice(device));
     Workspace& w = workspace(B, T);
+    if (!use_graphs) {
+        enqueue(w, mel, B, T, pitch_pred, f0, st);
+        return;
+    }
+    // the 31 launches of one forward are captured once per shape and replayed
+    const size_t rows = static_cast<size_t>(B) * T;
+    B200_CUDA(cudaMemcpyAsync(w.in_mel.p, mel, rows * cfg.n_mel_bins * 4, cudaMemcpyDeviceToDevice, st));
+    if (!w.graph) {
+        cudaStream_t cs;
+        B200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t g = nullptr;
+        const unsigned long long before = launches;
+        B200_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        try {
+            enqueue(w, w.in_mel.as<float>(), B, T, w.out_pred.as<float>(), w.out_f0.as<float>(), cs);
+        } catch (...) {
+            cudaStreamEndCapture(cs, &g);
+            if (g) cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            throw;
+        }
+        B200_CUDA(cudaStreamEndCapture(cs, &g));
+        w.graph_nodes = launches - before;
+        launches = before;
+        g_launch_count -= w.graph_nodes;
+        B200_CUDA(cudaGraphInstantiate(&w.graph, g, 0));
+        cudaGraphDestroy(g);
+        cudaStreamDestroy(cs);
+    }
+    B200_CUDA(cudaGraphLaunch(w.graph, st));
+    launches += w.graph_nodes, g_launch_count += w.graph_nodes;
+    B200_CUDA(cudaMemcpyAsync(pitch_pred, w.out_pred.p, rows * 2 * 4, cudaMemcpyDeviceToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(f0, w.out_f0.p, rows * 4, cudaMemcpyDeviceToDevice, st));
+}
+
+void PitchExtractorPlan::enqueue(Workspace& w, const float* mel, int B, int T, float* pitch_pred, float* f0, cudaStream_t st) {
     const long long rows = static_cast<long long>(B) * T;
     const int row_blocks = static_cast<int>(std::min<long long>((rows + 7) / 8, static_cast<long long>(device_sm_count()) * 8));
     auto count = [&](int n) { launches += n; g_launch_count += n; };

@@ -79,6 +79,7 @@ public:
     int device;
     int hop = 1;
     bool pair_mode = true;   // 2-CTA tiles for the >= 128-channel stages (BSG_VOC_PAIR=0: single-CTA tiles everywhere)
+    bool use_graphs = true;  // forward without injected noise replays one captured CUDA graph per shape (BSG_VOC_GRAPH=0: plain launches)
     unsigned long long launches = 0;
 
 private:
@@ -100,6 +101,8 @@ private:
     Workspace& workspace(int B, int T);
     void run_source(Workspace& w, const float* f0, const float* rand_ini, const float* src_noise, unsigned long long seed, int B, int T,
                     cudaStream_t st);
+    void enqueue(Workspace& w, const float* mel, const float* f0, const float* rand_ini, const float* src_noise, unsigned long long seed,
+                 int B, int T, float* wav, cudaStream_t st);
 
     Conv conv_pre;
     std::vector<Stage> stages;
@@ -117,6 +120,7 @@ public:
     bsg_pe_config cfg;
     int device;
     bool pair_mode = true;   // 2-CTA tiles when the batch has >= 4096 rows (BSG_PE_PAIR=0: single-CTA tiles)
+    bool use_graphs = true;  // forward replays one captured CUDA graph per shape (BSG_PE_GRAPH=0: plain launches)
     unsigned long long launches = 0;
 
 private:
@@ -131,6 +135,7 @@ private:
         DevBuf p0, p1;
     };
     Workspace& workspace(int B, int T);
+    void enqueue(Workspace& w, const float* mel, int B, int T, float* pitch_pred, float* f0, cudaStream_t st);
 
     std::vector<Layer> prenet, encoder, predictor;
     Conv prenet_out, enc_in, enc_out;

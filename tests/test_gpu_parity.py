@@ -314,3 +314,25 @@ def test_drop_in_module_surface(dev):
     with torch.no_grad():
         eref = O.diffnet_forward(sd, inp["start_noise"], torch.full((2,), 10), inp["cond"].transpose(1, 2))
     assert float((eps.cpu() - eref).abs().max()) < 4e-3    # default fp16x2 contraction, single evaluation
+
+
+def test_vocoder_graph_replay_matches_plain_launches(voc, dev, monkeypatch):
+    """Production path (no injected noise): one captured CUDA graph per shape, replayed with new inputs through the plan-owned
+    staging buffers -- bit-identical to the plain launches (BSG_VOC_GRAPH=0), with and without the NSF branch."""
+    from bisinger_b200.vocoder import B200HifiGanGenerator
+    vsd, gen = voc
+    monkeypatch.setenv("BSG_VOC_GRAPH", "0")
+    plain = B200HifiGanGenerator(synth.HIFIGAN_CONFIG)
+    plain.load_folded_state_dict(vsd, strict=True)
+    plain.build_plan(dev)
+    for seed in (201, 202, 203):       # first call captures, the next replay with other inputs
+        vin = synth.vocoder_inputs(seed, 2, 70)
+        mel, f0 = vin["mel"].to(dev), vin["f0"].to(dev)
+        a, b = gen(mel, f0, seed=seed), plain(mel, f0, seed=seed)
+        assert torch.equal(a, b)
+        assert torch.equal(gen(mel, None, seed=seed), plain(mel, None, seed=seed))
+    # the replay leaves the injected-noise path intact
+    vin = synth.vocoder_inputs(204, 2, 70)
+    w1 = gen(vin["mel"].to(dev), vin["f0"].to(dev), vin["rand_ini"].to(dev), vin["src_noise"].to(dev))
+    w2 = plain(vin["mel"].to(dev), vin["f0"].to(dev), vin["rand_ini"].to(dev), vin["src_noise"].to(dev))
+    assert torch.equal(w1, w2)

@@ -163,6 +163,7 @@ def test_gpu_single_cta_tiles_and_determinism(dev, monkeypatch):
     b = pe(mel.to(dev))
     assert torch.equal(a["pitch_pred"], b["pitch_pred"]) and torch.equal(a["f0_denorm_pred"], b["f0_denorm_pred"])
     monkeypatch.setenv("BSG_PE_PAIR", "0")
+    monkeypatch.setenv("BSG_PE_GRAPH", "0")
     sd, pe1 = _pe(dev)
     c = pe1(mel.to(dev))
     with torch.no_grad():
@@ -192,3 +193,16 @@ def test_gpu_mel_to_wav_chain(dev):
         pytest.skip("a voicing logit within rounding of 0 flipped; the chain comparison needs identical decisions")
     wav = gen(vin["mel"].to(dev), f0, vin["rand_ini"].to(dev), vin["src_noise"].to(dev)).cpu()
     assert O.snr_db(wref, wav) >= 40.0
+
+
+@pytest.mark.gpu
+def test_gpu_graph_replay_matches_plain_launches(dev, monkeypatch):
+    """forward replays one captured CUDA graph per shape through plan-owned staging buffers: bit-identical to plain launches
+    (BSG_PE_GRAPH=0), also on the second and third call with other inputs."""
+    sd, pe = _pe(dev)
+    monkeypatch.setenv("BSG_PE_GRAPH", "0")
+    sd, plain = _pe(dev)
+    for seed in (301, 302, 303):
+        mel = synth.pe_inputs(seed, 2, 150, pad_tail=seed % 7).to(dev)
+        a, b = pe(mel), plain(mel)
+        assert torch.equal(a["pitch_pred"], b["pitch_pred"]) and torch.equal(a["f0_denorm_pred"], b["f0_denorm_pred"])
