@@ -68,7 +68,7 @@ def _rnd_w(w: Tensor, operand: Optional[str]) -> Tensor:
 def sinusoidal_pos_emb(t: Tensor, dim: int) -> Tensor:
     """usr/diff/net.py:32-44 -- emb = [sin(t*w_j), cos(t*w_j)], w_j = exp(-j ln(1e4)/(dim/2-1))."""
     half = dim // 2
-    w = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    w = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1))).to(t.device)
     e = t.to(torch.float32)[:, None] * w[None, :]
     return torch.cat((e.sin(), e.cos()), dim=-1)
 
@@ -195,7 +195,7 @@ def p_sample(p: Dict[str, Tensor], sched: Dict[str, Tensor], x: Tensor, t: int, 
     """usr/diff/shallow_diffusion_tts.py:149-166 (+ :134-147).  One ancestral step with
     injected noise z (the reference draws randn(x.shape) every step, also at t == 0)."""
     B = x.shape[0]
-    tt = torch.full((B,), t, dtype=torch.long)
+    tt = torch.full((B,), t, dtype=torch.long, device=x.device)
     eps = diffnet_forward(p, x, tt, cond, dilation_cycle, operand)
     x_recon = sched["sqrt_recip_alphas_cumprod"][t] * x - sched["sqrt_recipm1_alphas_cumprod"][t] * eps
     if clip_denoised:
@@ -265,10 +265,10 @@ def diffusion_infer_plms(p: Dict[str, Tensor], sched: Dict[str, Tensor], spec_mi
     B = x.shape[0]
     noise_list = []                                                      # deque(maxlen=4), :259
     for t in reversed(range(0, K_step, interval)):
-        noise_pred = diffnet_forward(p, x, torch.full((B,), t, dtype=torch.long), cond, dilation_cycle, operand)
+        noise_pred = diffnet_forward(p, x, torch.full((B,), t, dtype=torch.long, device=x.device), cond, dilation_cycle, operand)
         if len(noise_list) == 0:                                         # :188-191
             x_pred = plms_x_pred(sched, x, noise_pred, t, interval)
-            noise_pred_prev = diffnet_forward(p, x_pred, torch.full((B,), max(t - interval, 0), dtype=torch.long), cond,
+            noise_pred_prev = diffnet_forward(p, x_pred, torch.full((B,), max(t - interval, 0), dtype=torch.long, device=x.device), cond,
                                               dilation_cycle, operand)
             prime = (noise_pred + noise_pred_prev) / 2
         elif len(noise_list) == 1:                                       # :192-193
@@ -298,7 +298,7 @@ def sinegen(f0_up: Tensor, rand_ini: Tensor, noise: Tensor, sampling_rate: int, 
     returns (sine_waves [B,L,dim], uv [B,L,1])
     """
     dim = harmonic_num + 1
-    mult = torch.arange(1, dim + 1, dtype=torch.float32)
+    mult = torch.arange(1, dim + 1, dtype=torch.float32).to(f0_up.device)
     f0_buf = f0_up[:, :, :1] * mult[None, None, :]                      # :112-118
     rad = (f0_buf / sampling_rate) % 1                                   # :51
     ri = rand_ini.clone()

@@ -336,3 +336,23 @@ def test_vocoder_graph_replay_matches_plain_launches(voc, dev, monkeypatch):
     w1 = gen(vin["mel"].to(dev), vin["f0"].to(dev), vin["rand_ini"].to(dev), vin["src_noise"].to(dev))
     w2 = plain(vin["mel"].to(dev), vin["f0"].to(dev), vin["rand_ini"].to(dev), vin["src_noise"].to(dev))
     assert torch.equal(w1, w2)
+
+
+def test_batch_rows_are_independent(diff, voc, dev):
+    """What the replica sharding rests on: an utterance's result does not depend on which batch it is in.
+    Sampler (injected noise) and vocoder (injected source noise): a batch of 3 against the three single-utterance calls."""
+    sd, sched, plan = diff
+    vsd, gen = voc
+    B, T = 3, 140
+    inp = synth.kernel_inputs(401, B, T, K_STEP)
+    cond, fs2, sn, zn = (inp[k].to(dev) for k in ("cond", "fs2_mel", "start_noise", "step_noise"))
+    mel = plan.sample(cond, fs2, sn, zn)
+    for b in range(B):
+        one = plan.sample(cond[b:b + 1].contiguous(), fs2[b:b + 1].contiguous(), sn[b:b + 1].contiguous(), zn[:, b:b + 1].contiguous())
+        assert float((one[0] - mel[b]).abs().max()) <= 1e-5
+    vin = synth.vocoder_inputs(402, B, T)
+    m, f0, ri, nz = (vin[k].to(dev) for k in ("mel", "f0", "rand_ini", "src_noise"))
+    wav = gen(m, f0, ri, nz)
+    for b in range(B):
+        one = gen(m[b:b + 1].contiguous(), f0[b:b + 1].contiguous(), ri[b:b + 1].contiguous(), nz[b:b + 1].contiguous())
+        assert float((one[0] - wav[b]).abs().max()) <= 1e-6
