@@ -93,9 +93,8 @@ class ClockSampler:
 
 
 def build_models(dev, precision):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import synth   # seeded random-init weights of the named architecture (no checkpoints reachable)
     import torch
+    from bisinger_b200 import synthetic as synth   # seeded random-init weights of the named architecture (no checkpoints reachable)
     from bisinger_b200 import B200DiffNet, B200GaussianDiffusion
     from bisinger_b200.diffusion import linear_beta_schedule
     from bisinger_b200.vocoder import B200HifiGanGenerator

@@ -6,8 +6,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import synth  # noqa: E402  (synthetic weights only)
+from bisinger_b200 import synthetic as synth  # noqa: E402
 from bisinger_b200 import launch_count  # noqa: E402
 from bisinger_b200.pitch import B200PitchExtractor  # noqa: E402
 

@@ -10,8 +10,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import synth  # noqa: E402
+from bisinger_b200 import synthetic as synth  # noqa: E402
 from bisinger_b200 import B200DiffNet, DiffusionPlan  # noqa: E402
 from bisinger_b200.diffusion import _schedule_buffers, linear_beta_schedule  # noqa: E402
 from bisinger_b200.pitch import B200PitchExtractor  # noqa: E402
