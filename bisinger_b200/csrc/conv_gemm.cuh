@@ -21,7 +21,7 @@
 // TERMS == 2 is the "fp16x2" contraction: activations are ONE fp16 operand, weights are carried as fp16 hi/lo
 // (pre-scaled by a power of two so that lo stays out of the subnormal range; EpiParams::acc_scale undoes it) and each
 // k-block issues A*W_hi + A*W_lo.  Weight rounding is the systematic error of the 100-step sampler; activation rounding
-// at 11 significant bits is not (tools/precision_study.py), so this mode meets the tolerance with 2/3 of
+// at 11 significant bits is not (tests/tools/precision_study.py), so this mode meets the tolerance with 2/3 of
 // the MMAs and half the activation bytes of bf16x3.
 //
 // Warp roles (320 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer (one thread),
@@ -111,7 +111,7 @@ struct ConvGemmArgs {
                            //    memory for all its tiles (single-CTA tiles only).  Small-channel convolutions issue so little MMA work
                            //    per weight tile that streaming the weights per tile left the kernel bound by TMA round trips
                            //    (~150 cycles per MMA whatever N: profiles/r01_i)
-    unsigned long long* trace;   // optional [grid][16] cycle counters of the three roles (tools/gpu_probe.py tracetarget), or null
+    unsigned long long* trace;   // optional [grid][16] cycle counters of the three roles (tests/tools/gpu_probe.py tracetarget), or null
 };
 
 // mbar_wait that adds the cycles spent waiting to *acc when tracing

@@ -13,7 +13,7 @@
 // of the step is one K = L*C GEMM over that matrix) and come back through L2 by TMA; the epilogue warps order their stores
 // before the async-proxy reads with fence.proxy.async + an mbarrier the TMA producer waits on.
 //
-// Contraction (fp16x2 mode, tools/precision_study.py): activations are ONE fp16 operand; the weights are fp16(W 2^p) plus a
+// Contraction (fp16x2 mode, tests/tools/precision_study.py): activations are ONE fp16 operand; the weights are fp16(W 2^p) plus a
 // correction.  In the gate GEMM (3/4 of the FLOPs) the correction term runs on the fp8 pipe at twice the rate:
 //     acc += fp16(A) * fp16(W_hi)  [kind::f16, K = 16]   +   e4m3(A) * e5m2(W 2^p - W_hi)  [kind::f8f6f4, K = 32]
 // into the same fp32 accumulator (hardware-checked: csrc/experiments.cu bsg_experiment_f8).  The correction only has to be
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                 if (j + 1 < n_ops && layer_op(j + 1, cnt).kind == 1 && layer_op(j + 1, cnt).n == op.n) publish_z();
             } else {
                 // ---- residual: x <- (x + W_res z + b) / sqrt(2)  (net.py:76-78); fp16 / e4m3 of (x + d_next) feed the next layer's conv
-                // The residual stream is carried only as the fp16 conv input: x = fp16(x + d_cur) - d_cur (tools/precision_study.py
+                // The residual stream is carried only as the fp16 conv input: x = fp16(x + d_cur) - d_cur (tests/tools/precision_study.py
                 // "state fp16": 1.5-2.2e-3 vs 1.2-1.3e-3 max mel error).  No fp32 x is read or written: the epilogue streams the conv
                 // input once more (32-channel boxes) and stores only the next layer's fp16 / e4m3 conv input.
                 auto res_chunk = [&](int c, const uint32_t (&v)[32]) {   // 32 channels

@@ -1,7 +1,7 @@
 """GPU bring-up probe: runs each stage in its own subprocess (a kernel trap poisons the CUDA context) with a
-timeout, prints diagnostics instead of asserting.  Usage: python tools/gpu_probe.py [stage ...]"""
+timeout, prints diagnostics instead of asserting.  Usage: python tests/tools/gpu_probe.py [stage ...]"""
 import os, subprocess, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 

@@ -1,7 +1,7 @@
 """CPU study of operand-precision schemes for the 100-step sampler (emulation on the oracle, test infrastructure).
 Each scheme says how the operands of the contractions are represented; accumulation is fp32 (emulated in fp32/fp64)."""
 import math, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch, torch.nn.functional as F
 import svs_oracle as O, synth

@@ -10,6 +10,6 @@ if [ "$1" = "ncu" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 4500 -c 500 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 4309 -c 4 -o gpurun_out/prof_layer \
-      python tools/gpu_probe.py --run proftarget > gpurun_out/ncu_full.log 2>&1
+      python tests/tools/gpu_probe.py --run proftarget > gpurun_out/ncu_full.log 2>&1
   ls -la gpurun_out
 fi

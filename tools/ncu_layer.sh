@@ -3,6 +3,6 @@
 mkdir -p gpurun_out
 for w in ${BSG_KERNELS:-0 1 2}; do
   BSG_WHICH=$w timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 3 -c 2 -f -o gpurun_out/prof_k$w \
-      python tools/gpu_probe.py --run proftarget > gpurun_out/ncu_k$w.log 2>&1
+      python tests/tools/gpu_probe.py --run proftarget > gpurun_out/ncu_k$w.log 2>&1
 done
 ls -la gpurun_out/*.ncu-rep
