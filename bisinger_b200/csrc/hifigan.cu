@@ -39,25 +39,48 @@ __global__ void mel_prep_kernel(const float* __restrict__ mel, int B, int M, int
 // Phase at the start of each frame.  source.py:51-74: rad = (f0*h/sr) % 1 per sample, rad[0] += rand_ini, phase = cumsum(rad)
 // (the reference subtracts 1 at every wrap only to keep the fp32 running sum small; sin(2*pi*x) is invariant to it).
 // f0 is constant over a frame (nearest up-sampling, hifigan.py:113,147), so the cumulative phase at sample i of frame t is
-// P[t] + (i+1)*rad[t]; P is accumulated here in fp64 and stored modulo 1.
+// P[t] + (i+1)*rad[t].  P is kept as a 64-bit FIXED-POINT fraction of a turn (2^64 = one turn): rad is an fp32 number in [0,1), so
+// rad * 2^64 is an exact integer, the running sum is exact, and the "modulo 1" is the wrap of unsigned arithmetic -- no rounding
+// accumulates over a 60 s segment, and the scan needs no fp64 (whose latency made the serial scan 330 us).
+__device__ __forceinline__ unsigned long long turn_fixed(float r) {   // r in [0,1) -> r * 2^64, exact, integer only
+    const unsigned int u = __float_as_uint(r);
+    const int e = static_cast<int>((u >> 23) & 0xffu);
+    const unsigned long long m = (u & 0x7fffffu) | (e ? 0x800000u : 0u);
+    const int sh = (e ? e : 1) - 127 + 41;            // r = m * 2^(e-150)  =>  r * 2^64 = m * 2^(e-86); e <= 126 => sh <= 40
+    return sh >= 0 ? (m << sh) : (sh > -64 ? (m >> -sh) : 0ull);
+}
+__device__ __forceinline__ float rad_of(float f0, int h, float sr) {
+    const float r = f0 * static_cast<float>(h + 1) / sr;
+    return r - floorf(r);
+}
+// One warp per (utterance, harmonic): 32 frames per iteration, inclusive shuffle scan of the 64-bit increments plus a running carry.
+// Integer addition is associative, so the result is bit-identical to a serial scan.
 __global__ void nsf_phase_kernel(const float* __restrict__ f0, const float* __restrict__ rand_ini, int B, int T, int hop, int dim,
-                                 float sr, double* __restrict__ phase0) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+                                 float sr, unsigned long long* __restrict__ phase0) {
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (idx >= B * dim) return;
     const int b = idx / dim, h = idx % dim;
-    double p = (h == 0 || rand_ini == nullptr) ? 0.0 : static_cast<double>(rand_ini[b * dim + h]);   // rand_ini[:,0] = 0 (:56)
-    for (int t = 0; t < T; ++t) {
-        phase0[(static_cast<long long>(b) * T + t) * dim + h] = p;
-        const float fh = f0[static_cast<long long>(b) * T + t] * static_cast<float>(h + 1);
-        float r = fh / sr;
-        r = r - floorf(r);
-        p += static_cast<double>(hop) * static_cast<double>(r);
-        p -= floor(p);
+    float ri = (h == 0 || rand_ini == nullptr) ? 0.0f : rand_ini[b * dim + h];   // rand_ini[:,0] = 0 (:56)
+    ri = ri - floorf(ri);
+    unsigned long long carry = turn_fixed(ri);
+    const float* f = f0 + static_cast<long long>(b) * T;
+    unsigned long long* out = phase0 + static_cast<long long>(b) * T * dim + h;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        const int t = t0 + lane;
+        const unsigned long long inc = t < T ? static_cast<unsigned long long>(hop) * turn_fixed(rad_of(__ldg(f + t), h, sr)) : 0ull;
+        unsigned long long v = inc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        if (t < T) out[static_cast<long long>(t) * dim] = carry + v - inc;   // phase at the START of frame t
+        carry += __shfl_sync(0xffffffffu, v, 31);
     }
 }
 
 // har_source[b][l] = tanh( Linear_9->1( sine*uv + noise_amp*noise ) )   source.py:121-137,394-395
-__global__ void nsf_source_kernel(const float* __restrict__ f0, const double* __restrict__ phase0, const float* __restrict__ noise,
+__global__ void nsf_source_kernel(const float* __restrict__ f0, const unsigned long long* __restrict__ phase0, const float* __restrict__ noise,
                                   const unsigned long long* __restrict__ seed_ptr, const float* __restrict__ lin, int B, int T, int hop,
                                   int dim, float sr, float* __restrict__ har) {
     const long long L = static_cast<long long>(T) * hop;
@@ -70,15 +93,21 @@ __global__ void nsf_source_kernel(const float* __restrict__ f0, const double* __
     const float uv = f > 0.0f ? 1.0f : 0.0f;                      // voiced_threshold = 0 (:38-43)
     const float namp = uv * 0.003f + (1.0f - uv) * 0.1f / 3.0f;   // noise_std, sine_amp/3 (:131)
     float acc = lin[dim];                                         // l_linear bias
+    const unsigned long long seed = noise ? 0ull : __ldg(seed_ptr);
+    float4 zq = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int h = 0; h < dim; ++h) {
-        const float fh = f * static_cast<float>(h + 1);
-        float r = fh / sr;
-        r = r - floorf(r);
-        double ph = phase0[(static_cast<long long>(b) * T + t) * dim + h] + static_cast<double>(i + 1) * static_cast<double>(r);
-        ph -= floor(ph);
-        const float sine = sinf(static_cast<float>(ph) * 2.0f * 3.14159265358979323846f) * 0.1f;   // sine_amp (:121)
-        const long long ni = (static_cast<long long>(b) * L + l) * dim + h;
-        const float z = noise ? noise[ni] : philox_normal(__ldg(seed_ptr), 0x4E5Fu, static_cast<uint64_t>(ni));
+        // phase of this sample: P[t] + (i+1)*rad, wrapping = modulo one turn; the top 24 bits are all an fp32 phase can hold
+        const unsigned long long ph = phase0[(static_cast<long long>(b) * T + t) * dim + h] +
+                                      static_cast<unsigned long long>(i + 1) * turn_fixed(rad_of(f, h, sr));
+        const float phf = static_cast<float>(static_cast<unsigned int>(ph >> 40)) * 5.9604644775390625e-08f;   // 2^-24
+        const float sine = sinf(phf * 2.0f * 3.14159265358979323846f) * 0.1f;   // sine_amp (:121)
+        float z;
+        if (noise) {
+            z = noise[(static_cast<long long>(b) * L + l) * dim + h];
+        } else {   // four normals per Philox call: counter = (sample, h / 4)
+            if ((h & 3) == 0) zq = philox_normal4(seed, 0x4E5Fu + static_cast<unsigned>(h >> 2), static_cast<uint64_t>(g));
+            z = (h & 3) == 0 ? zq.x : ((h & 3) == 1 ? zq.y : ((h & 3) == 2 ? zq.z : zq.w));
+        }
         acc = fmaf(lin[h], sine * uv + namp * z, acc);
     }
     har[g] = tanhf(acc);
@@ -144,6 +173,118 @@ __global__ void __launch_bounds__(256) noise_branch_kernel(const float* __restri
             const float xv = x[row * C + c] + v[j];
             x[row * C + c] = xv;
             act[row * act_pitch + c] = __float2bfloat16_rn(xv > 0.0f ? xv : xv * kLrelu);
+        }
+    }
+}
+
+// Same operation, laid out for memory-level parallelism: a row's C channels are spread over LPR = min(32, C/4) lanes as float4s, so a warp
+// works on 32/LPR rows at once (C = 32: four rows per warp), two such row groups per loop iteration with all their loads issued before
+// the arithmetic; LayerNorm reductions are shuffles within the LPR lanes of a row.  Needs ksz <= LPR (true for every stage of the hop-128
+// generator: k = 32, 8, 4, 1 at C = 256, 128, 64, 32); the host falls back to the kernel above otherwise.
+template <int C>
+__global__ void __launch_bounds__(256) noise_branch_v2_kernel(const float* __restrict__ har, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, int B, long long Lout, long long Lhar, int ksz,
+                                                              int stride, int pad, int has_source, float* __restrict__ x,
+                                                              __nv_bfloat16* __restrict__ act, int act_pitch) {
+    constexpr int LPR = C >= 128 ? 32 : C / 4;   // lanes per row
+    constexpr int RPW = 32 / LPR;                // rows per warp and group
+    constexpr int V = C / (LPR * 4);             // float4s per lane
+    constexpr int U = C >= 512 ? 2 : 4;          // row groups in flight; a weight float4 read from shared memory serves all of them
+    extern __shared__ float wsm[];   // [ksz][C] then bias [C]
+    if (has_source) {
+        for (int i = threadIdx.x; i < ksz * C; i += blockDim.x) wsm[(i % ksz) * C + i / ksz] = w[i];   // w is [C][ksz]
+        for (int i = threadIdx.x; i < C; i += blockDim.x) wsm[ksz * C + i] = bias[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, sub = lane % LPR, rsub = lane / LPR;
+    const long long warp_g = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const long long rows = static_cast<long long>(B) * Lout;
+    for (long long base = warp_g * (RPW * U); base < rows; base += n_warps * (RPW * U)) {
+        float4 xv[U][V];
+        float hs[U];
+        long long row[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            row[u] = base + u * RPW + rsub;
+            const bool ok = row[u] < rows;
+            hs[u] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                xv[u][j] = ok ? *reinterpret_cast<const float4*>(x + row[u] * C + (j * LPR + sub) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_source && ok && sub < ksz) {
+                const int b = static_cast<int>(row[u] / Lout);
+                const long long hl = (row[u] % Lout) * stride - pad + sub;
+                if (hl >= 0 && hl < Lhar) hs[u] = har[static_cast<long long>(b) * Lhar + hl];
+            }
+        }
+        float v[U][V][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[u][j][0] = v[u][j][1] = v[u][j][2] = v[u][j][3] = 0.0f;
+        if (has_source) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(wsm + ksz * C + (j * LPR + sub) * 4);
+#pragma unroll
+                for (int u = 0; u < U; ++u) { v[u][j][0] = bb.x; v[u][j][1] = bb.y; v[u][j][2] = bb.z; v[u][j][3] = bb.w; }
+            }
+            for (int k = 0; k < ksz; ++k) {
+                float hk[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) hk[u] = __shfl_sync(0xffffffffu, hs[u], k, LPR);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float4 ww = *reinterpret_cast<const float4*>(wsm + k * C + (j * LPR + sub) * 4);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        v[u][j][0] = fmaf(ww.x, hk[u], v[u][j][0]); v[u][j][1] = fmaf(ww.y, hk[u], v[u][j][1]);
+                        v[u][j][2] = fmaf(ww.z, hk[u], v[u][j][2]); v[u][j][3] = fmaf(ww.w, hk[u], v[u][j][3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float sum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { v[u][j][q] = fmaxf(v[u][j][q], 0.0f); sum += v[u][j][q]; }
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float mean = sum / static_cast<float>(C);
+                float qq = 0.0f;
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { v[u][j][q] -= mean; qq += v[u][j][q] * v[u][j][q]; }
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+                const float rstd = rsqrtf(qq / static_cast<float>(C) + 1e-5f);
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[u][j][q] *= rstd;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (row[u] < rows) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const int c = (j * LPR + sub) * 4;
+                    const float4 o4 = make_float4(xv[u][j].x + v[u][j][0], xv[u][j].y + v[u][j][1], xv[u][j].z + v[u][j][2],
+                                                  xv[u][j].w + v[u][j][3]);
+                    *reinterpret_cast<float4*>(x + row[u] * C + c) = o4;
+                    const __nv_bfloat162 a0 = __floats2bfloat162_rn(o4.x > 0.0f ? o4.x : o4.x * kLrelu, o4.y > 0.0f ? o4.y : o4.y * kLrelu);
+                    const __nv_bfloat162 a1 = __floats2bfloat162_rn(o4.z > 0.0f ? o4.z : o4.z * kLrelu, o4.w > 0.0f ? o4.w : o4.w * kLrelu);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&a0);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&a1);
+                    *reinterpret_cast<uint2*>(act + row[u] * act_pitch + c) = pk;
+                }
+            }
         }
     }
 }
@@ -338,6 +479,7 @@ HifiganPlan::HifiganPlan(const bsg_hifigan_config& c, const float* w, size_t n_w
     for (int nt : {256, 128, 64, 32}) launch_conv_gemm(nt, 1, EPI_BIAS_ACT, none, nullptr);
     if (const char* np = std::getenv("BSG_VOC_PAIR")) pair_mode = np[0] == '1';
     if (const char* ng = std::getenv("BSG_VOC_GRAPH")) use_graphs = ng[0] == '1';
+    if (const char* nv = std::getenv("BSG_VOC_NOISE_V2")) noise_v2 = nv[0] == '1';
     if (pair_mode) for (int nt : {256, 128}) launch_conv_gemm(nt, 1, EPI_BIAS_ACT, none, nullptr, 1);
 }
 
@@ -382,10 +524,10 @@ void HifiganPlan::run_source(Workspace& w, const float* f0, const float* rand_in
                              int T, cudaStream_t st) {
     const int dim = cfg.harmonic_num + 1;
     B200_CHECK(cfg.use_pitch_embed, "this generator was built without the NSF source (use_pitch_embed = 0)");
-    nsf_phase_kernel<<<(B * dim + 63) / 64, 64, 0, st>>>(f0, rand_ini, B, T, hop, dim, static_cast<float>(cfg.audio_sample_rate),
-                                                         w.phase0.as<double>());
+    nsf_phase_kernel<<<(B * dim * 32 + 255) / 256, 256, 0, st>>>(f0, rand_ini, B, T, hop, dim, static_cast<float>(cfg.audio_sample_rate),
+                                                         w.phase0.as<unsigned long long>());
     const long long n = static_cast<long long>(B) * T * hop;
-    nsf_source_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(f0, w.phase0.as<double>(), src_noise,
+    nsf_source_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(f0, w.phase0.as<unsigned long long>(), src_noise,
                                                                               d_seed.as<unsigned long long>(), src_lin.as<float>(), B, T,
                                                                               hop, dim, static_cast<float>(cfg.audio_sample_rate),
                                                                               w.har.as<float>());
@@ -521,9 +663,17 @@ void HifiganPlan::enqueue(Workspace& w, const float* mel, const float* f0, const
             const float* nw = has_src ? s.noise_w.as<float>() : nullptr;
             const float* nb = has_src ? s.noise_b.as<float>() : nullptr;
             const long long Lhar = static_cast<long long>(T) * hop;
-#define B200_NOISE(CPL)                                                                                                              \
-    noise_branch_kernel<CPL><<<blocks, 256, sm_bytes, st>>>(w.har.as<float>(), nw, nb, B, Lout, Lhar, s.noise_k, s.noise_stride, \
-                                                           s.noise_pad, has_src ? 1 : 0, w.X0.as<float>(), A0, Cp)
+            const int lpr = C >= 128 ? 32 : C / 4;
+            const bool v2 = noise_v2 && s.noise_k <= lpr && Cp % 4 == 0 && C <= 512;
+#define B200_NOISE(CPL)                                                                                                                 \
+    do {                                                                                                                                \
+        if (v2)                                                                                                                         \
+            noise_branch_v2_kernel<CPL * 32><<<blocks, 256, sm_bytes, st>>>(w.har.as<float>(), nw, nb, B, Lout, Lhar, s.noise_k,        \
+                                                                           s.noise_stride, s.noise_pad, has_src ? 1 : 0, w.X0.as<float>(), A0, Cp); \
+        else                                                                                                                            \
+            noise_branch_kernel<CPL><<<blocks, 256, sm_bytes, st>>>(w.har.as<float>(), nw, nb, B, Lout, Lhar, s.noise_k, s.noise_stride, \
+                                                                   s.noise_pad, has_src ? 1 : 0, w.X0.as<float>(), A0, Cp);              \
+    } while (0)
             switch (C / 32) {
                 case 1: B200_NOISE(1); break;
                 case 2: B200_NOISE(2); break;
