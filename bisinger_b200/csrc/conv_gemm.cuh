@@ -265,6 +265,15 @@ __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpre
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
 
+// How the two groups of four epilogue warps share the work: 2 = they split the columns of every tile, 1 = each group takes whole tiles
+// (every other tile; the posterior epilogue alternates 16-channel chunks instead).  Narrow tiles are bound by the latency chain of an
+// epilogue, not by its width, so two tiles in flight beat two half-width passes over one -- for N = 32; for N = 64 the split is faster
+// (vocoder at cfg3: 56.3 ms vs 58.0 ms with -DB200_ALT_MAX_N=64, profiles/r01_m_vocoder_small_kernels.txt).
+#ifndef B200_ALT_MAX_N
+#define B200_ALT_MAX_N 32
+#endif
+__host__ __device__ constexpr int epi_col_split(int n_tile) { return (n_tile % 64 == 0 && n_tile > B200_ALT_MAX_N) ? 2 : 1; }
+
 // BIAS_ACT flags (HiFi-GAN epilogue)
 enum : int {
     BA_ADD_RES = 1,      // y += aux0[row][n]            (ResBlock1 residual, hifigan.py:60)
@@ -287,7 +296,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, int Lrows, uint
     const int rows_left = Lrows - t_warp - lp.r0;                          // row pair rp is valid iff 2*rp < rows_left
 #define B200_ROW_OK(rp) (FULL || 2 * (rp) < rows_left)
     // column range of this warp
-    constexpr int kSplit = (N_TILE % 64 == 0) ? 2 : 1;
+    constexpr int kSplit = epi_col_split(N_TILE);
     constexpr int kColsPerGrp = N_TILE / kSplit;
     // kSplit == 1 (narrow tiles): the two warp groups do not split the columns, they alternate TILES (see the kernel's
     // epilogue loop); the posterior epilogue alternates 16-channel chunks instead
@@ -585,7 +594,7 @@ __device__ __forceinline__ void prefetch_rmw_tile(const ConvGemmArgs& args, int 
     const int m = tile / args.n_tiles_n;
     const int b = m / args.tiles_per_batch;
     const int t0 = (m % args.tiles_per_batch) * tile_rows + row_in_tile;
-    constexpr int kSplit = (N_TILE % 64 == 0) ? 2 : 1;
+    constexpr int kSplit = epi_col_split(N_TILE);
     constexpr int kCols = N_TILE / kSplit;
     constexpr int kLinesPerRow = (kCols * 4 + 127) / 128;
     const float* src0 = nullptr;
@@ -676,7 +685,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     constexpr int kTileRows = PAIR ? 2 * kTileM : kTileM;
     // Narrow tiles (N_TILE = 32: the last HiFi-GAN stage) are bound by the epilogue's latency chain, not by its width: instead of
     // idling, the second group of four epilogue warps takes every other tile (accumulator buffer = tile parity = group).
-    constexpr bool kAltTiles = (N_TILE % 64 != 0) && EPI != EPI_POSTERIOR;
+    constexpr bool kAltTiles = epi_col_split(N_TILE) == 1 && EPI != EPI_POSTERIOR;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
