@@ -282,6 +282,7 @@ enum : int {
     BA_ACCUM_INIT = 8,   // with BA_ACCUM_F32B: '=' instead of '+='
     BA_WRITE_ACT = 16,   // out_hi[row][n] = bf16(lrelu(y, c1))
     BA_ACT_FROM_B = 32,  // the bf16 activation is taken from the accumulated f32_b value instead of y
+    BA_ROWS = 64,        // write-only epilogues (no BA_ADD_RES / BA_ACCUM_F32B) keep the accumulator's row-per-thread ownership: see below
 };
 
 // b: batch index, t_warp: first row (within the batch) of this warp's 32 accumulator lanes, grp: column group of the
@@ -542,6 +543,69 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, int Lrows, uint
             }
         }
     } else if constexpr (EPI == EPI_BIAS_ACT) {
+        if ((e.flags & BA_ROWS) && !(e.flags & (BA_ADD_RES | BA_ACCUM_F32B))) {
+            // Write-only epilogue (first conv of every ResBlock iteration, conv_pre, transposed-conv phases, PitchExtractor GEMMs): nothing is
+            // read from global memory, so the shared-memory transposition that buys coalesced READS is pure overhead (~30 thread instructions
+            // per output element; the narrow vocoder stages were bound by it, profiles/r01_l).  Each thread keeps the accumulator row that
+            // tcgen05.ld hands it (32 consecutive columns) and writes full 32-byte sectors with 256-bit stores: ~6 instructions per element.
+            const bool ok = FULL || lane < Lrows - t_warp;
+            const long long row = row_w + lane;
+#pragma unroll 1
+            for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {
+                float v[32];
+                ld_acc32(tacc + c, v, sc);
+                const int n = n_tile * N_TILE + c;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + n) + j);
+                    v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                }
+                if (e.flags & BA_WRITE_F32) {
+                    float* dst = e.f32_a + row * e.out_pitch + e.out_col0 + n;
+                    if (ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t q[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) q[i] = __float_as_uint(v[8 * j + i]);
+                            stg256(dst + 8 * j, q);
+                        }
+                    }
+                }
+                if (e.flags & BA_WRITE_ACT) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float a = v[2 * i] > 0.0f ? v[2 * i] : v[2 * i] * e.c1;
+                        const float bq = v[2 * i + 1] > 0.0f ? v[2 * i + 1] : v[2 * i + 1] * e.c1;
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(a, bq);
+                        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hi[i] << 16), bq - __uint_as_float(hi[i] & 0xffff0000u));
+                        lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    if (ok) {
+                        __nv_bfloat16* dh = e.out_hi + row * e.act_pitch + n;
+                        uint32_t q[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) q[i] = hi[i];
+                        stg256(dh, q);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) q[i] = hi[8 + i];
+                        stg256(dh + 16, q);
+                        if (e.out_lo != nullptr) {
+                            __nv_bfloat16* dl = e.out_lo + row * e.act_pitch + n;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) q[i] = lo[i];
+                            stg256(dl, q);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) q[i] = lo[8 + i];
+                            stg256(dl + 16, q);
+                        }
+                    }
+                }
+            }
+            return;
+        }
         const long long st = 2LL * e.out_pitch, sta = 2LL * e.act_pitch;
 #pragma unroll 1
         for (int c = c_begin; c < c_begin + kColsPerGrp; c += 32) {

@@ -167,11 +167,6 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
     return v;
 }
-__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
-                 "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
     return *reinterpret_cast<const uint32_t*>(&h);

@@ -336,6 +336,7 @@ PitchExtractorPlan::PitchExtractorPlan(const bsg_pe_config& c, const float* w, s
     launch_conv_gemm(256, 3, EPI_BIAS_ACT, none, nullptr);
     if (const char* np = std::getenv("BSG_PE_PAIR")) pair_mode = np[0] == '1';
     if (const char* ng = std::getenv("BSG_PE_GRAPH")) use_graphs = ng[0] == '1';
+    if (const char* nr = std::getenv("BSG_ROWS_EPI")) rows_epi = nr[0] == '1';
     if (pair_mode) launch_conv_gemm(256, 3, EPI_BIAS_ACT, none, nullptr, 1);
 }
 
@@ -437,6 +438,7 @@ void PitchExtractorPlan::enqueue(Workspace& w, const float* mel, int B, int T, f
             a.epi.out_hi = w.a_hi.as<__nv_bfloat16>();
             a.epi.out_lo = w.a_lo.as<__nv_bfloat16>();
         }
+        if (rows_epi) a.epi.flags |= BA_ROWS;   // write-only epilogues, 256-channel rows: row-per-thread 256-bit stores
         launch_conv_gemm(nt, 3, EPI_BIAS_ACT, a, st, pair);
         count(1);
     };

@@ -81,6 +81,7 @@ public:
     bool pair_mode = true;   // 2-CTA tiles for the >= 128-channel stages (BSG_VOC_PAIR=0: single-CTA tiles everywhere)
     bool use_graphs = true;  // forward without injected noise replays one captured CUDA graph per shape (BSG_VOC_GRAPH=0: plain launches)
     bool noise_v2 = true;    // row-group layout of the noise-branch kernel (BSG_VOC_NOISE_V2=0: one warp per row)
+    bool rows_epi = true;    // row-per-thread write-only epilogue with 256-bit stores (BSG_ROWS_EPI=0: transposing epilogue everywhere)
     unsigned long long launches = 0;
 
 private:
@@ -122,6 +123,7 @@ public:
     int device;
     bool pair_mode = true;   // 2-CTA tiles when the batch has >= 4096 rows (BSG_PE_PAIR=0: single-CTA tiles)
     bool use_graphs = true;  // forward replays one captured CUDA graph per shape (BSG_PE_GRAPH=0: plain launches)
+    bool rows_epi = true;    // row-per-thread write-only epilogue (BSG_ROWS_EPI=0: transposing epilogue)
     unsigned long long launches = 0;
 
 private:

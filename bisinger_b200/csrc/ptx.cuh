@@ -278,6 +278,12 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc_f8(int M, int N, int a_
 __device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N) { return umma_idesc_f16(M, N, false); }
 
 // ---------------------------------------------------------------- misc
+// 256-bit global store (sm_100): one full 32-byte sector per lane
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);

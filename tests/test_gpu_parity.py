@@ -378,3 +378,30 @@ def test_vocoder_small_kernel_variants(voc, dev, monkeypatch):
         assert O.snr_db(b, a) >= SNR_TOL_DB
         a0, b0 = gen(args[0], None).cpu(), old(args[0], None).cpu()      # no NSF branch: the kernel only adds 0 and applies lrelu
         assert torch.equal(a0, b0)
+
+
+def test_row_per_thread_epilogue_is_bit_identical(voc, dev, monkeypatch):
+    """The write-only epilogue with row-per-thread 256-bit stores (default) computes exactly what the transposing epilogue does
+    (BSG_ROWS_EPI=0): vocoder (full and partial tiles, 2-CTA tiles from 4096 rows up) and PitchExtractor outputs must be bit-identical."""
+    from bisinger_b200.pitch import B200PitchExtractor
+    from bisinger_b200.vocoder import B200HifiGanGenerator
+    vsd, gen = voc
+    psd = synth.pe_state(777, 2)
+    pe = B200PitchExtractor().eval()
+    pe.load_state_dict(psd, strict=True)
+    pe.build_plan(dev)
+    monkeypatch.setenv("BSG_ROWS_EPI", "0")
+    old = B200HifiGanGenerator(synth.HIFIGAN_CONFIG)
+    old.load_folded_state_dict(vsd, strict=True)
+    old.build_plan(dev)
+    pe_old = B200PitchExtractor().eval()
+    pe_old.load_state_dict(psd, strict=True)
+    pe_old.build_plan(dev)
+    for B, T in ((1, 5), (2, 77), (1, 600)):
+        vin = synth.vocoder_inputs(700 + T, B, T)
+        args = [vin[k].to(dev) for k in ("mel", "f0", "rand_ini", "src_noise")]
+        assert torch.equal(gen(*args), old(*args))
+    for B, T in ((2, 45), (3, 1500)):
+        mel = synth.pe_inputs(710 + T, B, T, pad_tail=7).to(dev)
+        a, b = pe(mel), pe_old(mel)
+        assert torch.equal(a["pitch_pred"], b["pitch_pred"]) and torch.equal(a["f0_denorm_pred"], b["f0_denorm_pred"])
