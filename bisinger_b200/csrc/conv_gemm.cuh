@@ -282,7 +282,8 @@ enum : int {
     BA_ACCUM_INIT = 8,   // with BA_ACCUM_F32B: '=' instead of '+='
     BA_WRITE_ACT = 16,   // out_hi[row][n] = bf16(lrelu(y, c1))
     BA_ACT_FROM_B = 32,  // the bf16 activation is taken from the accumulated f32_b value instead of y
-    BA_ROWS = 64,        // write-only epilogues (no BA_ADD_RES / BA_ACCUM_F32B) keep the accumulator's row-per-thread ownership: see below
+    BA_ROWS = 64,        // the epilogue keeps the accumulator's row-per-thread ownership and uses 256-bit global accesses (see below)
+    BA_ROWS_RMW = 128,   // ... also when it reads (BA_ADD_RES / BA_ACCUM_F32B)
 };
 
 // b: batch index, t_warp: first row (within the batch) of this warp's 32 accumulator lanes, grp: column group of the
@@ -601,6 +602,88 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, int Lrows, uint
                             for (int i = 0; i < 8; ++i) q[i] = lo[8 + i];
                             stg256(dl + 16, q);
                         }
+                    }
+                }
+            }
+            return;
+        }
+        if (e.flags & BA_ROWS_RMW) {
+            // Read-modify-write epilogues (second conv of a ResBlock iteration: residual add, running residual / MRF accumulator) in the same
+            // row-per-thread ownership: every lane reads and writes whole 32-byte sectors of its own row with 256-bit accesses, 16 columns per
+            // pass (loads of the pass are issued before the accumulator is fetched from TMEM).
+            const bool ok = FULL || lane < Lrows - t_warp;
+            const long long row = row_w + lane;
+            const bool add_res = (e.flags & BA_ADD_RES) != 0, accum = (e.flags & BA_ACCUM_F32B) != 0;
+            const bool rd_b = accum && !(e.flags & BA_ACCUM_INIT);
+#pragma unroll 1
+            for (int c = c_begin; c < c_begin + kColsPerGrp; c += 16) {
+                const int n = n_tile * N_TILE + c;
+                const long long o32 = row * e.out_pitch + e.out_col0 + n;
+                float r0[8], r1[8], s0[8], s1[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { r0[i] = r1[i] = s0[i] = s1[i] = 0.0f; }
+                if (ok && add_res) {
+                    ldg256(e.aux0 + o32, r0);
+                    ldg256(e.aux0 + o32 + 8, r1);
+                }
+                if (ok && rd_b) {
+                    ldg256(e.f32_b + o32, s0);
+                    ldg256(e.f32_b + o32 + 8, s1);
+                }
+                float v[16];
+                ld_acc16(tacc + c, v, sc);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + n) + j);
+                    v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                }
+                if (add_res) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { v[i] = __fadd_rn(v[i], r0[i]); v[8 + i] = __fadd_rn(v[8 + i], r1[i]); }
+                }
+                uint32_t q[8];
+                if ((e.flags & BA_WRITE_F32) && ok) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) q[i] = __float_as_uint(v[8 * j + i]);
+                        stg256(e.f32_a + o32 + 8 * j, q);
+                    }
+                }
+                if (accum) {
+                    float a[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        a[i] = __fmul_rn(v[i], e.c0);
+                        if (rd_b) a[i] = __fadd_rn(a[i], i < 8 ? s0[i & 7] : s1[i & 7]);
+                    }
+                    if (ok) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) q[i] = __float_as_uint(a[8 * j + i]);
+                            stg256(e.f32_b + o32 + 8 * j, q);
+                        }
+                    }
+                    if (e.flags & BA_ACT_FROM_B) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = a[i];
+                    }
+                }
+                if (e.flags & BA_WRITE_ACT) {
+                    uint32_t lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float y0 = v[2 * i] > 0.0f ? v[2 * i] : v[2 * i] * e.c1;
+                        const float y1 = v[2 * i + 1] > 0.0f ? v[2 * i + 1] : v[2 * i + 1] * e.c1;
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                        q[i] = *reinterpret_cast<const uint32_t*>(&h);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(y0 - __uint_as_float(q[i] << 16), y1 - __uint_as_float(q[i] & 0xffff0000u));
+                        lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    if (ok) {
+                        stg256(e.out_hi + row * e.act_pitch + n, q);
+                        if (e.out_lo != nullptr) stg256(e.out_lo + row * e.act_pitch + n, lo);
                     }
                 }
             }

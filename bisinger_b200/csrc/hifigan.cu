@@ -481,6 +481,7 @@ HifiganPlan::HifiganPlan(const bsg_hifigan_config& c, const float* w, size_t n_w
     if (const char* ng = std::getenv("BSG_VOC_GRAPH")) use_graphs = ng[0] == '1';
     if (const char* nv = std::getenv("BSG_VOC_NOISE_V2")) noise_v2 = nv[0] == '1';
     if (const char* nr = std::getenv("BSG_ROWS_EPI")) rows_epi = nr[0] == '1';
+    if (const char* nm = std::getenv("BSG_ROWS_RMW")) rows_rmw = nm[0] == '1';
     if (pair_mode) for (int nt : {256, 128}) launch_conv_gemm(nt, 1, EPI_BIAS_ACT, none, nullptr, 1);
 }
 
@@ -618,7 +619,8 @@ void HifiganPlan::enqueue(Workspace& w, const float* mel, const float* f0, const
         a.epi = epi;
         a.epi.bias = cv.bias.as<float>();
         // row-per-thread write-only epilogue: needs 32-byte aligned rows (channel counts that are multiples of 16 / 8)
-        if (rows_epi && a.epi.act_pitch % 16 == 0 && a.epi.out_pitch % 8 == 0 && a.epi.out_col0 % 8 == 0) a.epi.flags |= BA_ROWS;
+        if (rows_epi && a.epi.act_pitch % 16 == 0 && a.epi.out_pitch % 8 == 0 && a.epi.out_col0 % 8 == 0)
+            a.epi.flags |= BA_ROWS | (rows_rmw ? BA_ROWS_RMW : 0);
         launch_conv_gemm(nt, 1, EPI_BIAS_ACT, a, st, pair);
         launches += 1, g_launch_count += 1;
     };

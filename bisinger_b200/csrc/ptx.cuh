@@ -278,6 +278,16 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc_f8(int M, int N, int a_
 __device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int M, int N) { return umma_idesc_f16(M, N, false); }
 
 // ---------------------------------------------------------------- misc
+// 256-bit global load (sm_100): one full 32-byte sector per lane
+__device__ __forceinline__ void ldg256(const void* p, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 // 256-bit global store (sm_100): one full 32-byte sector per lane
 __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),

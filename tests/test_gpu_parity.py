@@ -380,9 +380,9 @@ def test_vocoder_small_kernel_variants(voc, dev, monkeypatch):
         assert torch.equal(a0, b0)
 
 
-def test_row_per_thread_epilogue_is_bit_identical(voc, dev, monkeypatch):
-    """The write-only epilogue with row-per-thread 256-bit stores (default) computes exactly what the transposing epilogue does
-    (BSG_ROWS_EPI=0): vocoder (full and partial tiles, 2-CTA tiles from 4096 rows up) and PitchExtractor outputs must be bit-identical."""
+def test_row_per_thread_epilogue_matches_transposing_epilogue(voc, dev, monkeypatch):
+    """The row-per-thread epilogues with 256-bit global accesses (default) against the transposing epilogue (BSG_ROWS_EPI=0): vocoder
+    (full and partial tiles, 2-CTA tiles from 4096 rows up) and PitchExtractor (write-only epilogues: bit-identical)."""
     from bisinger_b200.pitch import B200PitchExtractor
     from bisinger_b200.vocoder import B200HifiGanGenerator
     vsd, gen = voc
@@ -400,7 +400,12 @@ def test_row_per_thread_epilogue_is_bit_identical(voc, dev, monkeypatch):
     for B, T in ((1, 5), (2, 77), (1, 600)):
         vin = synth.vocoder_inputs(700 + T, B, T)
         args = [vin[k].to(dev) for k in ("mel", "f0", "rand_ini", "src_noise")]
-        assert torch.equal(gen(*args), old(*args))
+        a, b = gen(*args).cpu(), old(*args).cpu()
+        # the read-modify-write epilogues use explicit mul / add where the transposing epilogue leaves the contraction to the compiler
+        assert O.snr_db(b, a) >= 60.0
+        with torch.no_grad():
+            ref = O.hifigan_forward(vsd, synth.HIFIGAN_CONFIG, vin["mel"], vin["f0"], vin["rand_ini"], vin["src_noise"])
+        assert O.snr_db(ref, a) >= SNR_TOL_DB
     for B, T in ((2, 45), (3, 1500)):
         mel = synth.pe_inputs(710 + T, B, T, pad_tail=7).to(dev)
         a, b = pe(mel), pe_old(mel)
