@@ -82,7 +82,7 @@ public:
     bool use_graphs = true;  // forward without injected noise replays one captured CUDA graph per shape (BSG_VOC_GRAPH=0: plain launches)
     bool noise_v2 = true;    // row-group layout of the noise-branch kernel (BSG_VOC_NOISE_V2=0: one warp per row)
     bool rows_epi = true;    // row-per-thread write-only epilogue with 256-bit stores (BSG_ROWS_EPI=0: transposing epilogue everywhere)
-    bool rows_rmw = false;   // ... also for the read-modify-write epilogues, with 256-bit loads (BSG_ROWS_RMW=1; off until measured)
+    bool rows_rmw = true;    // ... also for the read-modify-write epilogues, with 256-bit loads (BSG_ROWS_RMW=0: transposing epilogue for those)
     unsigned long long launches = 0;
 
 private:
