@@ -73,3 +73,22 @@ def test_gaussian_diffusion_buffers():
     assert gd.spec_min.shape == (1, 1, 80)
     with pytest.raises(NotImplementedError):
         gd(torch.zeros(1, 4, dtype=torch.long), infer=False)
+
+
+def test_ctypes_structs_follow_the_header():
+    """Field names and order of the config structs in include/bisinger_b200.h == the ctypes mirrors in _lib.py (an ABI drift between
+    the header and the binding would otherwise only show up as wrong results on the GPU)."""
+    hdr = open(os.path.join(ROOT, "include", "bisinger_b200.h")).read()
+    structs = {name: body for body, name in re.findall(r"typedef struct \{([^}]*)\}\s*(\w+);", hdr)}
+    for cname, ctype in (("bsg_diffnet_config", _lib.DiffnetConfig), ("bsg_hifigan_config", _lib.HifiganConfig), ("bsg_pe_config", _lib.PeConfig),
+                         ("bsg_schedule", _lib.Schedule)):
+        body = re.sub(r"/\*.*?\*/", "", structs[cname], flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?(int|float|double|unsigned|size_t)\s*\*?\s*", "", decl)
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*", "", part.strip()))
+        assert names == [f[0] for f in ctype._fields_], (cname, names)
