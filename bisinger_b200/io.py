@@ -66,6 +66,16 @@ def load_diffusion_checkpoint(model, ckpt_base_dir: str, prefix_in_ckpt: str = "
     return path, fs2
 
 
+def load_pitch_extractor_checkpoint(pe, ckpt_base_dir: str, prefix_in_ckpt: str = "model", strict: bool = True) -> str:
+    """``utils.load_ckpt(self.pe, hparams['pe_ckpt'], 'model', strict=True)`` (inference/m4singer/bisinger/a-*.py:600-603,
+    usr/diffsinger_task.py:37-40) for a B200PitchExtractor: the newest ``model_ckpt_steps_*.ckpt`` under ``checkpoints/m4singer_pe``, keys
+    under ``model.``; the parameter / buffer names are the reference's, so the load is strict.  The device plan is rebuilt lazily."""
+    path = find_checkpoint(ckpt_base_dir)
+    sd = strip_prefix(torch.load(path, map_location="cpu")["state_dict"], prefix_in_ckpt)
+    pe.load_state_dict(sd, strict=strict)
+    return path
+
+
 def wav_to_int16(wav, norm: bool = False) -> np.ndarray:
     """utils/audio.py:13-17: ``wav / max|wav|`` if norm, ``* 32767``, C-style truncation to int16."""
     wav = np.asarray(wav, dtype=np.float32).reshape(-1).copy()

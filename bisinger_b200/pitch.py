@@ -100,6 +100,15 @@ class B200PitchExtractor(nn.Module):
         self._plan = None
         return super().load_state_dict(*a, **k)
 
+    @classmethod
+    def from_checkpoint(cls, ckpt_base_dir: str, hparams: Optional[dict] = None, n_mel_bins=80, conv_layers=2):
+        """``PitchExtractor().to(device); load_ckpt(pe, hparams['pe_ckpt'], 'model', strict=True); pe.eval()``
+        (inference/m4singer/bisinger/a-*.py:600-603) in one call."""
+        from .io import load_pitch_extractor_checkpoint
+        pe = cls(n_mel_bins, conv_layers, hparams).eval()
+        load_pitch_extractor_checkpoint(pe, ckpt_base_dir)
+        return pe
+
     # weight blob in the order include/bisinger_b200.h documents
     def flat_weights(self) -> torch.Tensor:
         parts = []

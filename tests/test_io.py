@@ -49,3 +49,20 @@ def test_save_wav_matches_reference_semantics(tmp_path):
         return
     sr, back = wavfile.read(str(path))
     assert sr == 24000 and np.array_equal(back, pcm)
+
+
+def test_pitch_extractor_checkpoint_layout(tmp_path):
+    """checkpoints/m4singer_pe layout: ``state_dict`` keys under ``model.`` (tasks/tts/pe.py:109 trains ``self.model = PitchExtractor``); the
+    drop-in loads it strictly and folds BatchNorm from the loaded running statistics."""
+    from bisinger_b200.pitch import B200PitchExtractor
+    sd = synth.pe_state(777, 2)
+    torch.save({"state_dict": {"model." + k: v for k, v in sd.items()}, "global_step": 60000}, tmp_path / "model_ckpt_steps_60000.ckpt")
+    torch.save({"state_dict": {"model." + k: torch.zeros_like(v) for k, v in sd.items()}}, tmp_path / "model_ckpt_steps_100.ckpt")
+    pe = B200PitchExtractor.from_checkpoint(str(tmp_path))
+    assert not pe.training
+    got = pe.state_dict()
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+    w = pe.flat_weights()
+    bn = sd["mel_prenet.layers.0.2.weight"] / torch.sqrt(sd["mel_prenet.layers.0.2.running_var"] + 1e-5)
+    off = 256 * 80 * 5 + 256
+    assert torch.allclose(w[off:off + 256], bn)                       # folded scale follows conv weight + bias in the blob
