@@ -92,3 +92,20 @@ def test_ctypes_structs_follow_the_header():
             for part in decl.split(","):
                 names.append(re.sub(r"\[.*", "", part.strip()))
         assert names == [f[0] for f in ctype._fields_], (cname, names)
+
+
+def test_library_sass_uses_tcgen05_tma_tmem():
+    """The built library really is a tcgen05 / TMA / TMEM implementation (B200_PROFILING.md's SASS mnemonics): UTCHMMA (tcgen05.mma, also the
+    2-CTA form), UTCQMMA (kind::f8f6f4 correction MMAs), UTMALDG (cp.async.bulk.tensor, 2-D / 3-D, multicast), LDTM (tcgen05.ld), UTCBAR
+    (tcgen05.commit) and the 256-bit global accesses of the row-per-thread epilogues -- and no legacy HMMA / wgmma path."""
+    import shutil
+    import subprocess
+    _ensure_built()
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTCQMMA", "UTMALDG.2D", "UTMALDG.3D", "UTMALDG.2D.MULTICAST.2CTA", "LDTM.x32", "UTCBAR",
+                     "UTCBAR.2CTA.MULTICAST", "STG.E.ENL2.256", "LDG.E.ENL2.256"):
+        assert mnemonic in sass, mnemonic
+    assert " HMMA." not in sass and "HGMMA" not in sass
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
