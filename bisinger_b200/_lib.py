@@ -107,6 +107,16 @@ def check(status: int) -> None:
         raise RuntimeError("bisinger_b200: " + lib().bsg_last_error().decode("utf-8", "replace"))
 
 
+def resolve_seed(seed) -> int:
+    """``seed=None`` (the default of every entry point): a fresh 62-bit Philox key drawn from torch's global CPU generator, so that
+    repeated calls get fresh noise as in the reference (which draws from the global RNG: shallow_diffusion_tts.py:163, source.py:54,133)
+    while ``torch.manual_seed(s)`` still makes a run reproducible.  An explicit integer is used as is."""
+    if seed is None:
+        import torch
+        return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    return int(seed) & (2 ** 64 - 1)
+
+
 def launch_count() -> int:
     return int(lib().bsg_kernel_launch_count())
 

@@ -83,6 +83,17 @@ class B200DiffNet(nn.Module):
         nn.init.zeros_(self.output_projection.weight)  # net.py:105
         self._standalone_plan = None
 
+    # a plan holds packed copies of the weights on the device: anything that changes the parameters drops it
+    def load_state_dict(self, *a, **k):
+        self._standalone_plan = None
+        self._version = getattr(self, "_version", 0) + 1
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._standalone_plan = None
+        self._version = getattr(self, "_version", 0) + 1
+        return super()._apply(fn, *a, **k)
+
     # -- weight blob in the order include/bisinger_b200.h documents (== state_dict registration order)
     def flat_weights(self) -> torch.Tensor:
         names = ["input_projection.weight", "input_projection.bias", "mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias"]
@@ -168,7 +179,7 @@ class DiffusionPlan:
         _lib.check(_lib.lib().bsg_diffusion_time_kernel(self._h, which, B, T, reps, C.byref(ms), _lib.current_stream_ptr(self.device)))
         return float(ms.value)
 
-    def sample(self, cond_btH, fs2_mel=None, start_noise=None, step_noise=None, seed: int = 0, mel2ph=None,
+    def sample(self, cond_btH, fs2_mel=None, start_noise=None, step_noise=None, seed: Optional[int] = None, mel2ph=None,
                return_x: bool = False):
         """cond_btH [B,T,H]; fs2_mel [B,T,M] or None (Gaussian start); start_noise [B,1,M,T]; step_noise [K,B,1,M,T]
         (None => drawn on the device, CUDA-graph path).  Returns mel_out [B,T,M] (and x_0 [B,1,M,T])."""
@@ -187,12 +198,12 @@ class DiffusionPlan:
         xf = torch.empty((B, 1, self.M, T), device=dev, dtype=torch.float32) if return_x else None
         _lib.check(_lib.lib().bsg_diffusion_sample(
             self._h, _lib.dev_ptr(cond), _lib.dev_ptr(fs2_mel), _lib.dev_ptr(start_noise), _lib.dev_ptr(step_noise),
-            C.c_ulonglong(seed & (2 ** 64 - 1)), _lib.dev_ptr(mel2ph), B, T, _lib.dev_ptr(mel), _lib.dev_ptr(xf),
+            C.c_ulonglong(_lib.resolve_seed(seed)), _lib.dev_ptr(mel2ph), B, T, _lib.dev_ptr(mel), _lib.dev_ptr(xf),
             _lib.current_stream_ptr(dev)))
         return (mel, xf) if return_x else mel
 
 
-    def sample_plms(self, cond_btH, fs2_mel=None, start_noise=None, interval: int = 5, seed: int = 0, mel2ph=None,
+    def sample_plms(self, cond_btH, fs2_mel=None, start_noise=None, interval: int = 5, seed: Optional[int] = None, mel2ph=None,
                     return_x: bool = False):
         """The PLMS / PNDM sampler (hparams['pndm_speedup'] = interval; shallow_diffusion_tts.py:168-201,258-264): K_step / interval
         iterations, deterministic after the start.  Arguments as ``sample``; returns mel_out [B,T,M] (and x_0 [B,1,M,T])."""
@@ -210,7 +221,7 @@ class DiffusionPlan:
         mel = torch.empty((B, T, self.M), device=dev, dtype=torch.float32)
         xf = torch.empty((B, 1, self.M, T), device=dev, dtype=torch.float32) if return_x else None
         _lib.check(_lib.lib().bsg_diffusion_sample_plms(
-            self._h, _lib.dev_ptr(cond), _lib.dev_ptr(fs2_mel), _lib.dev_ptr(start_noise), C.c_ulonglong(seed & (2 ** 64 - 1)),
+            self._h, _lib.dev_ptr(cond), _lib.dev_ptr(fs2_mel), _lib.dev_ptr(start_noise), C.c_ulonglong(_lib.resolve_seed(seed)),
             _lib.dev_ptr(mel2ph), _lib.fptr(self._alphas_cumprod), int(interval), B, T, _lib.dev_ptr(mel), _lib.dev_ptr(xf),
             _lib.current_stream_ptr(dev)))
         return (mel, xf) if return_x else mel
@@ -304,7 +315,7 @@ class B200GaussianDiffusion(nn.Module):
         return (x + 1) / 2 * (self.spec_max - self.spec_min) + self.spec_min
 
     @torch.no_grad()
-    def sample(self, decoder_inp, fs2_mel, mel2ph=None, start_noise=None, step_noise=None, seed=0, return_x=False):
+    def sample(self, decoder_inp, fs2_mel, mel2ph=None, start_noise=None, step_noise=None, seed=None, return_x=False):
         gaussian = bool(self.hparams.get("gaussian_start"))
         if self.hparams.get("pndm_speedup"):   # shallow_diffusion_tts.py:258-264
             return self.plan.sample_plms(decoder_inp, None if gaussian else fs2_mel, start_noise, int(self.hparams["pndm_speedup"]), seed,

@@ -142,10 +142,20 @@ class B200HifiGanGenerator(nn.Module):
     def plan(self) -> "HifiganPlan":
         return self._plan if self._plan is not None else self.build_plan()
 
+    # a plan holds packed copies of the weights on the device: anything that changes the parameters drops it
+    def load_state_dict(self, *a, **k):
+        self._plan = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
     @torch.no_grad()
-    def forward(self, x, f0=None, rand_ini=None, src_noise=None, seed: int = 0):
+    def forward(self, x, f0=None, rand_ini=None, src_noise=None, seed: Optional[int] = None):
         """x [B,80,T], f0 [B,T] or None -> [B,1,T*hop] (hifigan.py:144-173).  ``rand_ini`` [B,9] / ``src_noise`` [B,L,9]
-        inject the tensors the reference draws from the global RNG (source.py:54,133)."""
+        inject the tensors the reference draws from the global RNG (source.py:54,133); otherwise both are drawn on the device
+        from ``seed`` (None: a fresh seed from torch's global generator per call)."""
         return self.plan.forward(x, f0, rand_ini, src_noise, seed)[:, None, :]
 
 
@@ -197,61 +207,198 @@ class HifiganPlan:
     def _prep(self, t):
         return None if t is None else t.to(self.device, torch.float32).contiguous()
 
-    def forward(self, mel, f0=None, rand_ini=None, src_noise=None, seed: int = 0):
+    def forward(self, mel, f0=None, rand_ini=None, src_noise=None, seed: Optional[int] = None):
         mel, f0, rand_ini, src_noise = self._prep(mel), self._prep(f0), self._prep(rand_ini), self._prep(src_noise)
         B, M, T = mel.shape
         wav = torch.empty((B, T * self.hop), device=self.device, dtype=torch.float32)
         _lib.check(_lib.lib().bsg_hifigan_forward(self._h, _lib.dev_ptr(mel), _lib.dev_ptr(f0), _lib.dev_ptr(rand_ini),
-                                                  _lib.dev_ptr(src_noise), C.c_ulonglong(seed & (2 ** 64 - 1)), B, T,
+                                                  _lib.dev_ptr(src_noise), C.c_ulonglong(_lib.resolve_seed(seed)), B, T,
                                                   _lib.dev_ptr(wav), _lib.current_stream_ptr(self.device)))
         return wav
 
-    def source(self, f0, rand_ini=None, src_noise=None, seed: int = 0):
+    def source(self, f0, rand_ini=None, src_noise=None, seed: Optional[int] = None):
         f0, rand_ini, src_noise = self._prep(f0), self._prep(rand_ini), self._prep(src_noise)
         B, T = f0.shape
         har = torch.empty((B, T * self.hop), device=self.device, dtype=torch.float32)
         _lib.check(_lib.lib().bsg_hifigan_source(self._h, _lib.dev_ptr(f0), _lib.dev_ptr(rand_ini), _lib.dev_ptr(src_noise),
-                                                 C.c_ulonglong(seed & (2 ** 64 - 1)), B, T, _lib.dev_ptr(har),
+                                                 C.c_ulonglong(_lib.resolve_seed(seed)), B, T, _lib.dev_ptr(har),
                                                  _lib.current_stream_ptr(self.device)))
         return har
 
 
-class B200HifiGAN:
-    """Vocoder-registry drop-in for ``vocoders.hifigan.HifiGAN`` (vocoders/hifigan.py:36-69): ``spec2wav(mel[T,80], f0=)``
-    returns a flat numpy waveform.  Select it in the reference with ``vocoder: bisinger_b200.vocoder.B200HifiGAN``
-    (``get_vocoder_cls`` imports dotted paths, vocoders/base_vocoder.py:12-20).  Also offers the batched
-    ``spec2wav_batch`` that returns ``[B, L]`` (the reference's ``run_vocoder`` flattens across the batch,
+def _ref_hparams() -> dict:
+    """The reference's global ``utils.hparams.hparams`` when the reference tree is importable, else an empty dict."""
+    try:
+        from utils.hparams import hparams as ref_hp  # type: ignore
+        return ref_hp
+    except Exception:
+        return {}
+
+
+def _base_vocoder_cls():
+    """``vocoders.base_vocoder.BaseVocoder`` and ``register_vocoder`` of the reference when it is importable (so that the drop-in IS a
+    BaseVocoder and sits in the VOCODERS registry, vocoders/base_vocoder.py:3-20); a stand-in with the same two methods otherwise."""
+    try:
+        from vocoders.base_vocoder import BaseVocoder, register_vocoder  # type: ignore
+        return BaseVocoder, register_vocoder
+    except Exception:
+        class BaseVocoder:  # vocoders/base_vocoder.py:23-40
+            def spec2wav(self, mel):
+                raise NotImplementedError
+
+            @staticmethod
+            def wav2spec(wav_fn):
+                raise NotImplementedError
+
+        return BaseVocoder, (lambda cls: cls)
+
+
+_BaseVocoder, _register_vocoder = _base_vocoder_cls()
+
+
+def load_vocoder_config(config_path: str) -> dict:
+    """``config.yaml`` (with the ``base_config`` inheritance chain of utils/hparams.py:48-66, deep first, later files override) or
+    ``config.json`` (vocoders/hifigan.py:19-25)."""
+    if config_path.endswith(".json"):
+        import json
+        with open(config_path) as f:
+            return json.load(f)
+    import os
+    import yaml
+    loaded = set()
+
+    def override(old, new):
+        for k, v in new.items():
+            if isinstance(v, dict) and k in old:
+                override(old[k], v)
+            else:
+                old[k] = v
+
+    def load(fn):
+        with open(fn) as f:
+            hp = yaml.safe_load(f) or {}
+        loaded.add(fn)
+        if "base_config" not in hp:
+            return hp
+        ret = {}
+        bases = hp["base_config"] if isinstance(hp["base_config"], list) else [hp["base_config"]]
+        for c in bases:
+            if c in loaded:
+                continue
+            if c.startswith("."):
+                c = os.path.normpath(f"{os.path.dirname(fn)}/{c}")
+            override(ret, load(c))
+        override(ret, hp)
+        return ret
+
+    return load(config_path)
+
+
+def find_vocoder_checkpoint(base_dir: str):
+    """vocoders/hifigan.py:40-52: ``config.yaml`` + the ``model_ckpt_steps_*.ckpt`` with the highest step count, else
+    ``config.json`` + ``generator_v1``.  Returns (config_path, checkpoint_path)."""
+    import glob
+    import os
+    import re as _re
+    cfg = os.path.join(base_dir, "config.yaml")
+    if os.path.exists(cfg):
+        found = glob.glob(os.path.join(base_dir, "model_ckpt_steps_*.ckpt"))
+        if not found:
+            raise FileNotFoundError(f"no model_ckpt_steps_*.ckpt in {base_dir}")
+        return cfg, max(found, key=lambda p: int(_re.findall(r"model_ckpt_steps_(\d+)\.ckpt$", p)[0]))
+    cfg = os.path.join(base_dir, "config.json")
+    if os.path.exists(cfg):
+        return cfg, os.path.join(base_dir, "generator_v1")
+    raise FileNotFoundError(f"neither config.yaml nor config.json in vocoder_ckpt = {base_dir}")
+
+
+def denoise(wav, v=0.0, fft_size=512, hop_size=128, win_size=512):
+    """The optional spectral-subtraction post-filter (vocoders/vocoder_utils.py:7-15; hparams['vocoder_denoise_c'] > 0):
+    STFT (hann window, centred, constant = zero padding) -> magnitudes reduced by ``v`` and clipped at 0, phases kept -> inverse
+    STFT.  The reference calls librosa.stft / librosa.istft; the same transform pair is evaluated here with torch.stft / torch.istft on
+    the host (periodic hann of ``win_size`` zero-padded to ``fft_size``, squared-window overlap-add normalisation, the centre padding
+    trimmed, output length hop * (frames - 1)).  librosa is not installed in the build container, so this one function is pinned
+    by its algebra (identity at v = 0, tests/test_vocoder_registry.py), not against librosa's output."""
+    x = torch.as_tensor(np.asarray(wav), dtype=torch.float32)
+    win = torch.hann_window(win_size, periodic=True)
+    spec = torch.stft(x, n_fft=fft_size, hop_length=hop_size, win_length=win_size, window=win, center=True, pad_mode="constant",
+                      return_complex=True)
+    mag = torch.clamp(spec.abs() - float(v), min=0.0)
+    out = torch.istft(torch.polar(mag, torch.angle(spec)), n_fft=fft_size, hop_length=hop_size, win_length=win_size, window=win,
+                      center=True)
+    return out.numpy()
+
+
+@_register_vocoder
+class B200HifiGAN(_BaseVocoder):
+    """Vocoder-registry drop-in for ``vocoders.hifigan.HifiGAN`` (vocoders/hifigan.py:36-69).
+
+    ``get_vocoder_cls(hparams)()`` (tasks/tts/tts.py:109, usr/diffsinger_task.py:36) instantiates the class WITHOUT arguments: the
+    constructor then reads ``hparams['vocoder_ckpt']`` exactly like the reference -- ``config.yaml`` + newest
+    ``model_ckpt_steps_*.ckpt`` (``state_dict.model_gen``) or ``config.json`` + ``generator_v1`` (``generator``) -- loads the state dict
+    with ``strict=True``, folds weight-norm and builds the device plan.  Select it with the config line
+    ``vocoder: bisinger_b200.vocoder.B200HifiGAN`` (``get_vocoder_cls`` imports dotted paths, vocoders/base_vocoder.py:12-20); when the
+    reference's ``vocoders`` package is importable the class also IS a ``BaseVocoder`` registered as ``B200HifiGAN`` / ``b200hifigan``.
+    ``spec2wav(mel[T,80], f0=...)`` returns the flat numpy waveform, honours ``hparams['use_nsf']`` and ``hparams['vocoder_denoise_c']``.
+    Also offers ``spec2wav_batch`` returning ``[B, L]`` (the reference's ``run_vocoder`` flattens across the batch,
     inference/m4singer/base_svs_infer.py:142-151 -- a latent bug for B > 1)."""
 
-    def __init__(self, generator: Optional[B200HifiGanGenerator] = None, config: Optional[dict] = None, use_nsf: bool = True):
+    def __init__(self, generator: Optional[B200HifiGanGenerator] = None, config: Optional[dict] = None, use_nsf: Optional[bool] = None,
+                 hparams: Optional[dict] = None):
+        self.hparams = hp = hparams if hparams is not None else _ref_hparams()
         if generator is None:
-            raise RuntimeError("B200HifiGAN needs a generator (build one from a checkpoint with B200HifiGAN.from_checkpoint)")
+            base_dir = hp.get("vocoder_ckpt")
+            if not base_dir:
+                raise RuntimeError("B200HifiGAN(): hparams['vocoder_ckpt'] is not set (the zero-argument constructor reads the "
+                                   "reference's global hparams, vocoders/hifigan.py:38; or pass hparams=...)")
+            config_path, ckpt = find_vocoder_checkpoint(base_dir)
+            generator, config = self._load_model(config_path, ckpt)
+            print("| load B200HifiGAN: ", ckpt)
         self.model = generator
         self.config = config or generator.h
-        self.use_nsf = use_nsf
+        self.use_nsf = bool(hp.get("use_nsf")) if use_nsf is None else bool(use_nsf)
         self.device = generator.plan.device
 
+    @staticmethod
+    def _load_model(config_path: str, checkpoint_path: str):
+        """load_model (vocoders/hifigan.py:17-33)."""
+        ckpt = torch.load(checkpoint_path, map_location="cpu")
+        config = load_vocoder_config(config_path)
+        state = ckpt["state_dict"]["model_gen"] if config_path.endswith(".yaml") else ckpt["generator"]
+        gen = B200HifiGanGenerator(config)
+        gen.load_state_dict(state, strict=True)
+        gen.remove_weight_norm()
+        return gen.eval().cuda(), config
+
     @classmethod
-    def from_checkpoint(cls, config: dict, checkpoint_path: str, use_nsf: bool = True):
-        """vocoders/hifigan.py:17-33: ``state_dict.model_gen`` (yaml config) or ``generator`` (json config)."""
+    def from_checkpoint(cls, config, checkpoint_path: str, use_nsf: bool = True, hparams: Optional[dict] = None):
+        """Explicit form: ``config`` is a dict or a path to config.yaml / config.json; ``state_dict.model_gen`` or ``generator``."""
+        if isinstance(config, str):
+            config = load_vocoder_config(config)
         ckpt = torch.load(checkpoint_path, map_location="cpu")
         state = ckpt["state_dict"]["model_gen"] if "state_dict" in ckpt else ckpt["generator"]
         gen = B200HifiGanGenerator(config)
         gen.load_state_dict(state, strict=True)
         gen.remove_weight_norm()
-        return cls(gen.eval().cuda(), config, use_nsf)
+        return cls(gen.eval().cuda(), config, use_nsf, hparams=hparams if hparams is not None else {})
 
     def spec2wav(self, mel, **kwargs):
+        """mel [T,80] (numpy) -> wav [T*hop] (numpy); f0=[T] Hz is used when hparams['use_nsf'] (vocoders/hifigan.py:55-69)."""
         c = torch.as_tensor(np.asarray(mel), dtype=torch.float32).unsqueeze(0).transpose(2, 1)
         f0 = kwargs.get("f0")
         if f0 is not None and self.use_nsf:
             f0 = torch.as_tensor(np.asarray(f0), dtype=torch.float32)[None, :]
         else:
             f0 = None
-        y = self.model(c, f0, seed=kwargs.get("seed", 0)).view(-1)
-        return y.cpu().numpy()
+        y = self.model(c, f0, seed=kwargs.get("seed")).view(-1)
+        wav_out = y.cpu().numpy()
+        hp = self.hparams
+        if hp.get("vocoder_denoise_c", 0.0) > 0:
+            wav_out = denoise(wav_out, v=hp["vocoder_denoise_c"], fft_size=hp["fft_size"], hop_size=hp["hop_size"],
+                              win_size=hp["win_size"])
+        return wav_out
 
-    def spec2wav_batch(self, mel_btm, f0_bt=None, seed: int = 0):
+    def spec2wav_batch(self, mel_btm, f0_bt=None, seed: Optional[int] = None):
         y = self.model(torch.as_tensor(mel_btm).transpose(2, 1), f0_bt if self.use_nsf else None, seed=seed)
         return y[:, 0]
 
