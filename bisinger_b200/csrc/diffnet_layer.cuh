@@ -67,7 +67,9 @@ struct LayerArgs {
     __half* xa16_out[2];   // conv input buffers as plain pointers (layer l writes [(l + 1) & 1])
     uint8_t* xa8_out[2];
     const float* lut_t;    // [total layers][C] step embeddings d_l of this diffusion step
-    int* flags;            // n_layers > 1: [total layers][n_row_tiles] completion counters, zero before the launch
+    int* flags;            // n_layers > 1: [total layers][n_row_tiles] completion counters: every launch adds 16 (epilogue warps per row tile)
+                           //    to each; they are zeroed ONCE per sampling call, not per launch
+    int epoch;             // 1-based count of launches since the counters were zeroed: a row tile is complete at 16 * epoch
     int flags_ablate;      // timing ablations (bit 1: no fp8 MMAs, bit 2: no fp16 MMAs)
     unsigned long long* trace;
 };
@@ -286,13 +288,14 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
         const int ti = m % args.tiles_per_batch;
         const int lo = ti > 0 ? m - 1 : m, hi = (ti + 1 < args.tiles_per_batch) ? m + 1 : m;
         const int* f = args.flags + static_cast<size_t>(l - 1) * args.n_row_tiles;
+        const int done = 2 * kEpiWarps * args.epoch;   // counters run on from launch to launch (no memset node between the kernels of a step)
         for (int mm = lo; mm <= hi; ++mm) {
             int v;
             unsigned spins = 0;
             long long t_start = 0;
             do {
                 asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(f + mm) : "memory");
-                if (v < 2 * kEpiWarps && (++spins & 15) == 0) {
+                if (v < done && (++spins & 15) == 0) {
                     __nanosleep(64);
                     // bounded: the dataflow needs every CTA of the grid resident (one per SM, sized from the device's SM count);
                     // if something else pins SMs for seconds, fail loudly instead of hanging the device
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                         __trap();
                     }
                 }
-            } while (v < 2 * kEpiWarps);
+            } while (v < done);
         }
         asm volatile("fence.proxy.async.global;" ::: "memory");
         if (tr_on) acc_wait += clock64() - t0w;
@@ -672,7 +675,10 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
             if (lane == 0) mbar_arrive_remote_relaxed(tempty_remote0 + acc * 8);   // TMEM reads ordered by tcgen05.wait::ld + fence
             if (op.kind == 1 && args.flags != nullptr && l + 1 < layer_end) {
                 // this warp's rows of the next layer's conv input are written: make them visible device-wide, then count the
-                // warp in (16 warps per row tile; readers: wait_inputs)
+                // warp in (16 warps per row tile; readers: wait_inputs).  The readers are TMA loads (async proxy) issued by OTHER
+                // CTAs: the generic-proxy stores are ordered against the async proxy HERE, by the threads that made them (as
+                // publish_z does for the z rows), not only by the reader's fence after its acquire
+                asm volatile("fence.proxy.async.global;" ::: "memory");
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(args.flags + static_cast<size_t>(l) * args.n_row_tiles + m) : "memory");

@@ -185,8 +185,16 @@ struct DiffusionPlan::Workspace {
     DevBuf layer_flags;              // ... and the row-tile completion counters of a multi-layer launch [L][row tiles]
     cudaGraphExec_t graph = nullptr;
     bool graph_has_mask = false;
+    cudaGraphExec_t plms_graph = nullptr;   // the PLMS loop for (plms_interval, plms_has_mask, plms_ac)
+    int plms_interval = 0;
+    bool plms_has_mask = false;
+    std::vector<float> plms_ac;
+    unsigned long long plms_nodes = 0;
+    unsigned long long last_use = 0;        // LRU stamp
+    size_t bytes = 0;
     ~Workspace() {
         if (graph) cudaGraphExecDestroy(graph);
+        if (plms_graph) cudaGraphExecDestroy(plms_graph);
     }
 };
 
@@ -338,6 +346,7 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, none, nullptr);
     launch_conv_gemm(kResTile, terms, EPI_RELU_BF16, none, nullptr);
     if (const char* np = std::getenv("BSG_NO_PAIR")) use_pair = !(np[0] == '1');
+    if (const char* ng = std::getenv("BSG_DIFF_GRAPH")) use_graphs = ng[0] == '1';   // 0: plain launches instead of captured graphs
     gate_mode = skip_mode = use_pair ? 1 : 0;
     if (const char* mc = std::getenv("BSG_MC")) {   // bit 0: gate GEMM, bit 1: skip-sum GEMM on 4-CTA clusters with multicast weights
         const int bits = std::atoi(mc);
@@ -367,10 +376,28 @@ DiffusionPlan::~DiffusionPlan() = default;
 DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
     const auto key = std::make_pair(B, T);
     auto it = ws.find(key);
-    if (it != ws.end()) return *it->second;
-    // keep at most a few shapes alive (graphs + buffers); drop everything when the table grows
-    if (ws.size() >= 4) ws.clear();
+    if (it != ws.end()) {
+        it->second->last_use = ++use_clock;
+        return *it->second;
+    }
+    // Keep a few shapes alive (buffers + captured graphs): utterance lengths vary from call to call, so evict ONE least-recently
+    // used entry at a time -- when there are more than kMaxShapes, or while the cached workspaces plus the new one (~70 KB per mel
+    // frame) would exceed the byte budget (BSG_WS_BUDGET_GB, default 48).
+    {
+        static const double budget_gb = [] { const char* e = std::getenv("BSG_WS_BUDGET_GB"); return e ? std::atof(e) : 48.0; }();
+        const size_t need = static_cast<size_t>(B) * T * 72 * 1024;
+        auto total = [&] { size_t n = 0; for (auto& kv : ws) n += kv.second->bytes; return n; };
+        while (!ws.empty() && (ws.size() >= static_cast<size_t>(kMaxShapes) || static_cast<double>(total() + need) > budget_gb * 1e9)) {
+            auto lru = ws.begin();
+            for (auto jt = ws.begin(); jt != ws.end(); ++jt)
+                if (jt->second->last_use < lru->second->last_use) lru = jt;
+            ws.erase(lru);
+        }
+    }
+    size_t free_before = 0, free_after = 0, total_mem = 0;
+    cudaMemGetInfo(&free_before, &total_mem);
     auto w = std::make_unique<Workspace>();
+    w->last_use = ++use_clock;
     const int M = cfg.in_dims, H = cfg.hidden_size, C = cfg.residual_channels;
     const size_t rows = static_cast<size_t>(B) * T;
     w->B = B;
@@ -442,6 +469,8 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
         const int n_row_tiles = B * ((T + 2 * kTileM - 1) / (2 * kTileM));
         w->layer_flags.alloc(static_cast<size_t>(cfg.residual_layers) * n_row_tiles * sizeof(int));
     }
+    cudaMemGetInfo(&free_after, &total_mem);
+    w->bytes = free_before > free_after ? free_before - free_after : 0;
     auto& ref = *w;
     ws[key] = std::move(w);
     return ref;
@@ -515,7 +544,7 @@ ConvGemmArgs DiffusionPlan::resskip_args(Workspace& w, int l, const float* lut_t
 
 // ResidualBlocks [l0, l0 + n) in one launch of the fused layer kernel (diffnet_layer.cuh): per 256-row tile the gate GEMM of both
 // channel halves + the residual GEMM; n > 1: row-tile dataflow across the layers (zero w.layer_flags before the launch)
-LayerArgs DiffusionPlan::fused_args(Workspace& w, int l0, int n, const float* lut_t) {
+LayerArgs DiffusionPlan::fused_args(Workspace& w, int l0, int n, const float* lut_t, int epoch) {
     const int C = cfg.residual_channels, L = cfg.residual_layers;
     LayerArgs a{};
     a.xa16[0] = w.m_xa[0]; a.xa16[1] = w.m_xa16_b;
@@ -538,6 +567,7 @@ LayerArgs DiffusionPlan::fused_args(Workspace& w, int l0, int n, const float* lu
     a.xa8_out[0] = w.xa8.as<uint8_t>(); a.xa8_out[1] = w.xa8_b.as<uint8_t>();
     a.lut_t = lut_t;
     a.flags = n > 1 ? w.layer_flags.as<int>() : nullptr;
+    a.epoch = epoch;
     if (const char* ab = std::getenv("BSG_ABLATE")) a.flags_ablate = std::atoi(ab);   // timing experiments only (wrong results)
     return a;
 }
@@ -578,13 +608,14 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
     cudaEvent_t e0, e1;
     B200_CUDA(cudaEventCreate(&e0));
     B200_CUDA(cudaEventCreate(&e1));
+    int epoch = 0;
+    if (which == 4) B200_CUDA(cudaMemsetAsync(w.layer_flags.p, 0, w.layer_flags.bytes, st));
     auto run = [&](int n) {
         for (int i = 0; i < n; ++i) {
             const int l = i % L;
             if (which == 4) {
                 if (l != 0) continue;
-                B200_CUDA(cudaMemsetAsync(w.layer_flags.p, 0, w.layer_flags.bytes, st));
-                launch_diffnet_layer(fused_args(w, 0, L, lut.as<float>()), st, fused_mc);
+                launch_diffnet_layer(fused_args(w, 0, L, lut.as<float>(), ++epoch), st, fused_mc);
             } else if (which == 3) launch_diffnet_layer(fused_args(w, l, 1, lut.as<float>()), st, fused_mc);
             else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
             else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
@@ -610,8 +641,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
         ConvGemmArgs a = which == 0 ? gate_args(w, 1) : (which == 1 ? resskip_args(w, 1, lut.as<float>()) : skipsum_args(w));
         a.trace = tb.as<unsigned long long>();
         if (which >= 3) {
-            if (which == 4) B200_CUDA(cudaMemsetAsync(w.layer_flags.p, 0, w.layer_flags.bytes, st));
-            LayerArgs la = which == 4 ? fused_args(w, 0, L, lut.as<float>()) : fused_args(w, 1, 1, lut.as<float>());
+            LayerArgs la = which == 4 ? fused_args(w, 0, L, lut.as<float>(), ++epoch) : fused_args(w, 1, 1, lut.as<float>());
             la.trace = tb.as<unsigned long long>();
             launch_diffnet_layer(la, st, fused_mc);
         } else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, a, st, gate_mode);
@@ -643,8 +673,14 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
 
 // One DiffNet evaluation at diffusion step t (net.py:107-130) followed by `tail`:
 //   tail == 0: posterior update of xt (p_sample), tail == 1: write eps to ws.eps
+// epoch: 1-based index of this evaluation since reset_dataflow() (the fused layer kernel's row-tile counters run on from launch to
+// launch instead of being zeroed by a memset node per step, which cut the programmatic-dependent-launch chain twice per step)
+void DiffusionPlan::reset_dataflow(Workspace& w, cudaStream_t st) {
+    if (use_fused && fused_stack) B200_CUDA(cudaMemsetAsync(w.layer_flags.p, 0, w.layer_flags.bytes, st));
+}
+
 void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail,
-                                 cudaStream_t st, float* eps_out) {
+                                 cudaStream_t st, float* eps_out, int epoch) {
     const int M = cfg.in_dims, H = cfg.hidden_size, C = cfg.residual_channels, L = cfg.residual_layers;
     const int B = w.B, T = w.T;
     const float* lut_t = lut.as<float>() + static_cast<size_t>(t) * L * C;
@@ -668,8 +704,12 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
     }
     if (use_fused && fused_stack) {
         // all ResidualBlocks in ONE launch: row tiles flow from layer to layer as soon as their three input tiles are done
-        B200_CUDA(cudaMemsetAsync(w.layer_flags.p, 0, w.layer_flags.bytes, st));
-        launch_diffnet_layer(fused_args(w, 0, L, lut_t), st, fused_mc);
+        static const bool memset_each = [] { const char* e = std::getenv("BSG_LAYER_MEMSET"); return e && e[0] == '1'; }();
+        if (memset_each) {   // round-1 behaviour (A/B experiments): zero the counters before every launch
+            B200_CUDA(cudaMemsetAsync(w.layer_flags.p, 0, w.layer_flags.bytes, st));
+            epoch = 1;
+        }
+        launch_diffnet_layer(fused_args(w, 0, L, lut_t, epoch), st, fused_mc);
         ++launches, ++g_launch_count;
     } else {
         for (int l = 0; l < L; ++l) {
@@ -759,7 +799,8 @@ void DiffusionPlan::sample(const float* cond, const float* fs2_mel, const float*
             const unsigned long long before = launches;
             B200_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
             try {
-                for (int k = 0; k < K; ++k) enqueue_step(w, K - 1 - k, k, nullptr, k == K - 1, use_mask, 0, cs);
+                reset_dataflow(w, cs);
+                for (int k = 0; k < K; ++k) enqueue_step(w, K - 1 - k, k, nullptr, k == K - 1, use_mask, 0, cs, nullptr, k + 1);
             } catch (...) {
                 cudaStreamEndCapture(cs, &g);
                 if (g) cudaGraphDestroy(g);
@@ -779,9 +820,10 @@ void DiffusionPlan::sample(const float* cond, const float* fs2_mel, const float*
         launches += graph_nodes, g_launch_count += graph_nodes;
     } else {
         const size_t per_step = rows * M;
+        reset_dataflow(w, st);
         for (int k = 0; k < K; ++k)
             enqueue_step(w, K - 1 - k, k, step_noise ? step_noise + static_cast<size_t>(k) * per_step : nullptr, k == K - 1, use_mask, 0,
-                         st);
+                         st, nullptr, k + 1);
     }
     B200_CUDA(cudaMemcpyAsync(mel_out, w.mel.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
     if (x_final) B200_CUDA(cudaMemcpyAsync(x_final, w.xt.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
@@ -835,26 +877,72 @@ void DiffusionPlan::sample_plms(const float* cond, const float* fs2_mel, const f
         ++launches, ++g_launch_count;
         B200_CUDA(cudaGetLastError());
     };
-    int n_hist = 0, head = 0;   // ring of the last noise predictions: plms_eps[(head - j) & 3] = j-th most recent
-    const int t_first = ((K - 1) / interval) * interval;
-    for (int t = t_first, it = 0; t >= 0; t -= interval, ++it) {
-        head = (head + 1) & 3;
-        float* e0 = w.plms_eps[head].as<float>();
-        enqueue_step(w, t, it, nullptr, false, false, 1, st, e0);
-        const bool last = t - interval < 0;
-        const float* e1 = w.plms_eps[(head + 3) & 3].as<float>();
-        const float* e2 = w.plms_eps[(head + 2) & 3].as<float>();
-        const float* e3 = w.plms_eps[(head + 1) & 3].as<float>();
-        if (n_hist == 0) {
-            // first iteration (:188-191): predictor step, a second evaluation at max(t - interval, 0), average
-            update(0, 0, t, e0, nullptr, nullptr, nullptr, false);
-            float* ep = w.eps.as<float>();
-            enqueue_step(w, t - interval > 0 ? t - interval : 0, it, nullptr, false, false, 1, st, ep);
-            update(1, 1, t, e0, ep, nullptr, nullptr, last);
-        } else {
-            update(n_hist + 1 > 4 ? 4 : n_hist + 1, 1, t, e0, e1, e2, e3, last);
+    // the iterations: deterministic after the start, so the whole loop (K/interval + 1 denoiser evaluations and as many updates) is
+    // captured once per (shape, interval, mask, schedule) and replayed, like the ancestral sampler's K steps
+    auto body = [&](cudaStream_t s) {
+        cudaStream_t saved = st;
+        st = s;
+        reset_dataflow(w, s);
+        int epoch = 0;
+        int n_hist = 0, head = 0;   // ring of the last noise predictions: plms_eps[(head - j) & 3] = j-th most recent
+        const int t_first = ((K - 1) / interval) * interval;
+        for (int t = t_first, it = 0; t >= 0; t -= interval, ++it) {
+            head = (head + 1) & 3;
+            float* e0 = w.plms_eps[head].as<float>();
+            enqueue_step(w, t, it, nullptr, false, false, 1, s, e0, ++epoch);
+            const bool last = t - interval < 0;
+            const float* e1 = w.plms_eps[(head + 3) & 3].as<float>();
+            const float* e2 = w.plms_eps[(head + 2) & 3].as<float>();
+            const float* e3 = w.plms_eps[(head + 1) & 3].as<float>();
+            if (n_hist == 0) {
+                // first iteration (:188-191): predictor step, a second evaluation at max(t - interval, 0), average
+                update(0, 0, t, e0, nullptr, nullptr, nullptr, false);
+                float* ep = w.eps.as<float>();
+                enqueue_step(w, t - interval > 0 ? t - interval : 0, it, nullptr, false, false, 1, s, ep, ++epoch);
+                update(1, 1, t, e0, ep, nullptr, nullptr, last);
+            } else {
+                update(n_hist + 1 > 4 ? 4 : n_hist + 1, 1, t, e0, e1, e2, e3, last);
+            }
+            if (n_hist < 3) ++n_hist;
         }
-        if (n_hist < 3) ++n_hist;
+        st = saved;
+    };
+    if (use_graphs) {
+        const std::vector<float> ac(alphas_cumprod, alphas_cumprod + cfg.timesteps);
+        const bool has_mask = mel2ph != nullptr;
+        if (w.plms_graph && (w.plms_interval != interval || w.plms_has_mask != has_mask || w.plms_ac != ac)) {
+            cudaGraphExecDestroy(w.plms_graph);
+            w.plms_graph = nullptr;
+        }
+        if (!w.plms_graph) {
+            cudaStream_t cs;
+            B200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            const unsigned long long before = launches;
+            B200_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            try {
+                body(cs);
+            } catch (...) {
+                cudaStreamEndCapture(cs, &g);
+                if (g) cudaGraphDestroy(g);
+                cudaStreamDestroy(cs);
+                throw;
+            }
+            B200_CUDA(cudaStreamEndCapture(cs, &g));
+            w.plms_nodes = launches - before;
+            launches = before;
+            g_launch_count -= w.plms_nodes;
+            B200_CUDA(cudaGraphInstantiate(&w.plms_graph, g, 0));
+            cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            w.plms_interval = interval;
+            w.plms_has_mask = has_mask;
+            w.plms_ac = ac;
+        }
+        B200_CUDA(cudaGraphLaunch(w.plms_graph, st));
+        launches += w.plms_nodes, g_launch_count += w.plms_nodes;
+    } else {
+        body(st);
     }
     B200_CUDA(cudaMemcpyAsync(mel_out, w.mel.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
     if (x_final) B200_CUDA(cudaMemcpyAsync(x_final, w.xt.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
@@ -877,7 +965,8 @@ void DiffusionPlan::denoise(const float* spec, int t, const float* cond, int B, 
     launches += 2, g_launch_count += 2;
     B200_CUDA(cudaGetLastError());
     precompute_cond(w, st);
-    enqueue_step(w, t, 0, nullptr, false, false, 1, st);
+    reset_dataflow(w, st);
+    enqueue_step(w, t, 0, nullptr, false, false, 1, st, nullptr, 1);
     B200_CUDA(cudaMemcpyAsync(eps_out, w.eps.p, rows * M * 4, cudaMemcpyDeviceToDevice, st));
 }
 

@@ -1,9 +1,12 @@
 // Instantiations + host dispatcher of conv_gemm_kernel, and TMA tensor-map encoding.
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "runtime.h"
 #include "diffnet_layer.cuh"
+#include "resblock_fused.cuh"
 
 namespace b200 {
 
@@ -41,12 +44,50 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
     return make_tmap_ex(base, bytes ? 1 : 0, 128, rank, dims, strides_bytes, box);
 }
 
+// SM count of the current device (cached per device; plans of different devices may live in one process)
 int device_sm_count() {
-    int dev = 0, n = 0;
+    static std::mutex mu;
+    static int cache[64] = {0};
+    int dev = 0;
     B200_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+    int n = 0;
     B200_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < 64) cache[dev] = n;
     return n;
 }
+
+namespace {
+// How many clusters of `cluster` CTAs of `kern` can be co-resident on the current device (cached per device and kernel): the
+// persistent kernels size their grids from it.  On a whole B200 it is SMs / 2 for CTA pairs and 33 for 4-CTA clusters; it is
+// smaller when the context only owns part of the device (MPS active-thread percentage, green contexts).
+template <class K>
+int max_active_clusters(K kern, int cluster, int threads, int smem_bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, int> cache;   // (device, kernel) -> clusters
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(dev, reinterpret_cast<const void*>(kern));
+    const auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(cluster * 128);
+    q.blockDim = dim3(threads);
+    q.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute qa;
+    qa.id = cudaLaunchAttributeClusterDimension;
+    qa.val.clusterDim.x = cluster; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
+    q.attrs = &qa;
+    q.numAttrs = 1;
+    int n = 0;
+    B200_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+    B200_CHECK(n > 0, "no cluster of this kernel fits on the device");
+    cache[key] = n;
+    return n;
+}
+}  // namespace
 
 namespace {
 
@@ -63,28 +104,14 @@ void launch_inst(const ConvGemmArgs& args, cudaStream_t stream) {
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal); });
     B200_CUDA(attr_err);
-    static int sms = 0;
-    if (sms == 0) sms = device_sm_count();
+    const int sms = device_sm_count();
     if (args.num_tiles > 0)
         B200_CHECK(args.a_rows >= kTileM && args.a_rows <= S::kASlotRows && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
     const int pairs = sms / 2;
     int grid = PAIR ? 2 * (args.num_tiles < pairs ? args.num_tiles : pairs) : (args.num_tiles < sms ? args.num_tiles : sms);
     if (MC) {
         // clusters of four CTAs: the GPCs cannot host sms/4 of them at once -- ask the driver (33 on B200)
-        static int max_clusters = 0;
-        if (max_clusters == 0) {
-            cudaLaunchConfig_t q{};
-            q.gridDim = dim3(4 * 64);
-            q.blockDim = dim3(kGemmThreads);
-            q.dynamicSmemBytes = S::kTotal;
-            cudaLaunchAttribute qa;
-            qa.id = cudaLaunchAttributeClusterDimension;
-            qa.val.clusterDim.x = 4; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
-            q.attrs = &qa;
-            q.numAttrs = 1;
-            B200_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q));
-            B200_CHECK(max_clusters > 0, "no 4-CTA cluster fits on this device");
-        }
+        const int max_clusters = max_active_clusters(kern, 4, kGemmThreads, S::kTotal);
         const int units = ((args.B * args.tiles_per_batch + 1) / 2) * args.n_tiles_n;
         grid = 4 * (units < max_clusters ? units : max_clusters);
     }
@@ -125,27 +152,11 @@ static void launch_layer_inst(const LayerArgs& args, cudaStream_t stream) {
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LayerSmem::kTotal); });
     B200_CUDA(attr_err);
-    static int sms = 0;
-    if (sms == 0) sms = device_sm_count();
     constexpr int kCtas = MC ? 4 : 2;
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
-        if (MC) {
-            cudaLaunchConfig_t q{};
-            q.gridDim = dim3(4 * 64);
-            q.blockDim = dim3(kLayerThreads);
-            q.dynamicSmemBytes = LayerSmem::kTotal;
-            cudaLaunchAttribute qa;
-            qa.id = cudaLaunchAttributeClusterDimension;
-            qa.val.clusterDim.x = 4; qa.val.clusterDim.y = 1; qa.val.clusterDim.z = 1;
-            q.attrs = &qa;
-            q.numAttrs = 1;
-            B200_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q));
-            B200_CHECK(max_clusters > 0, "no 4-CTA cluster of the fused layer kernel fits on this device");
-        } else {
-            max_clusters = sms / 2;
-        }
-    }
+    // The layer-to-layer dataflow of a multi-layer launch makes CTAs wait for rows other CTAs of the grid produce: every CTA of
+    // the grid must be resident.  The grid is therefore sized from what the driver says fits on THIS context's share of the device,
+    // and the launch is cooperative (below), which makes the scheduler place the whole grid or nothing.
+    const int max_clusters = max_active_clusters(kern, kCtas, kLayerThreads, LayerSmem::kTotal);
     if (args.n_row_tiles <= 0) return;
     B200_CHECK(args.n_layers == 1 || args.flags != nullptr, "a multi-layer launch needs the row-tile completion counters");
     B200_CHECK(args.a_rows >= kTileM && args.a_rows * 128 <= LayerSmem::kASlotBytes && args.a_rows % 8 == 0, "A halo box does not fit the shared-memory slot");
@@ -155,9 +166,17 @@ static void launch_layer_inst(const LayerArgs& args, cudaStream_t stream) {
     cfg.blockDim = dim3(kLayerThreads);
     cfg.dynamicSmemBytes = LayerSmem::kTotal;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     int na = 0;
-    if (use_pdl()) {
+    // co-residency guarantee for the cross-CTA waits: a cooperative launch is only scheduled when ALL its CTAs fit at
+    // once, so a concurrent kernel of another stream / plan can delay this launch but cannot strand half of its grid.
+    // (BSG_LAYER_COOP=0: plain launch with the PDL attribute, as in round 1 -- safe only on an otherwise idle device.)
+    static const bool coop = [] { const char* e = std::getenv("BSG_LAYER_COOP"); return !(e && e[0] == '0'); }();
+    if (coop && args.n_layers > 1) {
+        attr[na].id = cudaLaunchAttributeCooperative;
+        attr[na].val.cooperative = 1;
+        ++na;
+    } else if (use_pdl()) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
@@ -175,6 +194,55 @@ static void launch_layer_inst(const LayerArgs& args, cudaStream_t stream) {
 void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream, bool mc) {
     if (mc) launch_layer_inst<1>(args, stream);
     else launch_layer_inst<0>(args, stream);
+}
+
+// One fused ResBlock1 iteration (resblock_fused.cuh): persistent CTAs over the output-row tiles.  args.num_tiles == 0 only sets the
+// kernel attribute up (outside of any stream capture).
+template <int C>
+static void launch_resblock_inst(const ResblockArgs& args, cudaStream_t stream) {
+    using S = ResblockSmem<C>;
+    auto kern = resblock_iter_kernel<C>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal); });
+    B200_CUDA(attr_err);
+    if (args.num_tiles <= 0) return;
+    B200_CHECK(args.a_rows % 8 == 0 && args.a_rows * 128 <= S::kASlotBytes, "halo box does not fit the shared-memory slot");
+    B200_CHECK(args.ntaps >= 1 && args.ntaps <= kMaxTaps && (args.ntaps & 1), "odd kernel size <= 11 expected");
+    B200_CHECK(args.w_slots >= 2 && args.w_slots <= S::kWSlots, "weight ring depth");
+    const int sms = device_sm_count();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(args.num_tiles < sms ? args.num_tiles : sms);
+    cfg.blockDim = dim3(kRbThreads);
+    cfg.dynamicSmemBytes = S::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    int na = 0;
+    if (use_pdl()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+    B200_CUDA(cudaGetLastError());
+}
+void launch_resblock_iter(int channels, const ResblockArgs& args, cudaStream_t stream) {
+    switch (channels) {
+        case 32: return launch_resblock_inst<32>(args, stream);
+        case 64: return launch_resblock_inst<64>(args, stream);
+        case 128: return launch_resblock_inst<128>(args, stream);
+        default: throw Error("fused ResBlock kernel: unsupported channel count " + std::to_string(channels));
+    }
+}
+int resblock_weight_slots(int channels) {
+    switch (channels) {
+        case 32: return ResblockSmem<32>::kWSlots;
+        case 64: return ResblockSmem<64>::kWSlots;
+        case 128: return ResblockSmem<128>::kWSlots;
+        default: return 0;
+    }
 }
 
 int conv_gemm_weight_slots(int n_tile, int terms) {

@@ -22,6 +22,7 @@
 #include <memory>
 
 #include "plans.h"
+#include "resblock_fused.cuh"
 
 namespace b200 {
 
@@ -55,12 +56,25 @@ __device__ __forceinline__ float rad_of(float f0, int h, float sr) {
 }
 // One warp per (utterance, harmonic): 32 frames per iteration, inclusive shuffle scan of the 64-bit increments plus a running carry.
 // Integer addition is associative, so the result is bit-identical to a serial scan.
-__global__ void nsf_phase_kernel(const float* __restrict__ f0, const float* __restrict__ rand_ini, int B, int T, int hop, int dim,
-                                 float sr, unsigned long long* __restrict__ phase0) {
+// rand_ini == nullptr (production): the initial phase of every harmonic h >= 1 is drawn U[0,1) on the device from the Philox key
+// (torch.rand(B, dim) at source.py:54; the fundamental gets none, :56) -- 24 random bits, so the value is exactly representable.
+__global__ void nsf_phase_kernel(const float* __restrict__ f0, const float* __restrict__ rand_ini,
+                                 const unsigned long long* __restrict__ seed_ptr, int B, int T, int hop, int dim, float sr,
+                                 unsigned long long* __restrict__ phase0) {
     const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (idx >= B * dim) return;
     const int b = idx / dim, h = idx % dim;
-    float ri = (h == 0 || rand_ini == nullptr) ? 0.0f : rand_ini[b * dim + h];   // rand_ini[:,0] = 0 (:56)
+    float ri = 0.0f;                                                              // rand_ini[:,0] = 0 (:56)
+    if (h != 0) {
+        if (rand_ini != nullptr) {
+            ri = rand_ini[b * dim + h];
+        } else {
+            const unsigned long long seed = __ldg(seed_ptr);
+            const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), 0u, 0x1417u, 0x5eedu),
+                                          make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+            ri = static_cast<float>(r.x >> 8) * 5.9604644775390625e-08f;          // [0, 1)
+        }
+    }
     ri = ri - floorf(ri);
     unsigned long long carry = turn_fixed(ri);
     const float* f = f0 + static_cast<long long>(b) * T;
@@ -185,7 +199,8 @@ template <int C>
 __global__ void __launch_bounds__(256) noise_branch_v2_kernel(const float* __restrict__ har, const float* __restrict__ w,
                                                               const float* __restrict__ bias, int B, long long Lout, long long Lhar, int ksz,
                                                               int stride, int pad, int has_source, float* __restrict__ x,
-                                                              __nv_bfloat16* __restrict__ act, int act_pitch) {
+                                                              __nv_bfloat16* __restrict__ act, int act_pitch, int out_f16) {
+    // out_f16: the activation is stored as fp16 (the fused ResBlock kernel's 16-bit stream: the ONLY copy of x) and x is not written back
     constexpr int LPR = C >= 128 ? 32 : C / 4;   // lanes per row
     constexpr int RPW = 32 / LPR;                // rows per warp and group
     constexpr int V = C / (LPR * 4);             // float4s per lane
@@ -276,12 +291,17 @@ __global__ void __launch_bounds__(256) noise_branch_v2_kernel(const float* __res
                     const int c = (j * LPR + sub) * 4;
                     const float4 o4 = make_float4(xv[u][j].x + v[u][j][0], xv[u][j].y + v[u][j][1], xv[u][j].z + v[u][j][2],
                                                   xv[u][j].w + v[u][j][3]);
-                    *reinterpret_cast<float4*>(x + row[u] * C + c) = o4;
-                    const __nv_bfloat162 a0 = __floats2bfloat162_rn(o4.x > 0.0f ? o4.x : o4.x * kLrelu, o4.y > 0.0f ? o4.y : o4.y * kLrelu);
-                    const __nv_bfloat162 a1 = __floats2bfloat162_rn(o4.z > 0.0f ? o4.z : o4.z * kLrelu, o4.w > 0.0f ? o4.w : o4.w * kLrelu);
                     uint2 pk;
-                    pk.x = *reinterpret_cast<const uint32_t*>(&a0);
-                    pk.y = *reinterpret_cast<const uint32_t*>(&a1);
+                    if (out_f16) {
+                        pk.x = pack_h2(lrelu_f(o4.x, kLrelu), lrelu_f(o4.y, kLrelu));
+                        pk.y = pack_h2(lrelu_f(o4.z, kLrelu), lrelu_f(o4.w, kLrelu));
+                    } else {
+                        *reinterpret_cast<float4*>(x + row[u] * C + c) = o4;
+                        const __nv_bfloat162 a0 = __floats2bfloat162_rn(o4.x > 0.0f ? o4.x : o4.x * kLrelu, o4.y > 0.0f ? o4.y : o4.y * kLrelu);
+                        const __nv_bfloat162 a1 = __floats2bfloat162_rn(o4.z > 0.0f ? o4.z : o4.z * kLrelu, o4.w > 0.0f ? o4.w : o4.w * kLrelu);
+                        pk.x = *reinterpret_cast<const uint32_t*>(&a0);
+                        pk.y = *reinterpret_cast<const uint32_t*>(&a1);
+                    }
                     *reinterpret_cast<uint2*>(act + row[u] * act_pitch + c) = pk;
                 }
             }
@@ -291,7 +311,9 @@ __global__ void __launch_bounds__(256) noise_branch_v2_kernel(const float* __res
 
 // wav = tanh( conv_post( lrelu(x, 0.01) ) )   hifigan.py:169-171 ; conv_post: Conv1d(C -> 1, k, padding (k-1)/2), C == 32.
 // A block stages blockDim + k - 1 rows of lrelu(x) in shared memory (pitch 33: conflict-free) with coalesced loads.
-__global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// HALF_IN: x is the fused path's fp16 tensor with leaky_relu(0.01) already applied by the producing epilogue.
+template <bool HALF_IN>
+__global__ void __launch_bounds__(256) conv_post_kernel(const void* __restrict__ xin, const float* __restrict__ w,
                                                         const float* __restrict__ bias, int B, long long L, int ksz,
                                                         float* __restrict__ wav) {
     constexpr int C = 32, P = 33;
@@ -308,8 +330,12 @@ __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict_
         const long long g = g0 + r - half;          // flattened source row
         float v = 0.0f;
         if (g >= 0 && g < total) {
-            v = x[g * C + lane];
-            v = v > 0.0f ? v : v * 0.01f;
+            if (HALF_IN) {
+                v = __half2float(reinterpret_cast<const __half*>(xin)[g * C + lane]);
+            } else {
+                v = reinterpret_cast<const float*>(xin)[g * C + lane];
+                v = v > 0.0f ? v : v * 0.01f;
+            }
         }
         xs[r * P + lane] = v;
     }
@@ -344,6 +370,8 @@ struct HifiganPlan::Workspace {
     DevBuf in_mel, in_f0, out_wav;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [has_src]
     unsigned long long graph_nodes[2] = {0, 0};
+    unsigned long long last_use = 0;                 // LRU stamp
+    size_t bytes = 0;
     ~Workspace() {
         for (auto& g : graph)
             if (g) cudaGraphExecDestroy(g);
@@ -440,11 +468,28 @@ HifiganPlan::HifiganPlan(const bsg_hifigan_config& c, const float* w, size_t n_w
             upload(s.noise_b, take(p, s.cout));
         }
     }
+    if (const char* nf = std::getenv("BSG_VOC_FUSE")) fuse_resblocks = nf[0] == '1';
+    // a [C][C][k] conv weight -> fp16 K-major [C][k * C], taps packed densely (the fused ResBlock kernel's operand)
+    auto pack_half = [&](HalfConv& hc, const std::vector<float>& wt, int C, int k) {
+        std::vector<uint16_t> m(static_cast<size_t>(C) * k * C);
+        for (int o = 0; o < C; ++o)
+            for (int ci = 0; ci < C; ++ci)
+                for (int kk = 0; kk < k; ++kk)
+                    m[(static_cast<size_t>(o) * k + kk) * C + ci] = f32_to_f16_bits(wt[(static_cast<size_t>(o) * C + ci) * k + kk]);
+        upload(hc.w, m);
+        hc.map = make_w_tmap(hc.w.p, C, k * C, C);
+    };
     for (int i = 0; i < c.num_upsamples; ++i) {
         Stage& s = stages[i];
         const int C = s.cout;
         s.convs1.resize(c.num_kernels * c.num_dilations);
         s.convs2.resize(c.num_kernels * c.num_dilations);
+        // fused ResBlock iterations: channel counts the kernel is instantiated for, dilated halo within its shared-memory slab
+        s.fused = fuse_resblocks && (C == 32 || C == 64 || C == 128);
+        for (int j = 0; j < c.num_kernels && s.fused; ++j)
+            for (int m = 0; m < c.num_dilations; ++m)
+                if (128 + (c.resblock_kernel_sizes[j] - 1) * c.resblock_dilation_sizes[j][m] > 184) s.fused = false;
+        if (s.fused) { s.h1.resize(s.convs1.size()); s.h2.resize(s.convs2.size()); }
         for (int j = 0; j < c.num_kernels; ++j) {
             const int k = c.resblock_kernel_sizes[j];
             B200_CHECK(k % 2 == 1 && k <= kMaxTaps, "resblock kernel size must be odd and <= 11");
@@ -453,12 +498,14 @@ HifiganPlan::HifiganPlan(const bsg_hifigan_config& c, const float* w, size_t n_w
                 auto wt = take(p, static_cast<size_t>(C) * C * k);
                 auto bs = take(p, C);
                 pack_conv(s.convs1[j * c.num_dilations + m], wt, bs, C, C, k, c.resblock_dilation_sizes[j][m]);
+                if (s.fused) pack_half(s.h1[j * c.num_dilations + m], wt, C, k);
             }
             for (int m = 0; m < c.num_dilations; ++m) {
                 need(static_cast<size_t>(C) * C * k + C);
                 auto wt = take(p, static_cast<size_t>(C) * C * k);
                 auto bs = take(p, C);
                 pack_conv(s.convs2[j * c.num_dilations + m], wt, bs, C, C, k, 1);
+                if (s.fused) pack_half(s.h2[j * c.num_dilations + m], wt, C, k);
             }
         }
     }
@@ -483,6 +530,9 @@ HifiganPlan::HifiganPlan(const bsg_hifigan_config& c, const float* w, size_t n_w
     if (const char* nr = std::getenv("BSG_ROWS_EPI")) rows_epi = nr[0] == '1';
     if (const char* nm = std::getenv("BSG_ROWS_RMW")) rows_rmw = nm[0] == '1';
     if (pair_mode) for (int nt : {256, 128}) launch_conv_gemm(nt, 1, EPI_BIAS_ACT, none, nullptr, 1);
+    ResblockArgs rnone{};
+    for (const Stage& s : stages)
+        if (s.fused) launch_resblock_iter(s.cout, rnone, nullptr);
 }
 
 HifiganPlan::~HifiganPlan() = default;
@@ -490,9 +540,26 @@ HifiganPlan::~HifiganPlan() = default;
 HifiganPlan::Workspace& HifiganPlan::workspace(int B, int T) {
     const auto key = std::make_pair(B, T);
     auto it = ws.find(key);
-    if (it != ws.end()) return *it->second;
-    ws.clear();   // one shape at a time: the stage buffers are large
+    if (it != ws.end()) {
+        it->second->last_use = ++use_clock;
+        return *it->second;
+    }
+    // the stage buffers are large (~20 KB per mel frame): keep a few shapes, evict the least recently used one at a time
+    {
+        static const double budget_gb = [] { const char* e = std::getenv("BSG_WS_BUDGET_GB"); return e ? std::atof(e) : 48.0; }();
+        const size_t need = static_cast<size_t>(B) * T * 110 * 1024;
+        auto total = [&] { size_t n = 0; for (auto& kv : ws) n += kv.second->bytes; return n; };
+        while (!ws.empty() && (ws.size() >= static_cast<size_t>(kMaxShapes) || static_cast<double>(total() + need) > budget_gb * 1e9)) {
+            auto lru = ws.begin();
+            for (auto jt = ws.begin(); jt != ws.end(); ++jt)
+                if (jt->second->last_use < lru->second->last_use) lru = jt;
+            ws.erase(lru);
+        }
+    }
+    size_t free_before = 0, free_after = 0, total_mem = 0;
+    cudaMemGetInfo(&free_before, &total_mem);
     auto w = std::make_unique<Workspace>();
+    w->last_use = ++use_clock;
     w->B = B;
     w->T = T;
     const size_t BT = static_cast<size_t>(B) * T;
@@ -517,6 +584,8 @@ HifiganPlan::Workspace& HifiganPlan::workspace(int B, int T) {
     w->A0.alloc(max_b16);
     w->Ar.alloc(max_b16);
     w->Tb.alloc(max_b16);
+    cudaMemGetInfo(&free_after, &total_mem);
+    w->bytes = free_before > free_after ? free_before - free_after : 0;
     auto& ref = *w;
     ws[key] = std::move(w);
     return ref;
@@ -526,8 +595,8 @@ void HifiganPlan::run_source(Workspace& w, const float* f0, const float* rand_in
                              int T, cudaStream_t st) {
     const int dim = cfg.harmonic_num + 1;
     B200_CHECK(cfg.use_pitch_embed, "this generator was built without the NSF source (use_pitch_embed = 0)");
-    nsf_phase_kernel<<<(B * dim * 32 + 255) / 256, 256, 0, st>>>(f0, rand_ini, B, T, hop, dim, static_cast<float>(cfg.audio_sample_rate),
-                                                         w.phase0.as<unsigned long long>());
+    nsf_phase_kernel<<<(B * dim * 32 + 255) / 256, 256, 0, st>>>(f0, rand_ini, d_seed.as<unsigned long long>(), B, T, hop, dim,
+                                                                 static_cast<float>(cfg.audio_sample_rate), w.phase0.as<unsigned long long>());
     const long long n = static_cast<long long>(B) * T * hop;
     nsf_source_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(f0, w.phase0.as<unsigned long long>(), src_noise,
                                                                               d_seed.as<unsigned long long>(), src_lin.as<float>(), B, T,
@@ -669,12 +738,14 @@ void HifiganPlan::enqueue(Workspace& w, const float* mel, const float* f0, const
             const float* nb = has_src ? s.noise_b.as<float>() : nullptr;
             const long long Lhar = static_cast<long long>(T) * hop;
             const int lpr = C >= 128 ? 32 : C / 4;
-            const bool v2 = noise_v2 && s.noise_k <= lpr && Cp % 4 == 0 && C <= 512;
+            const bool v2 = (noise_v2 || s.fused) && s.noise_k <= lpr && Cp % 4 == 0 && C <= 512;
+            B200_CHECK(v2 || !s.fused, "the fused ResBlock path needs the row-group noise-branch kernel (kernel size <= lanes per row)");
 #define B200_NOISE(CPL)                                                                                                                 \
     do {                                                                                                                                \
         if (v2)                                                                                                                         \
             noise_branch_v2_kernel<CPL * 32><<<blocks, 256, sm_bytes, st>>>(w.har.as<float>(), nw, nb, B, Lout, Lhar, s.noise_k,        \
-                                                                           s.noise_stride, s.noise_pad, has_src ? 1 : 0, w.X0.as<float>(), A0, Cp); \
+                                                                           s.noise_stride, s.noise_pad, has_src ? 1 : 0, w.X0.as<float>(), A0, Cp, \
+                                                                           s.fused ? 1 : 0);                                            \
         else                                                                                                                            \
             noise_branch_kernel<CPL><<<blocks, 256, sm_bytes, st>>>(w.har.as<float>(), nw, nb, B, Lout, Lhar, s.noise_k, s.noise_stride, \
                                                                    s.noise_pad, has_src ? 1 : 0, w.X0.as<float>(), A0, Cp);              \
@@ -692,6 +763,52 @@ void HifiganPlan::enqueue(Workspace& w, const float* mel, const float* f0, const
             B200_CUDA(cudaGetLastError());
         }
         // ---- MRF: sum_j ResBlock1_j(x) / num_kernels (hifigan.py:161-168, :54-61)
+        if (s.fused) {
+            // One kernel per ResBlock iteration on the 16-bit single-tensor stream (resblock_fused.cuh): A0 = fp16 lrelu(x) is the stage
+            // input of all three ResBlocks, Ar / Tb ping-pong between iterations, S (viewed as fp16) accumulates the MRF sum; the last
+            // iteration of the last ResBlock writes the next stage's transposed-conv operand (bf16 lrelu 0.1) or conv_post's input
+            // (fp16 lrelu 0.01, hifigan.py:169).
+            __half* pp[2] = {reinterpret_cast<__half*>(Ar), reinterpret_cast<__half*>(Tb)};
+            for (int j = 0; j < nk; ++j) {
+                const int k = cfg.resblock_kernel_sizes[j];
+                for (int m = 0; m < nd; ++m) {
+                    const int d = s.convs1[j * nd + m].dilation;
+                    ResblockArgs a{};
+                    const __half* in = m == 0 ? reinterpret_cast<const __half*>(A0) : pp[(m - 1) & 1];
+                    a.B = B; a.L = static_cast<int>(Lout);
+                    a.ntaps = k; a.dil = d;
+                    a.V = kTileM - (k - 1);
+                    a.a_rows = ((kTileM + (k - 1) * d) + 7) / 8 * 8;
+                    a.tiles_per_batch = (a.L + a.V - 1) / a.V;
+                    a.num_tiles = B * a.tiles_per_batch;
+                    a.amap = make_act_tmap(in, B, a.L, C, C, a.a_rows);
+                    a.w1map = s.h1[j * nd + m].map;
+                    a.w2map = s.h2[j * nd + m].map;
+                    a.bias1 = s.convs1[j * nd + m].bias.as<float>();
+                    a.bias2 = s.convs2[j * nd + m].bias.as<float>();
+                    a.a_in = in;
+                    a.sum = w.S.as<__half>();
+                    a.c0 = 1.0f / static_cast<float>(nk);
+                    if (m + 1 < nd) {
+                        a.mode = 0;
+                        a.out = pp[m & 1];
+                    } else if (j + 1 < nk) {
+                        a.mode = j == 0 ? 1 : 2;
+                    } else {
+                        a.mode = 3;
+                        if (nk == 1) { a.mode = 3; }
+                        a.out = last_stage ? static_cast<void*>(w.X0.p) : static_cast<void*>(w.upin[up_sel ^ 1].p);
+                        a.out_bf16 = last_stage ? 0 : 1;
+                        a.slope_out = last_stage ? 0.01f : kLrelu;
+                    }
+                    a.w_slots = resblock_weight_slots(C);
+                    const int n_wt = C == 32 ? (k + 1) / 2 : k * (C / kBlockK);
+                    a.w_resident = 2 * n_wt <= a.w_slots ? 1 : 0;
+                    launch_resblock_iter(C, a, st);
+                    launches += 1, g_launch_count += 1;
+                }
+            }
+        } else
         for (int j = 0; j < nk; ++j) {
             const int k = cfg.resblock_kernel_sizes[j];
             for (int m = 0; m < nd; ++m) {
@@ -738,8 +855,12 @@ void HifiganPlan::enqueue(Workspace& w, const float* mel, const float* f0, const
         const int C = stages.back().cout;
         const long long n = static_cast<long long>(B) * Lcur;
         B200_CHECK(C == 32, "conv_post kernel is specialised for 32 input channels");
-        conv_post_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, (7 * 32 + (256 + 6) * 33) * sizeof(float), st>>>(
-            w.S.as<float>(), post_w.as<float>(), post_b.as<float>(), B, Lcur, 7, wav);
+        if (stages.back().fused)
+            conv_post_kernel<true><<<static_cast<unsigned>((n + 255) / 256), 256, (7 * 32 + (256 + 6) * 33) * sizeof(float), st>>>(
+                w.X0.p, post_w.as<float>(), post_b.as<float>(), B, Lcur, 7, wav);
+        else
+            conv_post_kernel<false><<<static_cast<unsigned>((n + 255) / 256), 256, (7 * 32 + (256 + 6) * 33) * sizeof(float), st>>>(
+                w.S.p, post_w.as<float>(), post_b.as<float>(), B, Lcur, 7, wav);
         launches += 1, g_launch_count += 1;
         B200_CUDA(cudaGetLastError());
     }

@@ -53,16 +53,19 @@ private:
     ConvGemmArgs gate_args(Workspace& w, int l);
     ConvGemmArgs resskip_args(Workspace& w, int l, const float* lut_t);
     ConvGemmArgs skipsum_args(Workspace& w);
-    struct LayerArgs fused_args(Workspace& w, int l0, int n, const float* lut_t);
+    struct LayerArgs fused_args(Workspace& w, int l0, int n, const float* lut_t, int epoch = 1);
+    void reset_dataflow(Workspace& w, cudaStream_t st);
     void enqueue_step(Workspace& w, int t, int k_exec, const float* noise_k, bool last, bool use_mask, int tail, cudaStream_t st,
-                      float* eps_out = nullptr);
+                      float* eps_out = nullptr, int epoch = 1);
 
     std::vector<Layer> layers;
     PackedW inproj, outproj, skipall;   // skipall: skip_projection x the skip halves of all output projections, [C][L*C]
     DevBuf inproj_bias, outproj_bias, skipall_bias;
     DevBuf lut, d_spec_min, d_spec_max, d_seed;
     std::vector<StepCoef> sched;
+    static constexpr int kMaxShapes = 6;   // cached (B, T) workspaces, least recently used evicted first
     std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
+    unsigned long long use_clock = 0;
     unsigned long long graph_nodes = 0;
 };
 
@@ -83,6 +86,7 @@ public:
     bool noise_v2 = true;    // row-group layout of the noise-branch kernel (BSG_VOC_NOISE_V2=0: one warp per row)
     bool rows_epi = true;    // row-per-thread write-only epilogue with 256-bit stores (BSG_ROWS_EPI=0: transposing epilogue everywhere)
     bool rows_rmw = true;    // ... also for the read-modify-write epilogues, with 256-bit loads (BSG_ROWS_RMW=0: transposing epilogue for those)
+    bool fuse_resblocks = true;   // stages with <= 128 channels: one kernel per ResBlock iteration (BSG_VOC_FUSE=0: two conv launches, fp32 stream)
     unsigned long long launches = 0;
 
 private:
@@ -92,8 +96,14 @@ private:
         DevBuf bias;
         int cin = 0, cout = 0, k = 1, dilation = 1;
     };
+    struct HalfConv {        // one convolution of a fused ResBlock iteration: fp16 weights [Cout][k * Cin] K-major (taps packed densely)
+        DevBuf w;
+        CUtensorMap map;     // box = 64 K-columns x Cout rows
+    };
     struct Stage {
         int cin = 0, cout = 0, rate = 1, ksize = 1;
+        bool fused = false;                        // ResBlock iterations on resblock_iter_kernel (C <= 128), 16-bit single-tensor stream
+        std::vector<HalfConv> h1, h2;              // fp16 copies of convs1 / convs2 for the fused kernel
         std::vector<Conv> up_phase;                // one 2-tap (generally ceil(k/u)-tap) conv per output phase
         std::vector<std::vector<int>> up_shifts;   // row shifts of each phase's taps
         DevBuf up_bias;
@@ -111,7 +121,9 @@ private:
     std::vector<Stage> stages;
     DevBuf post_w, post_b, src_lin;   // conv_post weights [7][C] f32, bias; l_linear weight[9]+bias
     DevBuf d_seed;
+    static constexpr int kMaxShapes = 3;   // cached (B, T) workspaces (several GB each at batch sizes), least recently used evicted first
     std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
+    unsigned long long use_clock = 0;
 };
 
 class PitchExtractorPlan {

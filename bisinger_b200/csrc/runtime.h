@@ -151,6 +151,12 @@ void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, 
 struct LayerArgs;
 void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream, bool mc = false);
 
+// One fused HiFi-GAN ResBlock1 iteration (resblock_fused.cuh) for channels in {32, 64, 128}; args.num_tiles == 0 only sets the kernel
+// attributes up.  resblock_weight_slots: weight tiles (C rows x 64 K-columns) its shared-memory weight area holds.
+struct ResblockArgs;
+void launch_resblock_iter(int channels, const ResblockArgs& args, cudaStream_t stream);
+int resblock_weight_slots(int channels);
+
 // fills the tile-geometry fields of args from (B, L, N_total, n_tile)
 inline void set_geometry(ConvGemmArgs& a, int B, int L, int n_total, int n_tile, bool pair = false) {
     a.B = B;

@@ -117,8 +117,42 @@ class B200DiffNet(nn.Module):
         return self._standalone_plan.denoise(spec, t, cond.transpose(1, 2))
 
 
+FP16_SAFE_BOUND = 3.0e4   # fp16 holds +-65504: the residual stream's worst-case bound must stay below half of that
+
+
+def fp16_activation_bound(denoise_fn: "B200DiffNet", x_abs_max: float = 16.0) -> float:
+    """Worst-case bound on the magnitude of what the fp16x2 mode stores as fp16: the residual stream ``x + d`` (the dilated conv's
+    input) and ``z``.  ``z = sigmoid * tanh`` lies in [-1, 1]; the stream obeys ``x' = (x + W_res z + b) / sqrt(2)``
+    (usr/diff/net.py:76-78), so ``|x'| <= (|x| + max_row(sum|W_res| + |b|)) / sqrt(2)``, starting from
+    ``|relu(W_in x_t + b)| <= max_row(sum|W_in|) * x_abs_max + |b|`` (x_t is the sampler state, O(1); 16 is > 10 sigma).
+    The step embeddings ``d_l`` are bounded by the last Linear's row sums times the bounded Mish output, taken here as
+    ``max_row(sum|W_dp| * H + |b|)`` with H the bound of the MLP output.  Pure weight arithmetic on the host (float64)."""
+    sd = {k: v.detach().double().cpu() for k, v in denoise_fn.state_dict().items()}
+    w_in, b_in = sd["input_projection.weight"], sd["input_projection.bias"]
+    x = float((w_in.abs().sum(dim=(1, 2)) * x_abs_max + b_in.abs()).max())
+    # MLP output bound: |emb| <= 1, Mish(v) <= |v|
+    h1 = sd["mlp.0.weight"].abs().sum(dim=1) + sd["mlp.0.bias"].abs()
+    e = float((sd["mlp.2.weight"].abs() @ h1 + sd["mlp.2.bias"].abs()).max())
+    worst = 0.0
+    for i in range(denoise_fn.n_layers):
+        pfx = f"residual_layers.{i}."
+        d = float((sd[pfx + "diffusion_projection.weight"].abs().sum(dim=1) * e + sd[pfx + "diffusion_projection.bias"].abs()).max())
+        worst = max(worst, x + d)
+        C_ = denoise_fn.residual_channels
+        w_o, b_o = sd[pfx + "output_projection.weight"][:C_], sd[pfx + "output_projection.bias"][:C_]
+        r = float((w_o.abs().sum(dim=(1, 2)) + b_o.abs()).max())
+        x = (x + r) / math.sqrt(2.0)
+    return max(worst, x)
+
+
 class DiffusionPlan:
-    """Owner of one ``bsg_diffusion_plan`` handle."""
+    """Owner of one ``bsg_diffusion_plan`` handle.
+
+    ``precision="fp16x2"`` (the default) stores the residual stream and the gated activations as fp16 (11 significant bits, range
+    +-65504).  Before the plan is built the worst-case magnitude of those tensors is bounded from the weights alone
+    (``fp16_activation_bound``); a checkpoint whose bound exceeds ``FP16_SAFE_BOUND`` is run in ``"bf16x3"`` instead (bf16 hi/lo
+    operands, fp32 exponent range, ~16 mantissa bits, 3 MMAs per product) and ``plan.precision`` / ``plan.precision_note`` say so.
+    ``precision="fp16x2!"`` forces the fp16 mode (its conversions saturate, they never produce inf)."""
 
     def __init__(self, denoise_fn: B200DiffNet, sched: Optional[dict] = None, timesteps: Optional[int] = None,
                  K_step: Optional[int] = None, spec_min=None, spec_max=None, precision: str = _lib.DEFAULT_PRECISION,
@@ -137,6 +171,17 @@ class DiffusionPlan:
             sched = {f[0]: z for f in _lib.Schedule._fields_}
         self.K_step = int(K_step)
         self.timesteps = int(timesteps)
+        self.precision_note = ""
+        if precision == "fp16x2!":
+            precision = "fp16x2"
+        elif precision == "fp16x2":
+            bound = fp16_activation_bound(denoise_fn)
+            if not bound < FP16_SAFE_BOUND:
+                self.precision_note = (f"fp16x2 -> bf16x3: worst-case activation bound {bound:.3g} >= {FP16_SAFE_BOUND:.3g} "
+                                       "(fp16 range); see DESIGN.md section 5")
+                import warnings
+                warnings.warn("bisinger_b200: " + self.precision_note)
+                precision = "bf16x3"
         cfg = _lib.DiffnetConfig(M, denoise_fn.encoder_hidden, denoise_fn.residual_channels, denoise_fn.n_layers,
                                  denoise_fn.dilation_cycle_length, self.timesteps, self.K_step, _lib.PRECISIONS[precision])
         w = denoise_fn.flat_weights()
@@ -259,23 +304,28 @@ def cosine_beta_schedule(timesteps, s=0.008):
 
 
 class B200GaussianDiffusion(nn.Module):
-    """Drop-in for GaussianDiffusion's inference branch (usr/diff/shallow_diffusion_tts.py:230-273).
+    """Drop-in for GaussianDiffusion (usr/diff/shallow_diffusion_tts.py:71-126, ``forward`` :230-273): the inference branch runs on the
+    CUDA plan, the training branch (``infer=False``, :237-242) is delegated to a wrapped reference instance.
 
     Differences to the reference constructor: ``fs2`` (the FastSpeech2 / FastSpeech2MIDI conditioner, which stays
     reference PyTorch and is out of scope here) is passed in instead of being built from ``phone_encoder``; ``hparams``
-    is explicit.  ``forward(..., infer=True)`` returns the reference's dict (``mel_out``, ``fs2_mel``, plus whatever
-    ``fs2`` returned).  Training (``infer=False``) is not part of this path and raises.
+    is explicit; ``reference`` is the reference ``GaussianDiffusion`` to which ``forward(..., infer=False)`` is forwarded
+    (``B200GaussianDiffusion.from_reference(ref)`` builds the whole drop-in from one).  ``forward(..., infer=True)`` returns the
+    reference's dict (``mel_out``, ``fs2_mel``, plus whatever ``fs2`` returned).  Without a wrapped reference ``infer=False`` raises.
     Extra keyword arguments for parity tests: ``start_noise`` [B,1,M,T], ``step_noise`` [K,B,1,M,T], ``seed``.
     """
 
     def __init__(self, phone_encoder, out_dims, denoise_fn, timesteps=1000, K_step=1000, loss_type="l1", betas=None,
                  spec_min=None, spec_max=None, fs2: Optional[nn.Module] = None, hparams: Optional[dict] = None,
-                 precision: str = _lib.DEFAULT_PRECISION):
+                 precision: str = _lib.DEFAULT_PRECISION, reference: Optional[nn.Module] = None):
         super().__init__()
         hp = _hp(hparams)
         self.hparams = hp
         self.denoise_fn = denoise_fn
         self.fs2 = fs2
+        # not registered as a sub-module: its parameters are the reference's own (state_dict / .to() of the drop-in leave them alone)
+        object.__setattr__(self, "reference", reference)
+        self._ref_dirty = False
         self.mel_bins = out_dims
         if betas is not None:
             betas = betas.detach().cpu().numpy() if isinstance(betas, torch.Tensor) else np.asarray(betas)
@@ -295,6 +345,45 @@ class B200GaussianDiffusion(nn.Module):
         self.precision = precision
         self._plan: Optional[DiffusionPlan] = None
 
+    @classmethod
+    def from_reference(cls, ref: nn.Module, hparams: Optional[dict] = None, precision: str = _lib.DEFAULT_PRECISION):
+        """Wrap a constructed (and checkpoint-loaded) reference ``GaussianDiffusion``: the denoiser weights go into a B200DiffNet
+        (same names, ``strict=True``), the schedule buffers and spec_min/max are copied as they stand (they may come from the
+        checkpoint), ``fs2`` is shared, and training calls are forwarded to ``ref``."""
+        hp = _hp(hparams)
+        den = ref.denoise_fn
+        if not isinstance(den, B200DiffNet):
+            den = B200DiffNet(ref.mel_bins, hparams=hp)
+            den.load_state_dict(ref.denoise_fn.state_dict(), strict=True)
+        self = cls(None, ref.mel_bins, den, timesteps=ref.num_timesteps, K_step=ref.K_step, loss_type=ref.loss_type, betas=ref.betas,
+                   spec_min=ref.spec_min.reshape(-1).tolist(), spec_max=ref.spec_max.reshape(-1).tolist(), fs2=ref.fs2, hparams=hp,
+                   precision=precision, reference=ref)
+        self.sync_from_reference()
+        return self
+
+    def sync_from_reference(self):
+        """Re-read denoiser weights, schedule buffers and spec_min/max from the wrapped reference (after it was trained or loaded)."""
+        ref = self.reference
+        if ref is None:
+            return
+        if ref.denoise_fn is not self.denoise_fn:
+            self.denoise_fn.load_state_dict(ref.denoise_fn.state_dict(), strict=True)
+        own = dict(self.named_buffers(recurse=False))
+        for k, v in ref.named_buffers(recurse=False):
+            if k in own and own[k].shape == v.shape:
+                own[k].copy_(v.detach().to(own[k].device))
+        self._ref_dirty = False
+        self._plan = None
+
+    # a plan holds packed copies of the weights / schedule on the device: anything that changes them drops it
+    def load_state_dict(self, *a, **k):
+        self._plan = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
     def build_plan(self) -> DiffusionPlan:
         """(Re)build the device plan from the *current* parameters and schedule buffers (call again after loading a
         checkpoint)."""
@@ -302,11 +391,16 @@ class B200GaussianDiffusion(nn.Module):
         sched["alphas_cumprod"] = self.alphas_cumprod      # the PLMS sampler's get_x_pred (shallow_diffusion_tts.py:175-176)
         self._plan = DiffusionPlan(self.denoise_fn, sched, self.num_timesteps, self.K_step, self.spec_min.reshape(-1),
                                    self.spec_max.reshape(-1), self.precision)
+        self._plan_version = getattr(self.denoise_fn, "_version", 0)
         return self._plan
 
     @property
     def plan(self) -> DiffusionPlan:
-        return self._plan if self._plan is not None else self.build_plan()
+        # a denoiser reloaded behind the sampler's back (utils.load_ckpt on model.denoise_fn) also invalidates the plan
+        v = getattr(self.denoise_fn, "_version", 0)
+        if self._plan is None or getattr(self, "_plan_version", v) != v:
+            self.build_plan()
+        return self._plan
 
     def norm_spec(self, x):
         return (x - self.spec_min) / (self.spec_max - self.spec_min) * 2 - 1
@@ -323,10 +417,18 @@ class B200GaussianDiffusion(nn.Module):
         return self.plan.sample(decoder_inp, None if gaussian else fs2_mel, start_noise, step_noise, seed, mel2ph, return_x)
 
     def forward(self, txt_tokens, mel2ph=None, spk_embed=None, ref_mels=None, f0=None, uv=None, energy=None, infer=False,
-                start_noise=None, step_noise=None, seed=0, **kwargs):
+                start_noise=None, step_noise=None, seed=None, **kwargs):
         if not infer:
-            raise NotImplementedError("B200GaussianDiffusion implements the inference branch only "
-                                      "(training stays in the reference: shallow_diffusion_tts.py:237-242)")
+            # the training branch (q_sample at a random t, p_losses with autograd: shallow_diffusion_tts.py:237-242) stays the
+            # reference's; the weights it updates are re-read before the next inference call
+            if self.reference is None:
+                raise NotImplementedError("B200GaussianDiffusion runs the inference branch on the device; for infer=False wrap the "
+                                          "reference module (B200GaussianDiffusion.from_reference(ref) / reference=ref) and the call is "
+                                          "forwarded to it (shallow_diffusion_tts.py:237-242)")
+            self._ref_dirty = True
+            return self.reference(txt_tokens, mel2ph, spk_embed, ref_mels, f0, uv, energy, infer=False, **kwargs)
+        if self._ref_dirty:
+            self.sync_from_reference()
         if self.fs2 is None:
             raise RuntimeError("no FastSpeech2 conditioner attached (pass fs2=...)")
         ret = self.fs2(txt_tokens, mel2ph, spk_embed, ref_mels, f0, uv, energy, skip_decoder=False, infer=True, **kwargs)

@@ -18,7 +18,7 @@ import torch
 
 
 @torch.no_grad()
-def mel_to_wav(mel_out: torch.Tensor, generator, pe=None, f0: Optional[torch.Tensor] = None, seed: int = 0, rand_ini=None,
+def mel_to_wav(mel_out: torch.Tensor, generator, pe=None, f0: Optional[torch.Tensor] = None, seed: Optional[int] = None, rand_ini=None,
                src_noise=None) -> torch.Tensor:
     """mel_out [B,T,80] (device) -> wav [B, T*hop].  ``pe``: a B200PitchExtractor (hparams['pe_enable']) or None, in which case
     ``f0`` [B,T] is used as given (``output['f0_denorm']``); ``generator``: a B200HifiGanGenerator.  ``rand_ini`` / ``src_noise``
@@ -30,8 +30,11 @@ def mel_to_wav(mel_out: torch.Tensor, generator, pe=None, f0: Optional[torch.Ten
 
 
 @torch.no_grad()
-def synthesize(diffusion, generator, pe, txt_tokens, seed: int = 0, **model_kwargs) -> torch.Tensor:
+def synthesize(diffusion, generator, pe, txt_tokens, seed: Optional[int] = None, **model_kwargs) -> torch.Tensor:
     """``forward_model`` (a-lang-esm-style-ori-shift.py:606-633) with the three drop-ins: ``diffusion`` is a
-    B200GaussianDiffusion holding the reference's FastSpeech2 conditioner (``fs2``)."""
-    out = diffusion(txt_tokens, infer=True, **model_kwargs)
-    return mel_to_wav(out["mel_out"], generator, pe, out.get("f0_denorm"), seed)
+    B200GaussianDiffusion holding the reference's FastSpeech2 conditioner (``fs2``).  ``seed`` keys the sampler's and the NSF
+    source's device-side noise (None: fresh per call, drawn from torch's global generator like the reference's noise)."""
+    from . import _lib
+    s = _lib.resolve_seed(seed)
+    out = diffusion(txt_tokens, infer=True, seed=s, **model_kwargs)
+    return mel_to_wav(out["mel_out"], generator, pe, out.get("f0_denorm"), s + 1)

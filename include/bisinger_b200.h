@@ -120,9 +120,13 @@ int bsg_diffnet_forward(bsg_diffusion_plan* plan, const float* spec, int t, cons
 
 /* Measurement hook for bench.py's roofline line: average duration (ms, CUDA events on `stream`) of `reps` back-to-back
  * launches of one hot kernel at batch shape (B, T), cycling through the residual layers.
- *   which = 0: dilated-conv + conditioner GEMM with the sigmoid*tanh gate epilogue (net.py:67-74)
- *   which = 1: residual half of the output-projection GEMM with the residual epilogue (net.py:76-78)
- *   which = 2: skip halves of all layers' output projections as one K = L*C GEMM (net.py:77-78,126)
+ *   which = 0: dilated-conv + conditioner GEMM with the sigmoid*tanh gate epilogue (net.py:67-74)            [unfused path]
+ *   which = 1: residual half of the output-projection GEMM with the residual epilogue (net.py:76-78)         [unfused path]
+ *   which = 2: skip halves of all layers' output projections (+ skip_projection) as one K = L*C GEMM (net.py:77-78,126-128)
+ *   which = 3: the fused ResidualBlock kernel, one launch per layer (fp16x2 plans only; diffnet_layer_kernel)
+ *   which = 4: the fused ResidualBlock kernel with ALL layers of a step in one launch, as a sampling step runs it; the
+ *              returned time is PER LAYER (launch time / residual_layers); `reps` counts layers, i.e. reps / L launches
+ *              (fp16x2 plans only).  bench.py's roofline line uses this one.
  * The kernels run on the plan's workspace (whatever the last sample left there); results are discarded.       */
 int bsg_diffusion_time_kernel(bsg_diffusion_plan* plan, int which, int B, int T, int reps, float* avg_ms, void* stream);
 
@@ -164,8 +168,11 @@ void bsg_hifigan_plan_destroy(bsg_hifigan_plan* plan);
 /* HifiGanGenerator.forward (hifigan.py:144-173).
  *   mel       device f32 [B][num_mels][T]
  *   f0        device f32 [B][T] in Hz (0 = unvoiced) or NULL (no NSF branch)
- *   rand_ini  device f32 [B][harmonic_num+1] initial phases (SineGen, source.py:54-57; column 0 is ignored) or NULL
+ *   rand_ini  device f32 [B][harmonic_num+1] initial phases (SineGen, source.py:54-57; column 0 is ignored) or NULL => drawn
+ *             U[0,1) on device from `seed` for every harmonic h >= 1 (the fundamental gets none), as torch.rand does at :54
  *   src_noise device f32 [B][T*hop][harmonic_num+1] ~ N(0,1) (source.py:133) or NULL => drawn on device from `seed`
+ *   Each of the two falls back to the device-side Philox4x32-10 stream independently; the captured-graph path is used when both
+ *   are NULL.
  *   wav       device f32 [B][T*hop]                                                                        */
 int bsg_hifigan_forward(bsg_hifigan_plan* plan, const float* mel, const float* f0, const float* rand_ini,
                         const float* src_noise, unsigned long long seed, int B, int T, float* wav, void* stream);

@@ -74,8 +74,13 @@ def test_sampler_bench_regime_vs_oracle(diff, dev, B, T, rows, runs):
     sd, sched, plan = diff
     args, cpu = _batch_with_seeded_rows(dev, 9000 + T, B, T, K_STEP, rows)
     outs = [plan.sample(*args) for _ in range(runs)]
-    for o in outs[1:]:
-        assert torch.equal(o, outs[0]), "run-to-run difference: an ordering hole in the layer-to-layer dataflow"
+    for i, o in enumerate(outs[1:], 1):
+        if not torch.equal(o, outs[0]):
+            idx = (o != outs[0]).nonzero()
+            raise AssertionError(
+                f"run {i} differs from run 0 in {idx.shape[0]} elements (max |diff| {float((o - outs[0]).abs().max()):.3e}): batch rows "
+                f"{sorted(set(idx[:, 0].tolist()))}, frames {int(idx[:, 1].min())}..{int(idx[:, 1].max())} -- an ordering hole in the "
+                f"layer-to-layer dataflow")
     assert bool(torch.isfinite(outs[0]).all())
     with torch.no_grad():
         ref = O.diffusion_infer(sd, sched, torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX), cpu["cond"], K_STEP,

@@ -139,3 +139,73 @@ def test_plms_sampler_vs_golden(sd_diff):
                                              inp["start_noise"], return_x=True)
         assert np.abs(mel.numpy() - g[f"mel.{i}"]).max() < 1e-4
         assert np.abs(x0.numpy() - g[f"x0.{i}"]).max() < 5e-5
+
+
+def _fwd_tol(ref):
+    """Tolerance of a forward-golden case: the north-star 1e-2 on a mel range of spec_max - spec_min ~ 6.2, scaled to the range the
+    reference output really has.  Case 1 (1000-step PLMS from a Gaussian start, no clamp in p_sample_plms) leaves the mel range by
+    orders of magnitude on a random-init denoiser (|mel| ~ 2e3): errors are amplified with the signal, so the bound is relative."""
+    return 1e-2 * max(1.0, float(np.abs(ref).max()) / 6.2)
+
+
+def test_forward_golden_vs_oracle(sd_diff):
+    """The restatement against the executed reference's public entry point GaussianDiffusion.forward(infer=True)
+    (oracle/make_golden_forward.py): the K = 100 ancestral sampler with a mel2ph mask, and BiSinger's shipped configuration
+    (timesteps = K_step = 1000, max_beta 0.02, pndm_speedup 5, gaussian_start; diff.yaml:16-23)."""
+    import os
+    from make_golden_forward import FWD_CASES, forward_inputs, forward_noise
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "forward_golden.npz"))
+    smin, smax = torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX)
+    for i, c in enumerate(FWD_CASES):
+        sched = O.schedule_buffers(O.linear_beta_schedule(c["timesteps"], c["max_beta"]))
+        cond, fs2_mel, mel2ph = forward_inputs(c)
+        start, steps = forward_noise(c)
+        with torch.no_grad():
+            if c["pndm_speedup"]:
+                mel = O.diffusion_infer_plms(sd_diff, sched, smin, smax, cond, c["K_step"], c["pndm_speedup"], fs2_mel, start,
+                                             mel2ph=mel2ph, gaussian_start=c["gaussian_start"])
+            else:
+                mel = O.diffusion_infer(sd_diff, sched, smin, smax, cond, c["K_step"], steps, fs2_mel, start, mel2ph=mel2ph,
+                                        gaussian_start=c["gaussian_start"])
+        ref = g[f"mel.{i}"]
+        assert np.abs(mel.numpy() - ref).max() < 0.05 * _fwd_tol(ref), i
+        if c["pad_tail"]:
+            assert float(np.abs(ref[-1, c["T"] - c["pad_tail"]:]).max()) == 0.0
+
+
+@pytest.mark.skipif(not reference_present, reason="/root/reference not mounted (GPU box)")
+def test_from_reference_wraps_the_live_module_and_delegates_training(sd_diff):
+    """B200GaussianDiffusion.from_reference(ref): denoiser weights, schedule buffers and spec_min/max are taken over from the live
+    reference module (strict load), ``fs2`` is shared, and ``forward(infer=False)`` -- the training branch,
+    shallow_diffusion_tts.py:237-242 -- runs in the reference and returns its ``diff_loss``."""
+    import ref_shim
+    from bisinger_b200 import B200GaussianDiffusion
+    ns = ref_shim.load()
+    gd = ns.gd
+    inp = synth.kernel_inputs(81, 2, 24, 1)
+
+    class StubFs2(torch.nn.Module):
+        def forward(self, txt_tokens, mel2ph, spk_embed, ref_mels, f0, uv, energy, skip_decoder=False, infer=True, **kw):
+            return {"decoder_inp": inp["cond"], "mel_out": inp["fs2_mel"]}
+
+    gd.FastSpeech2 = lambda *a, **k: StubFs2()
+    net = ns.DiffNet(80)
+    net.load_state_dict(sd_diff, strict=True)
+    ref = gd.GaussianDiffusion(None, 80, net, timesteps=K_STEP, K_step=K_STEP, loss_type="l1",
+                               betas=gd.linear_beta_schedule(K_STEP, max_beta=MAX_BETA), spec_min=synth.SPEC_MIN, spec_max=synth.SPEC_MAX)
+    ref.posterior_mean_coef1[3] = 0.123            # as if a checkpoint had overwritten a schedule buffer
+    model = B200GaussianDiffusion.from_reference(ref, hparams=dict(ns.hparams))
+    assert model.fs2 is ref.fs2 and model.reference is ref
+    assert float(model.posterior_mean_coef1[3]) == pytest.approx(0.123)
+    for k, v in ref.denoise_fn.state_dict().items():
+        assert torch.equal(model.denoise_fn.state_dict()[k], v)
+    assert "reference" not in dict(model.named_children())          # the reference's parameters stay its own
+    torch.manual_seed(3)
+    out = model(torch.zeros(2, 8, dtype=torch.long), ref_mels=inp["fs2_mel"], infer=False)
+    torch.manual_seed(3)
+    want = ref(torch.zeros(2, 8, dtype=torch.long), ref_mels=inp["fs2_mel"], infer=False)
+    assert "diff_loss" in out and torch.equal(out["diff_loss"], want["diff_loss"]) and out["diff_loss"].requires_grad
+    assert model._ref_dirty                                          # weights are re-read before the next inference call
+    with pytest.raises(NotImplementedError):
+        B200GaussianDiffusion(None, 80, model.denoise_fn, timesteps=K_STEP, K_step=K_STEP, betas=O.linear_beta_schedule(K_STEP, MAX_BETA),
+                              spec_min=synth.SPEC_MIN, spec_max=synth.SPEC_MAX)(torch.zeros(1, 4, dtype=torch.long), infer=False)

@@ -1,7 +1,7 @@
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bisinger_b200 import _lib
-L = _lib.lib()
+# the hardware experiments live in their own library (make -C bisinger_b200/csrc experiments), not in the product .so
+L = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bisinger_b200', 'libbsg_experiments.so'))
 L.bsg_experiment_rowoffset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 torch.manual_seed(0)
 a = torch.randn(256, 64, device="cuda").bfloat16()
