@@ -17,6 +17,7 @@
 // delta with 0 <= delta*u + p + pad < k, written to columns [p*Cout, (p+1)*Cout) of the [rows_in][u*Cout] view of the
 // output (which is the same memory as [rows_in*u][Cout]).
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -804,8 +805,35 @@ void HifiganPlan::enqueue(Workspace& w, const float* mel, const float* f0, const
                     a.w_slots = resblock_weight_slots(C);
                     const int n_wt = C == 32 ? (k + 1) / 2 : k * (C / kBlockK);
                     a.w_resident = 2 * n_wt <= a.w_slots ? 1 : 0;
+                    static const bool trace_on = std::getenv("BSG_TRACE") != nullptr;
+                    DevBuf tb;
+                    if (trace_on) {   // per-role cycle counters of this launch, averaged over the CTAs (measurement only: synchronises)
+                        tb.alloc(static_cast<size_t>(device_sm_count()) * 16 * 8);
+                        B200_CUDA(cudaMemsetAsync(tb.p, 0, tb.bytes, st));
+                        a.trace = tb.as<unsigned long long>();
+                    }
                     launch_resblock_iter(C, a, st);
                     launches += 1, g_launch_count += 1;
+                    if (trace_on) {
+                        const int grid = device_sm_count();
+                        std::vector<unsigned long long> h(static_cast<size_t>(grid) * 16);
+                        B200_CUDA(cudaMemcpyAsync(h.data(), tb.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+                        B200_CUDA(cudaStreamSynchronize(st));
+                        double sm[16] = {0};
+                        int n = 0;
+                        for (int c = 0; c < grid; ++c) {
+                            if (h[c * 16] == 0) continue;
+                            ++n;
+                            for (int i = 0; i < 16; ++i) sm[i] += static_cast<double>(h[c * 16 + i]);
+                        }
+                        if (n)
+                            std::fprintf(stderr,
+                                         "TRACE resblock C=%d k=%d d=%d mode %d resident %d: per tile (%.0f tiles/CTA): MMA warp %.0f clk [waits: acc1 free %.0f, "
+                                         "A tile %.0f, weights %.0f, acc2 free %.0f, t tile %.0f] | epilogue-1 %.0f [waits: acc1 full %.0f, t free %.0f] | "
+                                         "epilogue-2 %.0f [wait acc2 full %.0f]\n",
+                                         C, k, d, a.mode, a.w_resident, sm[6] / n, sm[0] / sm[6], sm[1] / sm[6], sm[2] / sm[6], sm[3] / sm[6], sm[4] / sm[6],
+                                         sm[5] / sm[6], sm[7] / sm[6], sm[8] / sm[6], sm[9] / sm[6], sm[10] / sm[6], sm[11] / sm[6]);
+                    }
                 }
             }
         } else

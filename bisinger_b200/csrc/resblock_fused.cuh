@@ -45,6 +45,7 @@ struct ResblockArgs {
     float c0, slope_out;
     int w_slots;                 // weight tiles the shared-memory weight area holds
     int w_resident;              // 1: 2 * n_wtiles <= w_slots, all weight tiles are loaded once per CTA
+    unsigned long long* trace;   // optional [grid][16] cycle counters of the roles (tests/tools/gpu_probe.py), or null
 };
 
 template <int C>
@@ -117,13 +118,133 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {   // saturating:
 }
 __device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.0f ? v : v * slope; }
 
+
+// ---- warp-uniform mbarrier wait (all 32 lanes poll; the loop condition is a vote, so control flow stays convergent and the
+//      compiler can keep the issue loop's state in uniform registers) ------------------------------------------------------------------
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait_s(bar, parity))) {
+        if (++spins > (1u << 26)) {   // ~seconds: a protocol bug must not hang the GPU box -- trap instead
+            if ((threadIdx.x & 31) == 0) printf("resblock_iter_kernel: block %d waited too long on barrier %u parity %u\n", blockIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void umma_commit_elect_s(uint32_t bar) {   // whole warp; one lane commits
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar)
+        : "memory");
+}
+
+// shared-memory addresses of everything the MMA warp touches (all warp-uniform)
+struct RbMmaCtx {
+    uint32_t smem_a, smem_t, smem_w;
+    uint32_t afull, aempty, wfull, wempty, acc1_full, acc1_empty, acc2_full, acc2_empty, t_full, t_empty, wres_full;
+    uint32_t tmem_base;
+    int n_my, dil, w_slots, wres;
+    unsigned long long* trace;   // this CTA's 16 counters or null
+};
+
+// The MMA warp's whole loop, specialised for the tap count so that the tap loops unroll with immediate descriptor offsets.
+template <int C, int NT>
+__device__ __forceinline__ void rb_mma_role(const RbMmaCtx& x) {
+    using S = ResblockSmem<C>;
+    constexpr int N = C, NKB = S::kNKB;
+    constexpr uint32_t kIdesc = umma_idesc_f16(kTileM, N, /*fp16=*/true);
+    constexpr int TILE16 = S::kWTileBytes >> 4;                       // weight tile size in descriptor units
+    constexpr int NWT = C == 32 ? (NT + 1) / 2 : NT * NKB;            // weight tiles per convolution
+    int as = 0, ws = 0;
+    uint32_t aph = 0, wph = 0;
+    const bool tr = x.trace != nullptr;
+    long long w_acc1 = 0, w_a = 0, w_w = 0, w_acc2 = 0, w_t = 0;
+    const long long t_begin = tr ? clock64() : 0;
+    auto wait_tr = [&](uint32_t bar, uint32_t parity, long long& acc) {
+        if (!tr) { mbar_wait_warp(bar, parity); return; }
+        const long long t0 = clock64();
+        mbar_wait_warp(bar, parity);
+        acc += clock64() - t0;
+    };
+    if (x.wres) { mbar_wait_warp(x.wres_full, 0); tc_fence_after(); }
+    const uint64_t w_desc0 = umma_smem_desc<128>(x.smem_w);
+    const uint64_t a_tap_step = static_cast<uint64_t>(x.dil) * 8;     // descriptor units of 16 bytes: dil rows x 128 B
+    // all taps of k-block kb of convolution `conv` into tacc; A operand of tap tp at a_desc + tp * a_step
+    auto conv_taps = [&](uint32_t tacc, uint64_t a_desc, uint64_t a_step, int conv, int kb, uint32_t first_acc) {
+        if (x.wres) {
+            const uint64_t b0 = w_desc0 + static_cast<uint64_t>(conv * NWT * TILE16) + static_cast<uint64_t>(C == 32 ? 0 : kb * TILE16);
+#pragma unroll
+            for (int tp = 0; tp < NT; ++tp) {
+                if (C == 32) mma_f16_x2(tacc, a_desc + tp * a_step, b0 + static_cast<uint64_t>((tp >> 1) * TILE16 + (tp & 1) * 4), kIdesc, tp == 0 ? first_acc : 1u);
+                else mma_f16_x4(tacc, a_desc + tp * a_step, b0 + static_cast<uint64_t>(tp * NKB * TILE16), kIdesc, tp == 0 ? first_acc : 1u);
+            }
+        } else {
+#pragma unroll
+            for (int tp = 0; tp < NT; ++tp) {
+                if (C != 32 || (tp & 1) == 0) { wait_tr(x.wfull + ws * 8, wph, w_w); tc_fence_after(); }
+                const uint64_t b = w_desc0 + static_cast<uint64_t>(ws * TILE16 + (C == 32 ? (tp & 1) * 4 : 0));
+                if (C == 32) mma_f16_x2(tacc, a_desc + tp * a_step, b, kIdesc, tp == 0 ? first_acc : 1u);
+                else mma_f16_x4(tacc, a_desc + tp * a_step, b, kIdesc, tp == 0 ? first_acc : 1u);
+                if (C != 32 || (tp & 1) || tp + 1 == NT) {
+                    umma_commit_elect_s(x.wempty + ws * 8);
+                    if (++ws == x.w_slots) { ws = 0; wph ^= 1; }
+                }
+            }
+        }
+    };
+    auto conv1 = [&](int it) {
+        const int buf = it & 1;
+        wait_tr(x.acc1_empty + buf * 8, ((it >> 1) & 1) ^ 1, w_acc1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+            wait_tr(x.afull + as * 8, aph, w_a);
+            tc_fence_after();
+            conv_taps(x.tmem_base + buf * N, umma_smem_desc<128>(x.smem_a + as * S::kASlotBytes), a_tap_step, 0, kb, kb == 0 ? 0u : 1u);
+            umma_commit_elect_s(x.aempty + as * 8);
+            if (++as == S::kAStages) { as = 0; aph ^= 1; }
+        }
+        umma_commit_elect_s(x.acc1_full + buf * 8);
+    };
+    auto conv2 = [&](int it) {
+        const int buf = it & 1;
+        wait_tr(x.acc2_empty + buf * 8, ((it >> 1) & 1) ^ 1, w_acc2);
+        wait_tr(x.t_full + buf * 8, (it >> 1) & 1, w_t);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb)
+            conv_taps(x.tmem_base + (2 + buf) * N, umma_smem_desc<128>(x.smem_t + buf * S::kTBytes + kb * S::kTSlabBytes), 8, 1, kb, kb == 0 ? 0u : 1u);
+        umma_commit_elect_s(x.acc2_full + buf * 8);
+        umma_commit_elect_s(x.t_empty + buf * 8);
+    };
+    if (x.n_my > 0) conv1(0);
+    for (int it = 0; it < x.n_my; ++it) {
+        if (it + 1 < x.n_my) conv1(it + 1);
+        conv2(it);
+    }
+    if (tr && (threadIdx.x & 31) == 0) {
+        x.trace[0] = clock64() - t_begin; x.trace[1] = w_acc1; x.trace[2] = w_a; x.trace[3] = w_w; x.trace[4] = w_acc2; x.trace[5] = w_t;
+        x.trace[6] = x.n_my;
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __grid_constant__ ResblockArgs args) {
     using S = ResblockSmem<C>;
     constexpr int N = C;
     constexpr int NKB = S::kNKB;
-    constexpr int KSTEPS = C >= 64 ? 4 : 2;
-    constexpr uint32_t kIdesc = umma_idesc_f16(kTileM, N, /*fp16=*/true);
     constexpr int kTmemCols = 4 * N;   // acc1[2], acc2[2]
     constexpr float kSlope = 0.1f, kInvSlope = 10.0f;   // LRELU_SLOPE, hifigan.py:11
 
@@ -147,7 +268,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
     uint64_t* wres_full = t_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_full + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler, too
     const int lane = threadIdx.x & 31;
     const int ntaps = args.ntaps;
     const int n_wt = C == 32 ? (ntaps + 1) / 2 : ntaps * NKB;   // weight tiles per convolution (C = 32: two taps share a 64-column tile)
@@ -226,90 +347,37 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
         }
     } else if (warp == 1) {
         // ================= MMA issuer: the whole warp, convergent; one elected lane issues =================
-        int as = 0, ws = 0;
-        uint32_t aph = 0, wph = 0;
-        if (wres) { mbar_wait(wres_full, 0); tc_fence_after(); }
-        const uint64_t w_desc0 = umma_smem_desc<128>(smem_w);
-        const uint64_t a_tap_step = static_cast<uint64_t>(args.dil) * 8;   // descriptor units of 16 bytes: dil rows x 128 B
-        // all taps of one k-block: A operand at a_desc + tap * a_step
-        auto conv_taps = [&](uint32_t tacc, uint64_t a_desc, uint64_t a_step, int conv, int kb, uint32_t& accum) {
-            if (C == 32) {
-                for (int tp = 0; tp < ntaps; ++tp) {
-                    uint64_t b_desc;
-                    if (wres) {
-                        b_desc = w_desc0 + static_cast<uint64_t>((conv * n_wt + (tp >> 1)) * (S::kWTileBytes >> 4) + (tp & 1) * 4);
-                    } else {
-                        if ((tp & 1) == 0) { mbar_wait(&wfull[ws], wph); tc_fence_after(); }
-                        b_desc = w_desc0 + static_cast<uint64_t>(ws * (S::kWTileBytes >> 4) + (tp & 1) * 4);
-                    }
-                    mma_f16_x2(tacc, a_desc + tp * a_step, b_desc, kIdesc, accum);
-                    accum = 1;
-                    if (!wres && ((tp & 1) || tp + 1 == ntaps)) {
-                        umma_commit_elect(&wempty[ws]);
-                        if (++ws == w_slots) { ws = 0; wph ^= 1; }
-                    }
-                }
-            } else {
-                for (int tp = 0; tp < ntaps; ++tp) {
-                    uint64_t b_desc;
-                    if (wres) {
-                        b_desc = w_desc0 + static_cast<uint64_t>((conv * n_wt + tp * NKB + kb) * (S::kWTileBytes >> 4));
-                    } else {
-                        mbar_wait(&wfull[ws], wph);
-                        tc_fence_after();
-                        b_desc = w_desc0 + static_cast<uint64_t>(ws * (S::kWTileBytes >> 4));
-                    }
-                    mma_f16_x4(tacc, a_desc + tp * a_step, b_desc, kIdesc, accum);
-                    accum = 1;
-                    if (!wres) {
-                        umma_commit_elect(&wempty[ws]);
-                        if (++ws == w_slots) { ws = 0; wph ^= 1; }
-                    }
-                }
-            }
-        };
-        auto conv1 = [&](int it) {
-            const int buf = it & 1;
-            mbar_wait(&acc1_empty[buf], ((it >> 1) & 1) ^ 1);
-            tc_fence_after();
-            uint32_t accum = 0;
-            for (int kb = 0; kb < NKB; ++kb) {
-                mbar_wait(&afull[as], aph);
-                tc_fence_after();
-                conv_taps(tmem_base + buf * N, umma_smem_desc<128>(smem_a + as * S::kASlotBytes), a_tap_step, 0, kb, accum);
-                umma_commit_elect(&aempty[as]);
-                if (++as == S::kAStages) { as = 0; aph ^= 1; }
-            }
-            umma_commit_elect(&acc1_full[buf]);
-        };
-        auto conv2 = [&](int it) {
-            const int buf = it & 1;
-            mbar_wait(&acc2_empty[buf], ((it >> 1) & 1) ^ 1);
-            mbar_wait(&t_full[buf], (it >> 1) & 1);
-            tc_fence_after();
-            uint32_t accum = 0;
-            for (int kb = 0; kb < NKB; ++kb)
-                conv_taps(tmem_base + (2 + buf) * N, umma_smem_desc<128>(smem_t + buf * S::kTBytes + kb * S::kTSlabBytes), 8, 1, kb, accum);
-            umma_commit_elect(&acc2_full[buf]);
-            umma_commit_elect(&t_empty[buf]);
-        };
-        if (n_my > 0) conv1(0);
-        for (int it = 0; it < n_my; ++it) {
-            if (it + 1 < n_my) conv1(it + 1);
-            conv2(it);
+        RbMmaCtx x;
+        x.smem_a = smem_a; x.smem_t = smem_t; x.smem_w = smem_w;
+        x.afull = smem_u32(afull); x.aempty = smem_u32(aempty); x.wfull = smem_u32(wfull); x.wempty = smem_u32(wempty);
+        x.acc1_full = smem_u32(acc1_full); x.acc1_empty = smem_u32(acc1_empty); x.acc2_full = smem_u32(acc2_full);
+        x.acc2_empty = smem_u32(acc2_empty); x.t_full = smem_u32(t_full); x.t_empty = smem_u32(t_empty); x.wres_full = smem_u32(wres_full);
+        x.tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+        x.n_my = n_my; x.dil = args.dil; x.w_slots = w_slots; x.wres = wres ? 1 : 0;
+        x.trace = args.trace ? args.trace + blockIdx.x * 16 : nullptr;
+        switch (ntaps) {
+            case 3: rb_mma_role<C, 3>(x); break;
+            case 5: rb_mma_role<C, 5>(x); break;
+            case 7: rb_mma_role<C, 7>(x); break;
+            case 9: rb_mma_role<C, 9>(x); break;
+            case 11: rb_mma_role<C, 11>(x); break;
+            default: rb_mma_role<C, 1>(x); break;   // ntaps == 1
         }
     } else if (warp >= 2 && warp < 6) {
         // ================= epilogue-1: TMEM -> bias, lrelu -> fp16 -> swizzled shared-memory tile (conv2's A operand) =================
         const int quad = warp & 3;
         const int r = quad * 32 + lane;          // row of the intermediate tile
+        const bool tr = args.trace != nullptr && warp == 2 && lane == 0;
+        long long w_f = 0, w_te = 0;
+        const long long t_begin = tr ? clock64() : 0;
         for (int it = 0; it < n_my; ++it) {
             const int buf = it & 1;
             const int m = tile_of(it);
             const int o0 = (m % args.tiles_per_batch) * args.V;
             const int g = o0 - h2 + r;           // row of this thread inside the utterance
             const bool inside = g >= 0 && g < args.L;
-            mbar_wait(&acc1_full[buf], (it >> 1) & 1);
-            mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+            mbar_wait_tr(&acc1_full[buf], (it >> 1) & 1, tr, w_f);
+            mbar_wait_tr(&t_empty[buf], ((it >> 1) & 1) ^ 1, tr, w_te);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * N;
             const uint32_t trow = smem_t + buf * S::kTBytes + r * 128;
@@ -323,8 +391,9 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
                 uint32_t h[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float y0 = lrelu_f(__uint_as_float(v[2 * i]) + vec[c + 2 * i], kSlope);
-                    const float y1 = lrelu_f(__uint_as_float(v[2 * i + 1]) + vec[c + 2 * i + 1], kSlope);
+                    const float2 bb = *reinterpret_cast<const float2*>(vec + c + 2 * i);
+                    const float y0 = lrelu_f(__uint_as_float(v[2 * i]) + bb.x, kSlope);
+                    const float y1 = lrelu_f(__uint_as_float(v[2 * i + 1]) + bb.y, kSlope);
                     h[i] = inside ? pack_h2(y0, y1) : 0u;
                 }
                 // 32 channels = four 16-byte chunks of the row's 128-byte line in slab c / 64; chunk j sits at (j ^ (row & 7))
@@ -342,11 +411,15 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
                 mbar_arrive(&t_full[buf]);
             }
         }
+        if (tr) { unsigned long long* t = args.trace + blockIdx.x * 16; t[7] = clock64() - t_begin; t[8] = w_f; t[9] = w_te; }
     } else if (warp >= 6) {
         // ================= epilogue-2: TMEM -> bias + residual -> HBM =================
         const int quad = warp & 3;
         const int q = quad * 32 + lane;          // output row of the tile
         const float* b2 = vec + C;
+        const bool tr = args.trace != nullptr && warp == 6 && lane == 0;
+        long long w_f = 0;
+        const long long t_begin = tr ? clock64() : 0;
         for (int it = 0; it < n_my; ++it) {
             const int buf = it & 1;
             const int m = tile_of(it);
@@ -356,7 +429,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
             const long long row = static_cast<long long>(b) * args.L + g;
             const __half* xrow = args.a_in + row * C;
             // (the residual rows were fetched by this tile's TMA a moment ago: the loads below are L2 hits)
-            mbar_wait(&acc2_full[buf], (it >> 1) & 1);
+            mbar_wait_tr(&acc2_full[buf], (it >> 1) & 1, tr, w_f);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (2 + buf) * N;
 #pragma unroll 1
@@ -431,6 +504,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive_relaxed(&acc2_empty[buf]);
         }
+        if (tr) { unsigned long long* t = args.trace + blockIdx.x * 16; t[10] = clock64() - t_begin; t[11] = w_f; }
     }
 
     tc_fence_before();

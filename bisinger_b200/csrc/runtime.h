@@ -138,6 +138,7 @@ inline CUtensorMap make_w_tmap(const void* base, int N, int K, int n_tile, int r
 }
 
 int device_sm_count();
+bool use_pdl();   // programmatic dependent launch attribute on the GEMM launches (BSG_NO_PDL=1: off)
 // weight-ring slots of the single-CTA conv_gemm instantiation (n_tile, terms): a convolution with n_taps * n_kb <= this many
 // weight tiles may keep them resident (ConvGemmArgs::w_resident)
 int conv_gemm_weight_slots(int n_tile, int terms);

@@ -145,6 +145,26 @@ def fp16_activation_bound(denoise_fn: "B200DiffNet", x_abs_max: float = 16.0) ->
     return max(worst, x)
 
 
+FP16_SKIP_GAIN_MAX = 8.0   # see fp16_skip_gain
+
+
+def fp16_skip_gain(denoise_fn: "B200DiffNet") -> float:
+    """L2 gain from the gated activations z of all layers to the denoiser output through the skip path,
+    ``max_m || (W_out W_skipproj [W_skip,0 .. W_skip,L-1])_m ||_2 / sqrt(L)`` (usr/diff/net.py:77-78,126-129; the ReLU between them has
+    slope <= 1).  In the fp16x2 mode z is stored with 11 significant bits; its rounding error reaches the output multiplied by this
+    gain.  Measured on B200 (tests/tools/exp_outlier.py): the skip path contributes about 3.4e-4 x gain to the final mel error of a
+    100-step sampling -- 1.1e-3 at the synthetic model's gain of 3.3, 6.5e-3 at 19 (a few 100x outlier rows in the skip halves of
+    ``output_projection``), where the 1e-2 tolerance is no longer safe.  Plans whose gain exceeds FP16_SKIP_GAIN_MAX run bf16x3."""
+    sd = {k: v.detach().double().cpu() for k, v in denoise_fn.state_dict().items()}
+    C_, L = denoise_fn.residual_channels, denoise_fn.n_layers
+    A = sd["output_projection.weight"][:, :, 0] @ sd["skip_projection.weight"][:, :, 0]
+    g2 = torch.zeros(A.shape[0], dtype=torch.float64)
+    for i in range(L):
+        G = A @ sd[f"residual_layers.{i}.output_projection.weight"][C_:, :, 0]
+        g2 += (G ** 2).sum(dim=1)
+    return float(g2.sqrt().max()) / math.sqrt(L)
+
+
 class DiffusionPlan:
     """Owner of one ``bsg_diffusion_plan`` handle.
 
@@ -176,9 +196,14 @@ class DiffusionPlan:
             precision = "fp16x2"
         elif precision == "fp16x2":
             bound = fp16_activation_bound(denoise_fn)
+            gain = fp16_skip_gain(denoise_fn)
             if not bound < FP16_SAFE_BOUND:
                 self.precision_note = (f"fp16x2 -> bf16x3: worst-case activation bound {bound:.3g} >= {FP16_SAFE_BOUND:.3g} "
                                        "(fp16 range); see DESIGN.md section 5")
+            elif not gain <= FP16_SKIP_GAIN_MAX:
+                self.precision_note = (f"fp16x2 -> bf16x3: skip-path gain {gain:.3g} > {FP16_SKIP_GAIN_MAX:.3g} (11-bit gated activations "
+                                       "would not keep the mel tolerance); see DESIGN.md section 5")
+            if self.precision_note:
                 import warnings
                 warnings.warn("bisinger_b200: " + self.precision_note)
                 precision = "bf16x3"

@@ -116,27 +116,39 @@ def test_range_large_conditioner_and_edge_mels(dev):
     assert float((mel - ref).abs().max()) <= MEL_TOL
 
 
-def test_range_outlier_weight_rows(dev):
-    """A few 100x outlier rows in the dilated conv / conditioner / output projections of several layers: the fp16 weight packing is
-    scaled by the largest weight of each matrix, so the ordinary weights lose head-room.  The worst-case bound stays inside the fp16
-    range here, the plan keeps fp16x2 and must still meet the tolerance."""
-    from bisinger_b200.diffusion import FP16_SAFE_BOUND, fp16_activation_bound, B200DiffNet
+def _with_outliers(scale, names=("dilated_conv", "conditioner_projection", "output_projection")):
     sd = synth.diffnet_state(1234)
     g = torch.Generator().manual_seed(9)
     for l in (0, 7, 19):
-        for name, n_rows in (("dilated_conv", 512), ("conditioner_projection", 512), ("output_projection", 512)):
-            rows = torch.randint(0, n_rows, (3,), generator=g)
+        for name in names:
+            rows = torch.randint(0, 512, (3,), generator=g)
             if name == "output_projection":
-                rows = rows % 256 + 256          # skip half: 100x skip contributions (the residual half is bounded separately below)
-            sd[f"residual_layers.{l}.{name}.weight"][rows] *= 100.0
-    sd["residual_layers.3.output_projection.weight"][5] *= 20.0     # residual half: the stream itself grows
-    net = B200DiffNet(80)
-    net.load_state_dict(sd, strict=True)
-    assert fp16_activation_bound(net) < FP16_SAFE_BOUND
+                rows = rows % 256 + 256          # skip half (the residual half is bounded separately by fp16_activation_bound)
+            sd[f"residual_layers.{l}.{name}.weight"][rows] *= scale
+    return sd
+
+
+def test_range_outlier_weight_rows(dev):
+    """A few outlier rows in the dilated conv / conditioner / output projections of several layers.  The fp16 weight packing is scaled
+    by the largest weight of each matrix (the ordinary weights lose head-room) and the skip path multiplies the 11-bit rounding of the
+    gated activations by its gain.  10x outliers (and 100x outliers off the skip path) keep fp16x2 and must meet the tolerance; 100x
+    outliers in the skip halves push the skip-path gain past FP16_SKIP_GAIN_MAX (measured: 8.5e-3 .. 2e-2 in fp16x2,
+    tests/tools/exp_outlier.py), so the plan falls back to bf16x3 -- and meets the tolerance there."""
+    from bisinger_b200.diffusion import FP16_SAFE_BOUND, FP16_SKIP_GAIN_MAX, fp16_activation_bound, fp16_skip_gain, B200DiffNet
     inp = synth.kernel_inputs(502, 2, 200, K_STEP)
-    plan, mel, ref = _run(dev, sd, inp)
-    assert plan.precision == "fp16x2"
-    assert float((mel - ref).abs().max()) <= MEL_TOL
+    for sd, want in ((_with_outliers(10.0), "fp16x2"), (_with_outliers(100.0, ("dilated_conv", "conditioner_projection")), "fp16x2"),
+                     (_with_outliers(100.0), "bf16x3")):
+        net = B200DiffNet(80)
+        net.load_state_dict(sd, strict=True)
+        assert fp16_activation_bound(net) < FP16_SAFE_BOUND
+        assert (fp16_skip_gain(net) <= FP16_SKIP_GAIN_MAX) == (want == "fp16x2")
+        if want == "bf16x3":
+            with pytest.warns(UserWarning, match="skip-path gain"):
+                plan, mel, ref = _run(dev, sd, inp)
+        else:
+            plan, mel, ref = _run(dev, sd, inp)
+        assert plan.precision == want
+        assert float((mel - ref).abs().max()) <= MEL_TOL, want
 
 
 def test_range_guard_falls_back_to_bf16x3(dev):
@@ -147,7 +159,7 @@ def test_range_guard_falls_back_to_bf16x3(dev):
     from bisinger_b200.diffusion import FP16_SAFE_BOUND, fp16_activation_bound
     sd = synth.diffnet_state(1234)
     for l in range(20):
-        sd[f"residual_layers.{l}.output_projection.weight"][:256] *= 40.0
+        sd[f"residual_layers.{l}.output_projection.weight"][:256] *= 1000.0
     net = B200DiffNet(80)
     net.load_state_dict(sd, strict=True)
     assert fp16_activation_bound(net) >= FP16_SAFE_BOUND
