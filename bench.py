@@ -293,6 +293,8 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         line["breakdown_ms"]["pitch_extractor_not_in_step"] = round(e3.elapsed_time(e4), 3)
         line["pipeline_algorithmic_tflops"] = round((FLOPS_DIFFNET_FRAME_STEP_HOISTED * K_STEP + FLOPS_COND_ONCE_FRAME + FLOPS_HIFIGAN_FRAME) * B * T * world * args.steps / (ms * 1e-3) / 1e12, 1)
+        if world == 1:
+            line["plms_shipped_config"] = plms_shipped(dev, synth, cond_d, args.precision, B, T)
         if world == 1 and not args.no_eager_baseline:
             line["gpu_eager_baseline"] = gpu_eager_reference(dev, B, T)
         if world == 1 and not args.no_cpu_baseline:
@@ -301,6 +303,114 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_cfg5(args):
+    """BASELINE.json cfg5: a batch-sharded throughput sweep of 4096 synthetic phrases (128 batches of 32 x 10 s) over the ranks --
+    STRONG scaling: the job is fixed, batches go round-robin to the replicas (bisinger_b200.shard.shard_batches), no collective on the
+    data path; every batch goes host -> device -> sampler -> vocoder -> host like a real job (pinned buffers, H2D / D2H inside the
+    timed region).  value = 40 960 audio-seconds / max-over-ranks time.  Run with  --workload cfg5 [--phrases N]."""
+    import torch
+    import torch.distributed as dist
+    from bisinger_b200 import launch_count
+    from bisinger_b200.shard import shard_batches
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path for the product arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gd, gen, synth = build_models(dev, args.precision)
+    B, T = args.batch, args.frames
+    mine = shard_batches(args.phrases, B, rank, world)
+    # four distinct pinned host batches, cycled (generating 128 x 80 MB of synthetic conditioner output on the host would time the host)
+    pool = []
+    for j in range(4):
+        c, m, f = host_inputs(synth, B, T, 5000 + 17 * rank + j)
+        pool.append((c.pin_memory(), m.pin_memory(), f.pin_memory()))
+    wav_p = torch.empty((B, T * HOP), dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def one(i, n_rows):
+        c, m, f = pool[i % 4]
+        cd, md, fd = c[:n_rows].to(dev, non_blocking=True), m[:n_rows].to(dev, non_blocking=True), f[:n_rows].to(dev, non_blocking=True)
+        mel = gd.sample(cd, md, seed=i)
+        wav = gen(mel.transpose(1, 2).contiguous(), fd, seed=i)
+        wav_p[:n_rows].copy_(wav[:, 0], non_blocking=True)
+
+    for i in range(max(3, args.warmup)):
+        one(i, B)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    cs = ClockSampler(local)
+    cs.start()
+    n0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i, (lo, hi) in enumerate(mine):
+        one(i, hi - lo)
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    clocks = cs.stop()
+    launches = launch_count() - n0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    audio = args.phrases * T * HOP / SR
+    if rank == 0:
+        v = audio / (ms / 1e3)
+        print(json.dumps({
+            "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": world, "steps": len(mine), "warmup": max(3, args.warmup),
+            "ms_per_step": round(ms / max(1, len(mine)), 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "fp16" if args.precision == "fp16x2" else "bf16", "data": "synthetic",
+            "config": {"workload": f"cfg5: {args.phrases} phrases x {T * HOP / SR:.0f} s in batches of {B}, round-robin over {world} replica(s) "
+                                   f"(rank 0 ran {len(mine)} batches), K={K_STEP} sampler + HiFi-GAN/NSF vocoder per batch, host buffers in / out",
+                       "global_batch": B, "frames": T, "k_step": K_STEP, "parallelism": f"replicas x{world}, batches round-robin",
+                       "l2": "per-batch working set ~6 GB >> 126 MB L2, no flush needed"},
+            "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": int(sum(t.numel() for t in pool[0])) * 4,
+                    "d2h_bytes_per_step": int(wav_p.numel()) * 4},
+            "job_seconds": round(ms / 1e3, 3), "gpu_launches": int(launches), "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def plms_shipped(dev, synth, cond_d, precision, B: int, T: int):
+    """Beside the K = 100 line: the sampler as BiSinger ships it (usr/configs/lang-esm-style-ori-shift/diff.yaml:16-23: timesteps =
+    K_step = 1000, max_beta 0.02, pndm_speedup 5, gaussian_start => 200 PLMS iterations, 201 denoiser evaluations), same batch, CUDA
+    graph replay; sampler only (the vocoder is the same as in the step above)."""
+    import torch
+    from bisinger_b200 import B200DiffNet, B200GaussianDiffusion
+    from bisinger_b200.diffusion import linear_beta_schedule
+    try:
+        net = B200DiffNet(MEL)
+        net.load_state_dict(synth.diffnet_state(1234), strict=True)
+        gd = B200GaussianDiffusion(None, MEL, net, timesteps=1000, K_step=1000, betas=linear_beta_schedule(1000, 0.02),
+                                   spec_min=synth.SPEC_MIN, spec_max=synth.SPEC_MAX, precision=precision,
+                                   hparams=dict(hidden_size=HID, residual_layers=20, residual_channels=256, dilation_cycle_length=4,
+                                                keep_bins=MEL, gaussian_start=True, pndm_speedup=5)).to(dev)
+        gd.sample(cond_d, None, seed=1)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(2):
+            gd.sample(cond_d, None, seed=2 + i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 2
+        del gd
+        torch.cuda.empty_cache()
+        return {"sampler_ms_per_batch": round(ms, 1), "denoiser_evaluations": 201, "sampler_audio_s_per_s": round(B * T * HOP / SR / (ms / 1e3), 1),
+                "unit": UNIT, "note": "timesteps = K_step = 1000, max_beta 0.02, pndm_speedup 5, gaussian_start; sampler only, graph replay"}
+    except Exception as e:
+        return {"unavailable": repr(e)[:200]}
 
 
 def gpu_eager_reference(dev, B: int, T: int):
@@ -413,6 +523,9 @@ def main():
     ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "bf16x3", "bf16"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5"],
+                    help="cfg3 (default): one 32 x 10 s batch per rank and step, weak scaling; cfg5: 4096 phrases sharded over the ranks, strong scaling")
+    ap.add_argument("--phrases", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     args = ap.parse_args()
@@ -425,7 +538,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_ours(args)
+    if args.workload == "cfg5":
+        run_cfg5(args)
+    else:
+        run_ours(args)
 
 
 if __name__ == "__main__":

@@ -804,7 +804,7 @@ void HifiganPlan::enqueue(Workspace& w, const float* mel, const float* f0, const
                     }
                     a.w_slots = resblock_weight_slots(C);
                     const int n_wt = C == 32 ? (k + 1) / 2 : k * (C / kBlockK);
-                    a.w_resident = 2 * n_wt <= a.w_slots ? 1 : 0;
+                    a.w_resident = 2 * n_wt <= a.w_slots ? 2 : (n_wt + 3 <= a.w_slots ? 1 : 0);   // both convs resident / conv1 only / streaming
                     static const bool trace_on = std::getenv("BSG_TRACE") != nullptr;
                     DevBuf tb;
                     if (trace_on) {   // per-role cycle counters of this launch, averaged over the CTAs (measurement only: synchronises)

@@ -44,7 +44,8 @@ struct ResblockArgs {
     int out_bf16;                // mode 3: out is bf16 (operand of the next stage's transposed convolution) instead of fp16
     float c0, slope_out;
     int w_slots;                 // weight tiles the shared-memory weight area holds
-    int w_resident;              // 1: 2 * n_wtiles <= w_slots, all weight tiles are loaded once per CTA
+    int w_resident;              // 2: all weight tiles of both convolutions are loaded once per CTA (2 * n_wtiles <= w_slots); 1: conv1's tiles
+                                 //    are resident and conv2's stream through the remaining slots (n_wtiles + 2 <= w_slots); 0: both stream
     unsigned long long* trace;   // optional [grid][16] cycle counters of the roles (tests/tools/gpu_probe.py), or null
 };
 
@@ -167,7 +168,8 @@ __device__ __forceinline__ void rb_mma_role(const RbMmaCtx& x) {
     constexpr uint32_t kIdesc = umma_idesc_f16(kTileM, N, /*fp16=*/true);
     constexpr int TILE16 = S::kWTileBytes >> 4;                       // weight tile size in descriptor units
     constexpr int NWT = C == 32 ? (NT + 1) / 2 : NT * NKB;            // weight tiles per convolution
-    int as = 0, ws = 0;
+    const int ring0 = x.wres == 1 ? NWT : 0;
+    int as = 0, ws = ring0;
     uint32_t aph = 0, wph = 0;
     const bool tr = x.trace != nullptr;
     long long w_acc1 = 0, w_a = 0, w_w = 0, w_acc2 = 0, w_t = 0;
@@ -183,7 +185,7 @@ __device__ __forceinline__ void rb_mma_role(const RbMmaCtx& x) {
     const uint64_t a_tap_step = static_cast<uint64_t>(x.dil) * 8;     // descriptor units of 16 bytes: dil rows x 128 B
     // all taps of k-block kb of convolution `conv` into tacc; A operand of tap tp at a_desc + tp * a_step
     auto conv_taps = [&](uint32_t tacc, uint64_t a_desc, uint64_t a_step, int conv, int kb, uint32_t first_acc) {
-        if (x.wres) {
+        if (x.wres == 2 || (x.wres == 1 && conv == 0)) {
             const uint64_t b0 = w_desc0 + static_cast<uint64_t>(conv * NWT * TILE16) + static_cast<uint64_t>(C == 32 ? 0 : kb * TILE16);
 #pragma unroll
             for (int tp = 0; tp < NT; ++tp) {
@@ -199,15 +201,16 @@ __device__ __forceinline__ void rb_mma_role(const RbMmaCtx& x) {
                 else mma_f16_x4(tacc, a_desc + tp * a_step, b, kIdesc, tp == 0 ? first_acc : 1u);
                 if (C != 32 || (tp & 1) || tp + 1 == NT) {
                     umma_commit_elect_s(x.wempty + ws * 8);
-                    if (++ws == x.w_slots) { ws = 0; wph ^= 1; }
+                    if (++ws == x.w_slots) { ws = ring0; wph ^= 1; }
                 }
             }
         }
     };
     auto conv1 = [&](int it) {
         const int buf = it & 1;
-        wait_tr(x.acc1_empty + buf * 8, ((it >> 1) & 1) ^ 1, w_acc1);
-        tc_fence_after();
+        // acc1[buf] is free without a wait of its own: conv1(it) is issued after conv2(it - 2), which waited for t_full(it - 2), and
+        // epilogue-1 signals that barrier only after it has read acc1[buf] out of TMEM
+        (void)w_acc1;
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb) {
             wait_tr(x.afull + as * 8, aph, w_a);
@@ -272,7 +275,8 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
     const int lane = threadIdx.x & 31;
     const int ntaps = args.ntaps;
     const int n_wt = C == 32 ? (ntaps + 1) / 2 : ntaps * NKB;   // weight tiles per convolution (C = 32: two taps share a 64-column tile)
-    const bool wres = args.w_resident != 0;
+    const int wres = args.w_resident;                      // 0 / 1 / 2, see ResblockArgs
+    const int ring0 = wres == 1 ? n_wt : 0;                // first slot of the streaming ring
     const int w_slots = args.w_slots;
 
     if (threadIdx.x == 32) {
@@ -304,18 +308,20 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
         const uint32_t a_bytes = static_cast<uint32_t>(args.a_rows) * 128;
-        int as = 0, ws = 0;
+        int as = 0;
         uint32_t aph = 0, wph = 0;
+        int ws = ring0;
         auto load_w = [&](const CUtensorMap* map, int wt) {   // weight tile wt of one convolution, through the ring
             mbar_wait(&wempty[ws], wph ^ 1);
             mbar_arrive_expect_tx(&wfull[ws], S::kWTileBytes);
             tma_load_2d(smem + S::kOffW + ws * S::kWTileBytes, map, &wfull[ws], wt * 64, 0);
-            if (++ws == w_slots) { ws = 0; wph ^= 1; }
+            if (++ws == w_slots) { ws = ring0; wph ^= 1; }
         };
         if (wres) {
-            mbar_arrive_expect_tx(wres_full, static_cast<uint32_t>(2 * n_wt) * S::kWTileBytes);
+            mbar_arrive_expect_tx(wres_full, static_cast<uint32_t>(wres * n_wt) * S::kWTileBytes);
             for (int wt = 0; wt < n_wt; ++wt) tma_load_2d(smem + S::kOffW + wt * S::kWTileBytes, &args.w1map, wres_full, wt * 64, 0);
-            for (int wt = 0; wt < n_wt; ++wt) tma_load_2d(smem + S::kOffW + (n_wt + wt) * S::kWTileBytes, &args.w2map, wres_full, wt * 64, 0);
+            if (wres == 2)
+                for (int wt = 0; wt < n_wt; ++wt) tma_load_2d(smem + S::kOffW + (n_wt + wt) * S::kWTileBytes, &args.w2map, wres_full, wt * 64, 0);
         }
         auto conv1_loads = [&](int it) {
             const int m = tile_of(it);
@@ -326,14 +332,14 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
                 mbar_arrive_expect_tx(&afull[as], a_bytes);
                 tma_load_3d(smem + as * S::kASlotBytes, &args.amap, &afull[as], kb * 64, o0 - halo, b);
                 if (++as == S::kAStages) { as = 0; aph ^= 1; }
-                if (!wres) {
+                if (wres == 0) {
                     if (C == 32) { for (int wt = 0; wt < n_wt; ++wt) load_w(&args.w1map, wt); }
                     else { for (int tp = 0; tp < ntaps; ++tp) load_w(&args.w1map, tp * NKB + kb); }
                 }
             }
         };
         auto conv2_loads = [&]() {
-            if (wres) return;
+            if (wres == 2) return;
             for (int kb = 0; kb < NKB; ++kb) {
                 if (C == 32) { for (int wt = 0; wt < n_wt; ++wt) load_w(&args.w2map, wt); }
                 else { for (int tp = 0; tp < ntaps; ++tp) load_w(&args.w2map, tp * NKB + kb); }
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
         x.acc1_full = smem_u32(acc1_full); x.acc1_empty = smem_u32(acc1_empty); x.acc2_full = smem_u32(acc2_full);
         x.acc2_empty = smem_u32(acc2_empty); x.t_full = smem_u32(t_full); x.t_empty = smem_u32(t_empty); x.wres_full = smem_u32(wres_full);
         x.tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
-        x.n_my = n_my; x.dil = args.dil; x.w_slots = w_slots; x.wres = wres ? 1 : 0;
+        x.n_my = n_my; x.dil = args.dil; x.w_slots = w_slots; x.wres = wres;
         x.trace = args.trace ? args.trace + blockIdx.x * 16 : nullptr;
         switch (ntaps) {
             case 3: rb_mma_role<C, 3>(x); break;
@@ -406,10 +412,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_iter_kernel(const __gr
             tc_fence_before();
             fence_proxy_async_smem();            // the tensor core reads the tile through the async proxy
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_relaxed(&acc1_empty[buf]);
-                mbar_arrive(&t_full[buf]);
-            }
+            if (lane == 0) mbar_arrive(&t_full[buf]);   // also hands acc1[buf] back (see the MMA warp)
         }
         if (tr) { unsigned long long* t = args.trace + blockIdx.x * 16; t[7] = clock64() - t_begin; t[8] = w_f; t[9] = w_te; }
     } else if (warp >= 6) {

@@ -19,7 +19,7 @@ static void launch_resblock_inst(const ResblockArgs& args, cudaStream_t stream) 
     if (args.num_tiles <= 0) return;
     B200_CHECK(args.a_rows % 8 == 0 && args.a_rows * 128 <= S::kASlotBytes, "halo box does not fit the shared-memory slot");
     B200_CHECK(args.ntaps >= 1 && args.ntaps <= kMaxTaps && (args.ntaps & 1), "odd kernel size <= 11 expected");
-    B200_CHECK(args.w_slots >= 2 && args.w_slots <= S::kWSlots, "weight ring depth");
+    B200_CHECK(args.w_slots >= 2 && args.w_slots <= S::kWSlots && args.w_resident >= 0 && args.w_resident <= 2, "weight ring depth");
     const int sms = device_sm_count();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(args.num_tiles < sms ? args.num_tiles : sms);
