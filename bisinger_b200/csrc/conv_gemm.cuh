@@ -823,7 +823,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     using S = GemmSmem<N_TILE, TERMS, PAIR>;
     static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "UMMA N constraint for M=128");
     constexpr int kTmemCols = tmem_cols_for(2 * N_TILE);
-    constexpr uint32_t kIdesc = umma_idesc_f16(PAIR ? 2 * kTileM : kTileM, N_TILE, /*fp16=*/TERMS == 2 || TERMS == 4);
+    // TERMS == 5: fp16 activations x ONE fp16 weight operand (hi only; the packing's 2^p scale still applies): the skip-sum GEMM, a
+    // once-per-step linear read-out whose weight rounding does not compound through the layers (tests/tools/exp_skip_x1.py)
+    constexpr uint32_t kIdesc = umma_idesc_f16(PAIR ? 2 * kTileM : kTileM, N_TILE, /*fp16=*/TERMS == 2 || TERMS == 4 || TERMS == 5);
     // TERMS == 4 ("fp16 + fp8 correction", PAIR only): amap[0] / wmap[0] = fp16 activations / fp16(W 2^p) as in TERMS 2; after every second
     // 64-channel k-block one 128-channel block of amap[1] = e4m3 activations x wmap[1] = e5m2(W 2^p - hi) on the fp8 pipe (K = 32 per
     // MMA, twice the rate) into the same accumulator -- see diffnet_layer.cuh

@@ -367,6 +367,10 @@ DiffusionPlan::DiffusionPlan(const bsg_diffnet_config& c, const float* w, size_t
     skip_fp8 = false;
     if (const char* e = std::getenv("BSG_SKIP_FP8")) skip_fp8 = use_fused && skip_mode == 1 && e[0] == '1';
     if (skip_fp8) launch_conv_gemm(kSkipTilePair, 4, EPI_RELU_BF16, none, nullptr, 1);
+    // skip-sum GEMM with ONE fp16 MMA per product (BSG_SKIP_X1=1|0): see conv_gemm.cuh TERMS == 5
+    skip_x1 = false;
+    if (const char* e = std::getenv("BSG_SKIP_X1")) skip_x1 = use_pair && terms == 2 && skip_mode == 1 && !skip_fp8 && e[0] == '1';
+    if (skip_x1) launch_conv_gemm(kSkipTilePair, 5, EPI_RELU_BF16, none, nullptr, 1);
     if (gate_mode == 2) launch_conv_gemm(256, terms, EPI_GATE, none, nullptr, 2);
     if (skip_mode == 2) launch_conv_gemm(kSkipTilePair, terms, EPI_RELU_BF16, none, nullptr, 2);
 }
@@ -619,7 +623,7 @@ float DiffusionPlan::time_kernel(int which, int B, int T, int reps, cudaStream_t
             } else if (which == 3) launch_diffnet_layer(fused_args(w, l, 1, lut.as<float>()), st, fused_mc);
             else if (which == 0) launch_conv_gemm(256, terms, EPI_GATE, gate_args(w, l), st, gate_mode);
             else if (which == 1) launch_conv_gemm(kResTile, terms, EPI_RES_SKIP, resskip_args(w, l, lut.as<float>()), st);
-            else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, skip_fp8 ? 4 : terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
+            else launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, skip_fp8 ? 4 : (skip_x1 ? 5 : terms), EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
             ++launches, ++g_launch_count;
         }
     };
@@ -725,7 +729,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         }
     }
     {   // skip sum sum_l (W_skip,l z_l + b_skip,l) / sqrt(L) (net.py:77-78,126) and skip_projection + ReLU (:127-128): one K = L*C GEMM
-        launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, skip_fp8 ? 4 : terms, EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
+        launch_conv_gemm(use_pair ? kSkipTilePair : kResTile, skip_fp8 ? 4 : (skip_x1 ? 5 : terms), EPI_RELU_BF16, skipsum_args(w), st, skip_mode);
         ++launches, ++g_launch_count;
     }
     {   // output_projection (net.py:129) fused with the DDPM posterior update (shallow_diffusion_tts.py:149-166)

@@ -153,8 +153,8 @@ static void launch_layer_inst(const LayerArgs& args, cudaStream_t stream) {
     B200_CUDA(attr_err);
     constexpr int kCtas = MC ? 4 : 2;
     // The layer-to-layer dataflow of a multi-layer launch makes CTAs wait for rows other CTAs of the grid produce: every CTA of
-    // the grid must be resident.  The grid is therefore sized from what the driver says fits on THIS context's share of the device,
-    // and the launch is cooperative (below), which makes the scheduler place the whole grid or nothing.
+    // the grid must be resident.  The grid is therefore sized from what the driver says fits on THIS context's share of the device
+    // (see the co-residency notes at the launch below).
     const int max_clusters = max_active_clusters(kern, kCtas, kLayerThreads, LayerSmem::kTotal);
     if (args.n_row_tiles <= 0) return;
     B200_CHECK(args.n_layers == 1 || args.flags != nullptr, "a multi-layer launch needs the row-tile completion counters");
@@ -167,10 +167,36 @@ static void launch_layer_inst(const LayerArgs& args, cudaStream_t stream) {
     cfg.stream = stream;
     cudaLaunchAttribute attr[3];
     int na = 0;
-    // co-residency guarantee for the cross-CTA waits: a cooperative launch is only scheduled when ALL its CTAs fit at
-    // once, so a concurrent kernel of another stream / plan can delay this launch but cannot strand half of its grid.
-    // (BSG_LAYER_COOP=0: plain launch with the PDL attribute, as in round 1 -- safe only on an otherwise idle device.)
-    static const bool coop = [] { const char* e = std::getenv("BSG_LAYER_COOP"); return !(e && e[0] == '0'); }();
+    // Co-residency of the whole grid is what the cross-CTA waits need.  Three measures:
+    //  (1) the grid is sized from cudaOccupancyMaxActiveClusters on this context (above), so a partitioned device (MPS active-thread
+    //      percentage, green contexts) gets a grid that fits;
+    //  (2) multi-layer launches of one process are serialised per device across streams (an event chain, below): two fused kernels of two
+    //      plans / streams never overlap, so neither can strand half of the other's grid.  Inside a stream capture the chain cannot be
+    //      recorded; captured graphs of different streams must not be replayed concurrently;
+    //  (3) BSG_LAYER_COOP=1 additionally launches cooperatively (the scheduler then places the whole grid or nothing).  Off by default:
+    //      Nsight Compute cannot replay a cooperative cluster launch (the launch fails under ncu, profiles/r02_e), and profiling must work.
+    // A kernel of ANOTHER process on the same SMs is outside our control: the bounded wait in wait_inputs traps after ~4 s instead of
+    // hanging, and BSG_LAYER_STACK=0 (one launch per layer, no cross-CTA waits) is the mode for shared GPUs.
+    static const bool coop = [] { const char* e = std::getenv("BSG_LAYER_COOP"); return e && e[0] == '1'; }();
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (args.n_layers > 1) cudaStreamIsCapturing(stream, &cap);
+    const bool chain = args.n_layers > 1 && cap == cudaStreamCaptureStatusNone;
+    static std::mutex chain_mu;
+    static std::map<int, cudaEvent_t> chain_ev;     // device -> completion of the last eager multi-layer launch
+    cudaEvent_t ev = nullptr;
+    if (chain) {
+        int dev = 0;
+        B200_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(chain_mu);
+        auto it = chain_ev.find(dev);
+        if (it == chain_ev.end()) {
+            B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            chain_ev[dev] = ev;
+        } else {
+            ev = it->second;
+            B200_CUDA(cudaStreamWaitEvent(stream, ev, 0));
+        }
+    }
     if (coop && args.n_layers > 1) {
         attr[na].id = cudaLaunchAttributeCooperative;
         attr[na].val.cooperative = 1;
@@ -189,6 +215,7 @@ static void launch_layer_inst(const LayerArgs& args, cudaStream_t stream) {
     cfg.numAttrs = na;
     B200_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
     B200_CUDA(cudaGetLastError());
+    if (chain) B200_CUDA(cudaEventRecord(ev, stream));
 }
 void launch_diffnet_layer(const LayerArgs& args, cudaStream_t stream, bool mc) {
     if (mc) launch_layer_inst<1>(args, stream);
@@ -232,6 +259,7 @@ void launch_conv_gemm(int n_tile, int terms, int epi, const ConvGemmArgs& args, 
     // DiffNet, fp16x2 per-layer GEMMs
     B200_CASE(256, 2, EPI_GATE) B200_PAIR(256, 2, EPI_GATE) B200_CASE(128, 2, EPI_RES_SKIP)
     B200_CASE(128, 2, EPI_RELU_BF16) B200_PAIR(256, 2, EPI_RELU_BF16) B200_PAIR(256, 4, EPI_RELU_BF16) B200_PAIR(256, 4, EPI_F32)
+    B200_PAIR(256, 5, EPI_RELU_BF16)
     // HiFi-GAN
     B200_PAIR(256, 1, EPI_BIAS_ACT) B200_PAIR(128, 1, EPI_BIAS_ACT)
     B200_CASE(256, 1, EPI_BIAS_ACT) B200_CASE(128, 1, EPI_BIAS_ACT) B200_CASE(64, 1, EPI_BIAS_ACT) B200_CASE(32, 1, EPI_BIAS_ACT)

@@ -33,6 +33,7 @@ public:
     bool use_pair = true;    // 2-CTA (cta_group::2) tiles for the tensor-bound GEMMs (gate GEMM, skip-sum GEMM)
     bool use_fused = false;  // one fused kernel per ResidualBlock (fp16x2 mode)
     bool skip_fp8 = false;   // skip-sum GEMM: fp16 MMA + fp8 correction MMA (needs the fused kernel's e4m3 copy of z)
+    bool skip_x1 = false;    // skip-sum GEMM: one fp16 MMA per product (no weight-rounding correction term)
     bool fused_mc = false;   // ... on 4-CTA clusters with multicast weight tiles
     bool fused_stack = true;    // ... all layers of a step in one launch (row-tile dataflow between the layers); BSG_LAYER_STACK=0: one launch per layer
     int gate_mode = 1, skip_mode = 1;   // launch_conv_gemm cluster mode of those two GEMMs: 0 single CTA, 1 pair, 2 two pairs + multicast weights
