@@ -50,6 +50,10 @@ class PeConfig(C.Structure):
                                        "use_uv")] + [("f0_mean", C.c_float), ("f0_std", C.c_float)]
 
 
+class FftConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("hidden_size", "num_layers", "num_heads", "ffn_kernel", "ffn_act", "use_pos_embed", "out_dims")]
+
+
 # every symbol include/bisinger_b200.h declares (tests check that the library exports all of them)
 EXPORTS = (
     "bsg_abi_version", "bsg_last_error", "bsg_kernel_launch_count",
@@ -57,6 +61,7 @@ EXPORTS = (
     "bsg_diffusion_time_kernel",
     "bsg_hifigan_plan_create", "bsg_hifigan_plan_destroy", "bsg_hifigan_forward", "bsg_hifigan_source",
     "bsg_pe_plan_create", "bsg_pe_plan_destroy", "bsg_pe_forward",
+    "bsg_fft_plan_create", "bsg_fft_plan_destroy", "bsg_fft_forward",
     "bsg_selftest_conv",
 )
 
@@ -94,6 +99,10 @@ def lib() -> C.CDLL:
     L.bsg_pe_plan_destroy.argtypes = [vp]
     L.bsg_pe_plan_destroy.restype = None
     L.bsg_pe_forward.argtypes = [vp, fp, ip, ip, fp, fp, vp]
+    L.bsg_fft_plan_create.argtypes = [C.POINTER(FftConfig), C.POINTER(C.c_float), C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.bsg_fft_plan_destroy.argtypes = [vp]
+    L.bsg_fft_plan_destroy.restype = None
+    L.bsg_fft_forward.argtypes = [vp, fp, fp, ip, ip, fp, fp, vp]
     L.bsg_selftest_conv.argtypes = [fp, C.POINTER(C.c_float), C.POINTER(C.c_float), ip, ip, ip, ip, ip, C.POINTER(C.c_int),
                                     ip, ip, fp, vp]
     if L.bsg_abi_version() != 1:

@@ -39,6 +39,11 @@ struct bsg_pe_plan {
     template <class... A> explicit bsg_pe_plan(A&&... a) : impl(std::forward<A>(a)...) {}
 };
 
+struct bsg_fft_plan {
+    b200::FftDecoderPlan impl;
+    template <class... A> explicit bsg_fft_plan(A&&... a) : impl(std::forward<A>(a)...) {}
+};
+
 extern "C" {
 
 int bsg_abi_version(void) { return BSG_ABI_VERSION; }
@@ -125,6 +130,22 @@ int bsg_pe_forward(bsg_pe_plan* plan, const float* mel, int B, int T, float* pit
     return guarded([&] {
         B200_CHECK(plan && mel && pitch_pred && f0, "null argument");
         plan->impl.forward(mel, B, T, pitch_pred, f0, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int bsg_fft_plan_create(const bsg_fft_config* cfg, const float* weights_host, size_t n_weights, int device, bsg_fft_plan** out) {
+    return guarded([&] {
+        B200_CHECK(cfg && weights_host && out, "null argument");
+        *out = new bsg_fft_plan(*cfg, weights_host, n_weights, device);
+    });
+}
+void bsg_fft_plan_destroy(bsg_fft_plan* plan) { delete plan; }
+
+int bsg_fft_forward(bsg_fft_plan* plan, const float* x, const float* tgt_nonpad, int B, int T, float* hidden_out, float* mel_out,
+                    void* stream) {
+    return guarded([&] {
+        B200_CHECK(plan && x, "null argument");
+        plan->impl.forward(x, tgt_nonpad, B, T, hidden_out, mel_out, static_cast<cudaStream_t>(stream));
     });
 }
 

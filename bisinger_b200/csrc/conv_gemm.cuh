@@ -284,6 +284,10 @@ enum : int {
     BA_ACT_FROM_B = 32,  // the bf16 activation is taken from the accumulated f32_b value instead of y
     BA_ROWS = 64,        // the epilogue keeps the accumulator's row-per-thread ownership and uses 256-bit global accesses (see below)
     BA_ROWS_RMW = 128,   // ... also when it reads (BA_ADD_RES / BA_ACCUM_F32B)
+    BA_GELU = 256,       // write-only row epilogue: y = gelu((acc + bias) * c0) (exact erf form, F.gelu) before the activation output -- the FFT
+                         //    blocks' conv-FFN (common_layers.py:630-637: ffn_1 -> * kernel_size^-0.5 -> gelu)
+    BA_RELU_SCALED = 512,   // ... same with relu instead of gelu (hparams['ffn_act'] == 'relu')
+    BA_ACT_F16 = 1024,   // write-only row epilogue: the activation output is ONE fp16 tensor (out_hi viewed as __half) instead of bf16 hi/lo
 };
 
 // b: batch index, t_warp: first row (within the batch) of this warp's 32 accumulator lanes, grp: column group of the
@@ -561,6 +565,13 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, int Lrows, uint
                     const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + n) + j);
                     v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
                 }
+                if (e.flags & (BA_GELU | BA_RELU_SCALED)) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float y = v[i] * e.c0;
+                        v[i] = (e.flags & BA_GELU) ? 0.5f * y * (1.0f + erff(y * 0.70710678118654752440f)) : fmaxf(y, 0.0f);
+                    }
+                }
                 if (e.flags & BA_WRITE_F32) {
                     float* dst = e.f32_a + row * e.out_pitch + e.out_col0 + n;
                     if (ok) {
@@ -573,7 +584,19 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, int Lrows, uint
                         }
                     }
                 }
-                if (e.flags & BA_WRITE_ACT) {
+                if ((e.flags & BA_WRITE_ACT) && (e.flags & BA_ACT_F16)) {
+                    uint32_t q[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const __half2 hh = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.0f), 65504.0f), fminf(fmaxf(v[2 * i + 1], -65504.0f), 65504.0f));
+                        q[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    if (ok) {
+                        __nv_bfloat16* dh = e.out_hi + row * e.act_pitch + n;
+                        stg256(dh, reinterpret_cast<const uint32_t(&)[8]>(q[0]));
+                        stg256(dh + 16, reinterpret_cast<const uint32_t(&)[8]>(q[8]));
+                    }
+                } else if (e.flags & BA_WRITE_ACT) {
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {

@@ -161,4 +161,36 @@ private:
     std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
 };
 
+// FastSpeech FFT blocks (FastspeechDecoder) + mel_out: SURVEY.md section 8f-3 (fft_decoder.cu)
+class FftDecoderPlan {
+public:
+    FftDecoderPlan(const bsg_fft_config& cfg, const float* weights, size_t n_weights, int device);
+    ~FftDecoderPlan();
+    void forward(const float* x, const float* tgt_nonpad, int B, int T, float* hidden_out, float* mel_out, cudaStream_t st);
+
+    bsg_fft_config cfg;
+    int device;
+    unsigned long long launches = 0;
+
+private:
+    struct Workspace;
+    struct Conv {
+        PackedW w;
+        DevBuf bias;
+        int cin = 0, cout = 0, k = 1;
+    };
+    struct Layer {
+        DevBuf ln1_g, ln1_b, ln2_g, ln2_b;
+        Conv in_proj, out_proj, ffn1, ffn2;
+    };
+    Workspace& workspace(int B, int T);
+
+    std::vector<Layer> layers;
+    Conv mel_out;
+    DevBuf ln_g, ln_b, pos_freq;
+    float pos_alpha = 1.0f;
+    std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
+    unsigned long long use_clock = 0;
+};
+
 }  // namespace b200

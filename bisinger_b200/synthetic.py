@@ -168,6 +168,42 @@ def pe_state(seed: int = 777, conv_layers: int = 2, n_mel: int = 80, C: int = 25
     return sd
 
 
+def fft_state(seed: int = 555, layers: int = 4, C: int = 256, k: int = 9, out_dims: int = 80) -> Dict[str, Tensor]:
+    """State dict with the parameter / buffer names of FastspeechDecoder (modules/fastspeech/tts_modules.py:253-283,340-347;
+    EncSALayer modules/commons/common_layers.py:680-701) plus ``mel_out.*`` (modules/fastspeech/fs2.py:60).  Non-trivial LayerNorm
+    affines and a pos_embed_alpha != 1 so that every term matters."""
+    g = _gen(seed)
+    sd: Dict[str, Tensor] = {}
+    sd["pos_embed_alpha"] = torch.tensor([0.9])
+    sd["embed_positions._float_tensor"] = torch.zeros(1)
+    xav = lambda out, inn: _uniform(g, (out, inn), math.sqrt(6.0 / (out + inn)))
+    for i in range(layers):
+        p = f"layers.{i}.op."
+        for ln in ("layer_norm1", "layer_norm2"):
+            sd[p + ln + ".weight"] = 1.0 + _uniform(g, (C,), 0.3)
+            sd[p + ln + ".bias"] = _uniform(g, (C,), 0.2)
+        sd[p + "self_attn.in_proj_weight"] = xav(3 * C, C) * 2.0        # sharper attention than xavier alone: the softmax must matter
+        sd[p + "self_attn.out_proj.weight"] = xav(C, C)
+        sd[p + "ffn.ffn_1.weight"] = _normal(g, (4 * C, C, k), math.sqrt(2.0 / (C * k)) * math.sqrt(k))
+        sd[p + "ffn.ffn_1.bias"] = _uniform(g, (4 * C,), 0.1)
+        sd[p + "ffn.ffn_2.weight"] = xav(C, 4 * C)
+        sd[p + "ffn.ffn_2.bias"] = _uniform(g, (C,), 0.1)
+    sd["layer_norm.weight"] = 1.0 + _uniform(g, (C,), 0.3)
+    sd["layer_norm.bias"] = _uniform(g, (C,), 0.2)
+    if out_dims:
+        sd["mel_out.weight"] = xav(out_dims, C)
+        sd["mel_out.bias"] = _uniform(g, (out_dims,), 0.5) - 3.0
+    return sd
+
+
+def fft_inputs(seed: int, B: int, T: int, C: int = 256, pad_tail: int = 0) -> Tensor:
+    """decoder_inp [B,T,C] ~ N(0,1); the last ``pad_tail`` frames of every odd batch row are all-zero padding frames."""
+    x = torch.randn((B, T, C), generator=_gen(seed))
+    if pad_tail > 0:
+        x[1::2, T - pad_tail:, :] = 0.0
+    return x
+
+
 def pe_inputs(seed: int, B: int, T: int, M: int = 80, pad_tail: int = 0) -> Tensor:
     """Log-mel input [B,T,80] as vocoder_inputs draws it; the last `pad_tail` frames of every odd batch row are all-zero
     padding frames (pe.py:30,145: padding = frames whose |mel| sums to 0)."""

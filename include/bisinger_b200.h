@@ -226,6 +226,42 @@ void bsg_pe_plan_destroy(bsg_pe_plan* plan);
 int bsg_pe_forward(bsg_pe_plan* plan, const float* mel, int B, int T, float* pitch_pred, float* f0, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * FastSpeech FFT blocks: the mel-rate decoder of FastSpeech2 / FastSpeech2MIDI and its mel_out projection -- the conditioner's
+ * handoff to the sampler.
+ * Replaces  x = self.decoder(decoder_inp); x = self.mel_out(x); return x * tgt_nonpadding   modules/fastspeech/fs2.py:236-240
+ * modules: modules/fastspeech/tts_modules.py:253-310 (FFTBlocks), :340-347 (FastspeechDecoder), modules/commons/common_layers.py:664-731
+ * (EncSALayer), :598-644 (TransformerFFNLayer), :199-420 (MultiheadAttention, bias=False); eval mode (no dropout).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct bsg_fft_plan bsg_fft_plan;
+typedef struct {
+    int hidden_size;    /* 256  hparams['hidden_size']                                                              */
+    int num_layers;     /* 4    hparams['dec_layers']                                                               */
+    int num_heads;      /* 2    hparams['num_heads'] (head width 128)                                               */
+    int ffn_kernel;     /* 9    hparams['dec_ffn_kernel_size'], padding 'SAME'                                      */
+    int ffn_act;        /* 0 = gelu (hparams['ffn_act'] default), 1 = relu                                          */
+    int use_pos_embed;  /* 1    FFTBlocks(use_pos_embed=True): x + pos_embed_alpha * SinusoidalPositionalEmbedding  */
+    int out_dims;       /* 80 = mel_out Linear present (fs2.py:60), 0 = FFT blocks only                             */
+} bsg_fft_config;
+
+/* weights_host: float32, in this order (names of the FastspeechDecoder / FastSpeech2 state_dict):
+ *   pos_embed_alpha[1], frequencies[C/2] = exp(arange(C/2) * -(ln 1e4 / (C/2 - 1)))   (common_layers.py:130-132)
+ *   for i < num_layers: layers.i.op.layer_norm1.{weight,bias}[C], layers.i.op.self_attn.in_proj_weight[3C][C],
+ *                       layers.i.op.self_attn.out_proj.weight[C][C], layers.i.op.layer_norm2.{weight,bias}[C],
+ *                       layers.i.op.ffn.ffn_1.{weight[4C][C][k],bias[4C]}, layers.i.op.ffn.ffn_2.{weight[C][4C],bias[C]}
+ *   layer_norm.{weight,bias}[C]
+ *   if out_dims > 0: mel_out.{weight[out_dims][C],bias[out_dims]}                                                   */
+int bsg_fft_plan_create(const bsg_fft_config* cfg, const float* weights_host, size_t n_weights, int device, bsg_fft_plan** out);
+void bsg_fft_plan_destroy(bsg_fft_plan* plan);
+
+/* FastspeechDecoder.forward(x) [+ mel_out, * tgt_nonpadding].
+ *   x           device f32 [B][T][C]   decoder_inp; all-zero frames are padding (tts_modules.py:291)
+ *   tgt_nonpad  device f32 [B][T] (1 / 0) or NULL: mel_out is multiplied by it (fs2.py:240, (mel2ph > 0))
+ *   hidden_out  device f32 [B][T][C] or NULL: the decoder's return value (layer_norm(x) * nonpadding)
+ *   mel_out     device f32 [B][T][out_dims] or NULL                                                                 */
+int bsg_fft_forward(bsg_fft_plan* plan, const float* x, const float* tgt_nonpad, int B, int T, float* hidden_out, float* mel_out,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Kernel self-test: C[b][l][n] = bias[n] + sum_taps A[b][l+shift][:] . W[n][tap][:] through the same tcgen05
  * implicit-GEMM kernel the plans use.  Device pointers; A f32 [B][L][Cin], W f32 host [N][ntaps][Cin].
  * ------------------------------------------------------------------------------------------------ */

@@ -478,6 +478,65 @@ def pe_forward(p: Dict[str, Tensor], mel: Tensor, hp: Optional[dict] = None) -> 
 # Metrics used by the parity tests
 # --------------------------------------------------------------------------------------
 
+# --------------------------------------------------------------------------------------
+# FastSpeech FFT blocks: the mel-rate decoder + mel_out
+# --------------------------------------------------------------------------------------
+FFT_HPARAMS = dict(hidden_size=256, dec_layers=4, num_heads=2, dec_ffn_kernel_size=9, ffn_act="gelu", use_pos_embed=True)
+
+
+def fft_n_layers(p: Dict[str, Tensor]) -> int:
+    n = 0
+    while f"layers.{n}.op.layer_norm1.weight" in p:
+        n += 1
+    return n
+
+
+def fft_decoder_forward(p: Dict[str, Tensor], x: Tensor, hp: Optional[dict] = None, mel_out: Optional[Dict[str, Tensor]] = None,
+                        tgt_nonpad: Optional[Tensor] = None):
+    """FastspeechDecoder.forward in eval mode (modules/fastspeech/tts_modules.py:286-310 FFTBlocks.forward, :340-347) over
+    TransformerEncoderLayer -> EncSALayer (modules/commons/common_layers.py:696-731): x [B,T,C] -> hidden [B,T,C]; with
+    ``mel_out`` = {'weight','bias'} also the projection and mask of FastSpeech2.run_decoder (modules/fastspeech/fs2.py:236-240).
+    The attention is MultiheadAttention(self_attention=True, bias=False) -> F.multi_head_attention_forward (:321-345): no biases,
+    q scaled by head_dim^-0.5, key_padding_mask = the padding frames, softmax over the keys."""
+    hp = {**FFT_HPARAMS, **(hp or {})}
+    B, T, C = x.shape
+    H = hp["num_heads"]
+    d = C // H
+    k = hp["dec_ffn_kernel_size"]
+    pad = x.abs().sum(-1).eq(0)                                        # tts_modules.py:291
+    nonpad = (~pad).float()[:, :, None]                                # :292 (as [B,T,1]; the reference works in [T,B,C])
+    if hp["use_pos_embed"]:                                            # :293-296
+        pos = pe_positions(x[..., 0])
+        table = pe_pos_table(int(pos.max()) + 2, C).to(x.device)
+        x = x + p["pos_embed_alpha"] * table[pos]
+    x = x * nonpad                                                     # :298
+    for i in range(fft_n_layers(p)):
+        pre = f"layers.{i}.op."
+        res = x                                                        # common_layers.py:703-714
+        h = F.layer_norm(x, (C,), p[pre + "layer_norm1.weight"], p[pre + "layer_norm1.bias"], 1e-5)
+        qkv = F.linear(h, p[pre + "self_attn.in_proj_weight"])
+        q, kk, v = qkv.chunk(3, dim=-1)
+        q = q * d ** -0.5
+        heads = lambda t: t.reshape(B, T, H, d).transpose(1, 2)       # [B,H,T,d]
+        sc = heads(q) @ heads(kk).transpose(-1, -2)                    # [B,H,T,T]
+        sc = sc.masked_fill(pad[:, None, None, :], float("-inf"))
+        o = (torch.softmax(sc, dim=-1) @ heads(v)).transpose(1, 2).reshape(B, T, C)
+        x = (res + F.linear(o, p[pre + "self_attn.out_proj.weight"])) * nonpad
+        res = x                                                        # :716-722, :626-644
+        h = F.layer_norm(x, (C,), p[pre + "layer_norm2.weight"], p[pre + "layer_norm2.bias"], 1e-5)
+        h = F.conv1d(h.transpose(1, 2), p[pre + "ffn.ffn_1.weight"], p[pre + "ffn.ffn_1.bias"], padding=k // 2).transpose(1, 2)
+        h = h * k ** -0.5
+        h = F.gelu(h) if hp["ffn_act"] == "gelu" else F.relu(h)
+        x = (res + F.linear(h, p[pre + "ffn.ffn_2.weight"], p[pre + "ffn.ffn_2.bias"])) * nonpad
+    x = F.layer_norm(x, (C,), p["layer_norm.weight"], p["layer_norm.bias"], 1e-5) * nonpad    # tts_modules.py:303-304
+    if mel_out is None:
+        return x
+    m = F.linear(x, mel_out["weight"], mel_out["bias"])                # fs2.py:238-240
+    if tgt_nonpad is not None:
+        m = m * tgt_nonpad[:, :, None]
+    return x, m
+
+
 def snr_db(ref: Tensor, out: Tensor) -> float:
     ref = ref.double().flatten()
     out = out.double().flatten()

@@ -22,6 +22,13 @@ class Scheme:
             return F.conv1d(x, w, b, **kw)
         xh, xl = split(x, dt)
         wh, wl = split(w, dt)
+        if wt == "alt":
+            # ONE fp16 weight operand whose rounding alternates from step to step: W_a = fp16(W) on even steps, W_b = fp16(2 W - W_a) on
+            # odd steps (rounding errors of opposite sign): each step has the fp16x1 error, but the SYSTEMATIC part -- what accumulates
+            # over the 100 steps -- cancels pairwise, since consecutive steps see nearly the same activations
+            if getattr(self, "parity", 0):
+                wh = r(2.0 * w - wh, dt)
+            return F.conv1d(xh, wh, b, **kw)
         y = F.conv1d(xh, wh, b, **kw)
         if a == 2:
             y = y + F.conv1d(xl, wh, None, **kw)
@@ -80,6 +87,7 @@ def sample(p, sched, inp, K, S):
     cache = {}
     for k, t in enumerate(reversed(range(K))):
         B = x.shape[0]
+        S.parity = k & 1
         eps = diffnet(p, x, torch.full((B,), t), cond, S, cache)
         x0 = (sched["sqrt_recip_alphas_cumprod"][t] * x - sched["sqrt_recipm1_alphas_cumprod"][t] * eps).clamp(-1, 1)
         mean = sched["posterior_mean_coef1"][t] * x0 + sched["posterior_mean_coef2"][t] * x
@@ -119,6 +127,11 @@ if __name__ == "__main__":
                 Scheme("cur but cp fp16", hf, 1, 2, per={**side, "cp": hf}),
                 Scheme("cur but cp bf16", hf, 1, 2, per={**side, "cp": bf})]
     schemes += [Scheme("cur + state fp16 (x carried as fp16(x+d))", hf, 1, 2, state16="fp16", per={**side, "gate": W52})]
+    WA = (hf, 1, "alt")
+    schemes += [Scheme("alt: gate+res+skip fp16x1 alternating rounding, state fp16", hf, 1, 2, state16="fp16", per={**side, "gate": WA, "res": WA, "skip": WA}),
+                Scheme("alt: gate+res alternating, skip Wsplit, state fp16", hf, 1, 2, state16="fp16", per={**side, "gate": WA, "res": WA}),
+                Scheme("alt: gate alternating only, state fp16", hf, 1, 2, state16="fp16", per={**side, "gate": WA}),
+                Scheme("noalt: gate+res+skip fp16x1, state fp16", hf, 1, 2, state16="fp16", per={**side, "gate": W1, "res": W1, "skip": W1})]
     sel = sys.argv[1:]
     for seed, (B, T) in ((7, (2, 40)), (8, (1, 96))):
         sd = synth.diffnet_state(1234)
