@@ -292,6 +292,26 @@ def run_ours(args):
         e3.record(stream); pe(mel_t); e4.record(stream)
         torch.cuda.synchronize(dev)
         line["breakdown_ms"]["pitch_extractor_not_in_step"] = round(e3.elapsed_time(e4), 3)
+        # the conditioner's mel-rate handoff (FastSpeech FFT decoder + mel_out): once per batch, before the sampler;
+        # reported beside the step like the PitchExtractor (the metric's workload feeds the sampler a synthetic fs2_mel / cond)
+        try:
+            from bisinger_b200.fft import B200FastspeechDecoder
+            fsd = synth.fft_state(555)
+            dec = B200FastspeechDecoder(hparams=dict(hidden_size=HID, dec_layers=4, num_heads=2, dec_ffn_kernel_size=9)).eval()
+            dec.load_state_dict({k: v for k, v in fsd.items() if not k.startswith("mel_out.")}, strict=True)
+            mo = torch.nn.Linear(HID, MEL)
+            mo.load_state_dict({"weight": fsd["mel_out.weight"], "bias": fsd["mel_out.bias"]})
+            dec, mo = dec.to(dev), mo.to(dev)
+            tgt = torch.ones((B, T), device=dev)
+            for _ in range(2):
+                dec.run_decoder(cond_d, tgt, mo)
+            e5, e6 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e5.record(stream); dec.run_decoder(cond_d, tgt, mo); e6.record(stream)
+            torch.cuda.synchronize(dev)
+            line["breakdown_ms"]["fft_decoder_handoff_not_in_step"] = round(e5.elapsed_time(e6), 3)
+            del dec, mo
+        except Exception as e:
+            line["breakdown_ms"]["fft_decoder_handoff_not_in_step"] = "unavailable: " + repr(e)[:120]
         line["pipeline_algorithmic_tflops"] = round((FLOPS_DIFFNET_FRAME_STEP_HOISTED * K_STEP + FLOPS_COND_ONCE_FRAME + FLOPS_HIFIGAN_FRAME) * B * T * world * args.steps / (ms * 1e-3) / 1e12, 1)
         if world == 1:
             line["plms_shipped_config"] = plms_shipped(dev, synth, cond_d, args.precision, B, T)
