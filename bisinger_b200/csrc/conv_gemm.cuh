@@ -335,7 +335,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, int Lrows, uint
                 if (B200_ROW_OK(rp)) {
                     const long long off = off0 + rp * st;
                     const float2 x = make_float2(fmaxf(o[rp].x + bias.x, 0.0f), fmaxf(o[rp].y + bias.y, 0.0f));
-                    st2(e.f32_a + off, x);
+                    if (e.f32_a != nullptr) st2(e.f32_a + off, x);   // the fp32 residual stream: not kept by the fused layer kernel
                     st_operand2<2>(e, make_float2(x.x + d.x, x.y + d.y), off);
                     if (e.out8 != nullptr)
                         *reinterpret_cast<uint16_t*>(e.out8 + off) = __nv_cvt_float2_to_fp8x2(make_float2(x.x + d.x, x.y + d.y), __NV_SATFINITE, __NV_E4M3);

@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
                 } else {
                     const int ng = ng0 + op.n;
                     mbar_wait_tr(&zfull_bar[ng & 1], static_cast<uint32_t>((ng >> 1) & 1), tr_on, w_z);   // this CTA's z rows of the tile are in global memory
+                    asm volatile("fence.proxy.async.global;" ::: "memory");   // reader side of the same hand-over
                     for (int kb = 0; kb < 4; ++kb) {
                         load_a(&args.z, kTileM * 128, l * C + kb * 64, t0, b);
                         load_w(&lp.wr[0], kb * 64, rank * 128);
@@ -493,9 +494,13 @@ __global__ void __launch_bounds__(kLayerThreads, 1) diffnet_layer_kernel(const _
         bool z_pending = false;   // z rows stored by the previous gate op, not yet fenced / signalled
         int z_tile = 0;           // ... and the local row tile they belong to
         auto publish_z = [&]() {
-            // the z rows are read back by this CTA's TMA loads of R(n): order the generic-proxy stores before the async
-            // proxy, then signal the producer.  Deferred to the start of the next op (the stores have drained by then and
-            // the fence returns at once) unless that op is the residual GEMM that needs them.
+            // the z rows are read back by this CTA's TMA loads of R(n).  The TMA unit reads L2, not this SM's store path: the
+            // stores must be PERFORMED at device scope (fence.acq_rel.gpu waits for their acknowledgements) before they are
+            // ordered against the async proxy and the producer is signalled -- an mbarrier arrive is a CTA-scope release and by
+            // itself let a load overtake a store still on its way to L2 (profiles/r02_c: a stale z tile, i.e. the previous
+            // diffusion step's values, in about one of three FIRST samplings on a new workspace inside the GPU test suite).  Deferred to the start of the next
+            // op (the stores have drained by then and the fences return at once) unless that op is the residual GEMM that needs them.
+            __threadfence();
             asm volatile("fence.proxy.async.global;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&zfull_bar[z_tile & 1]);

@@ -697,7 +697,7 @@ void DiffusionPlan::enqueue_step(Workspace& w, int t, int k_exec, const float* n
         set_w(a, inproj, 256);
         set_taps(a, 0, 0, (M + kBlockK - 1) / kBlockK, kOneTap, 1, 0);
         a.epi.bias = inproj_bias.as<float>();
-        a.epi.f32_a = w.xres.as<float>();
+        a.epi.f32_a = use_fused ? nullptr : w.xres.as<float>();   // fused layers carry the stream as the fp16 conv input only
         a.epi.out_hi = w.xa_hi.as<__nv_bfloat16>(); a.epi.out_lo = nz(w.xa_lo);
         a.epi.out_fp16 = terms == 2;
         a.epi.dvec = lut_t;

@@ -58,6 +58,10 @@ struct DevBuf {
         if (n == 0) n = 16;
         B200_CUDA(cudaMalloc(&p, n));
         bytes = n;
+        // debugging aid (BSG_ALLOC_FILL=<hex byte>): fill every fresh device buffer, e.g. ff = NaN patterns in f32 / f16 / e4m3, so a
+        // read of memory the path never wrote shows up in the results instead of depending on what the allocation held before
+        static const int fill = [] { const char* e = getenv("BSG_ALLOC_FILL"); return e ? static_cast<int>(strtol(e, nullptr, 16)) : -1; }();
+        if (fill >= 0) B200_CUDA(cudaMemset(p, fill, n));
     }
     void ensure(size_t n) {
         if (n > bytes) alloc(n);

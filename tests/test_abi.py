@@ -109,3 +109,33 @@ def test_library_sass_uses_tcgen05_tma_tmem():
         assert mnemonic in sass, mnemonic
     assert " HMMA." not in sass and "HGMMA" not in sass
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+
+
+def test_parameter_changes_invalidate_device_plans():
+    """a plan holds packed copies of the weights on the device; load_state_dict / .to() / a reloaded denoiser must drop it
+    (a stale plan would keep computing with the old weights without any error).  Checked on the host: the cached handles are reset."""
+    from bisinger_b200.fft import B200FastspeechDecoder
+    net = B200DiffNet(80)
+    net._standalone_plan = object()
+    v0 = getattr(net, "_version", 0)
+    net.load_state_dict(synth.diffnet_state(1), strict=True)
+    assert net._standalone_plan is None and net._version == v0 + 1
+    gd = B200GaussianDiffusion(None, 80, net, timesteps=100, K_step=100, betas=torch.linspace(1e-4, 0.06, 100), spec_min=synth.SPEC_MIN,
+                               spec_max=synth.SPEC_MAX)
+    gd._plan, gd._plan_version = object(), net._version
+    net.load_state_dict(synth.diffnet_state(2), strict=True)          # utils.load_ckpt(model.denoise_fn, ...) behind the sampler's back
+    assert gd._plan_version != net._version                            # .plan rebuilds on next use
+    gd._plan = object()
+    gd.load_state_dict(gd.state_dict())
+    assert gd._plan is None
+    gen = B200HifiGanGenerator(synth.HIFIGAN_CONFIG)
+    gen._plan = object()
+    gen.float()                                                        # any _apply (.to / .cuda / .float)
+    assert gen._plan is None
+    gen._plan = object()
+    gen.load_state_dict(gen.state_dict())
+    assert gen._plan is None
+    dec = B200FastspeechDecoder(hparams=dict(hidden_size=256, dec_layers=1, num_heads=2, dec_ffn_kernel_size=9))
+    dec._plan = object()
+    dec.load_state_dict(dec.state_dict())
+    assert dec._plan is None

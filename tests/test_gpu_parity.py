@@ -410,3 +410,22 @@ def test_row_per_thread_epilogue_matches_transposing_epilogue(voc, dev, monkeypa
         mel = synth.pe_inputs(710 + T, B, T, pad_tail=7).to(dev)
         a, b = pe(mel), pe_old(mel)
         assert torch.equal(a["pitch_pred"], b["pitch_pred"]) and torch.equal(a["f0_denorm_pred"], b["f0_denorm_pred"])
+
+
+def test_workspace_cache_evicts_least_recently_used_shape(diff, voc, dev):
+    """utterance lengths vary from call to call; the per-(B, T) workspaces (buffers + captured graphs) are evicted one at a time,
+    least recently used first (6 sampler / 3 vocoder shapes) -- more shapes than the cache holds, revisiting the first: same results."""
+    sd, sched, plan = diff
+    vsd, gen = voc
+    inp = synth.kernel_inputs(301, 1, 64, 1)
+    first = plan.sample(inp["cond"].to(dev), inp["fs2_mel"].to(dev), seed=9)
+    for T in (65, 70, 80, 96, 100, 110, 120, 130):
+        i2 = synth.kernel_inputs(300 + T, 1, T, 1)
+        assert bool(torch.isfinite(plan.sample(i2["cond"].to(dev), i2["fs2_mel"].to(dev), seed=9)).all())
+    assert torch.equal(plan.sample(inp["cond"].to(dev), inp["fs2_mel"].to(dev), seed=9), first)
+    vin = synth.vocoder_inputs(302, 1, 40)
+    w0 = gen(vin["mel"].to(dev), vin["f0"].to(dev), seed=3)
+    for T in (41, 50, 60, 70, 33):
+        v2 = synth.vocoder_inputs(300 + T, 1, T)
+        assert bool(torch.isfinite(gen(v2["mel"].to(dev), v2["f0"].to(dev), seed=3)).all())
+    assert torch.equal(gen(vin["mel"].to(dev), vin["f0"].to(dev), seed=3), w0)
