@@ -83,8 +83,8 @@ def test_sampler_bench_regime_vs_oracle(diff, dev, B, T, rows, runs):
             raise AssertionError(
                 f"run {i} differs from run 0 in {idx.shape[0]} elements (max |diff| {float((o - outs[0]).abs().max()):.3e}): batch rows "
                 f"{sorted(set(idx[:, 0].tolist()))}, frames {int(idx[:, 1].min())}..{int(idx[:, 1].max())}; runs equal to run 0: "
-                f"{[torch.equal(x, outs[0]) for x in outs]}, one more run equals run 0: {torch.equal(extra, outs[0])} / run {i}: {torch.equal(extra, o)} -- an ordering hole "
-                f"in the layer-to-layer dataflow")
+                f"{[torch.equal(x, outs[0]) for x in outs]}, one more run equals run 0: {torch.equal(extra, outs[0])} / run {i}: {torch.equal(extra, o)} -- a hand-over in the "
+                f"sampler's kernels is missing an ordering guarantee (profiles/r02_c_race_after_idle.txt: how the last one was found)")
     assert bool(torch.isfinite(outs[0]).all())
     with torch.no_grad():
         ref = O.diffusion_infer(sd, sched, torch.tensor(synth.SPEC_MIN), torch.tensor(synth.SPEC_MAX), cpu["cond"], K_STEP,
