@@ -61,7 +61,7 @@ EXPORTS = (
     "bsg_diffusion_time_kernel",
     "bsg_hifigan_plan_create", "bsg_hifigan_plan_destroy", "bsg_hifigan_forward", "bsg_hifigan_source",
     "bsg_pe_plan_create", "bsg_pe_plan_destroy", "bsg_pe_forward",
-    "bsg_fft_plan_create", "bsg_fft_plan_destroy", "bsg_fft_forward",
+    "bsg_fft_plan_create", "bsg_fft_plan_destroy", "bsg_fft_forward", "bsg_fft_forward_masked",
     "bsg_selftest_conv",
 )
 
@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
     L.bsg_fft_plan_destroy.argtypes = [vp]
     L.bsg_fft_plan_destroy.restype = None
     L.bsg_fft_forward.argtypes = [vp, fp, fp, ip, ip, fp, fp, vp]
+    L.bsg_fft_forward_masked.argtypes = [vp, fp, vp, fp, ip, ip, fp, fp, vp]
     L.bsg_selftest_conv.argtypes = [fp, C.POINTER(C.c_float), C.POINTER(C.c_float), ip, ip, ip, ip, ip, C.POINTER(C.c_int),
                                     ip, ip, fp, vp]
     if L.bsg_abi_version() != 1:

@@ -149,6 +149,14 @@ int bsg_fft_forward(bsg_fft_plan* plan, const float* x, const float* tgt_nonpad,
     });
 }
 
+int bsg_fft_forward_masked(bsg_fft_plan* plan, const float* x, const unsigned char* padding_mask, const float* tgt_nonpad, int B, int T,
+                           float* hidden_out, float* mel_out, void* stream) {
+    return guarded([&] {
+        B200_CHECK(plan && x && padding_mask, "null argument");
+        plan->impl.forward(x, tgt_nonpad, B, T, hidden_out, mel_out, static_cast<cudaStream_t>(stream), padding_mask);
+    });
+}
+
 int bsg_selftest_conv(const float* a_dev, const float* w_host, const float* bias_host, int B, int L, int Cin, int N, int ntaps,
                       const int* shifts, int n_tile, int precision, float* out_dev, void* stream) {
     using namespace b200;

@@ -72,6 +72,11 @@ __global__ void fft_nonpad_kernel(const float* __restrict__ x, long long rows, f
         if (lane == 0) nonpad[r] = s == 0.0f ? 0.0f : 1.0f;
     }
 }
+// nonpad[row] = !padding_mask[row]: FFTBlocks.forward's explicit mask (tts_modules.py:291-292; the encoder passes txt_tokens.eq(0), :333)
+__global__ void fft_nonpad_from_mask_kernel(const uint8_t* __restrict__ mask, long long rows, float* __restrict__ nonpad) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < rows) nonpad[i] = mask[i] ? 0.0f : 1.0f;
+}
 // keybits[b][w] bit e = key 32 w + e of utterance b may be attended to (key_padding_mask == 0 and inside [0, T))
 __global__ void fft_keybits_kernel(const float* __restrict__ nonpad, int B, int T, uint32_t* __restrict__ bits) {
     const int words = (T + 31) / 32;
@@ -309,7 +314,8 @@ FftDecoderPlan::Workspace& FftDecoderPlan::workspace(int B, int T) {
     return ref;
 }
 
-void FftDecoderPlan::forward(const float* x, const float* tgt_nonpad, int B, int T, float* hidden_out, float* mel, cudaStream_t st) {
+void FftDecoderPlan::forward(const float* x, const float* tgt_nonpad, int B, int T, float* hidden_out, float* mel, cudaStream_t st,
+                             const uint8_t* padding_mask) {
     B200_CHECK(B > 0 && T > 0, "empty batch");
     B200_CHECK(x != nullptr && (hidden_out != nullptr || mel != nullptr), "x and at least one output are required");
     B200_CHECK(mel == nullptr || cfg.out_dims > 0, "this plan was built without the mel_out projection");
@@ -345,7 +351,10 @@ void FftDecoderPlan::forward(const float* x, const float* tgt_nonpad, int B, int
     ra.rows = rows;
 
     // ---- padding mask, positions, positional embedding (tts_modules.py:291-298)
-    fft_nonpad_kernel<<<row_blocks, 256, 0, st>>>(x, rows, w.nonpad.as<float>());
+    if (padding_mask != nullptr)
+        fft_nonpad_from_mask_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, st>>>(padding_mask, rows, w.nonpad.as<float>());
+    else
+        fft_nonpad_kernel<<<row_blocks, 256, 0, st>>>(x, rows, w.nonpad.as<float>());
     fft_keybits_kernel<<<static_cast<unsigned>((static_cast<long long>(B) * ((T + 31) / 32) * 32 + 255) / 256), 256, 0, st>>>(
         w.nonpad.as<float>(), B, T, w.keybits.as<uint32_t>());
     count(2);

@@ -161,12 +161,15 @@ private:
     std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
 };
 
-// FastSpeech FFT blocks (FastspeechDecoder) + mel_out: SURVEY.md section 8f-3 (fft_decoder.cu)
+// FastSpeech FFT blocks (FastspeechDecoder; the FastspeechEncoder's block stack with use_pos_embed = 0 and an explicit mask) + mel_out:
+// SURVEY.md section 8f-3 (fft_decoder.cu)
 class FftDecoderPlan {
 public:
     FftDecoderPlan(const bsg_fft_config& cfg, const float* weights, size_t n_weights, int device);
     ~FftDecoderPlan();
-    void forward(const float* x, const float* tgt_nonpad, int B, int T, float* hidden_out, float* mel_out, cudaStream_t st);
+    // padding_mask: device u8 [B][T] (1 = padding) = FFTBlocks.forward(x, padding_mask); null = derived from all-zero frames of x
+    void forward(const float* x, const float* tgt_nonpad, int B, int T, float* hidden_out, float* mel_out, cudaStream_t st,
+                 const uint8_t* padding_mask = nullptr);
 
     bsg_fft_config cfg;
     int device;

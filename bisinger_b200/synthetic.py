@@ -196,6 +196,25 @@ def fft_state(seed: int = 555, layers: int = 4, C: int = 256, k: int = 9, out_di
     return sd
 
 
+def fft_encoder_state(seed: int = 777, vocab: int = 62, layers: int = 4, C: int = 256, k: int = 9) -> Dict[str, Tensor]:
+    """State dict with the names of FastspeechEncoder (modules/fastspeech/tts_modules.py:310-326: FFTBlocks(use_pos_embed=False) plus
+    ``embed_tokens`` and its own ``embed_positions``): the decoder's layer names without ``pos_embed_alpha``, and
+    ``embed_tokens.weight`` [vocab, C] ~ N(0, C^-0.5) with the padding row 0 zeroed (modules/commons/common_layers.py Embedding)."""
+    sd = {k_: v for k_, v in fft_state(seed, layers, C, k, out_dims=0).items() if k_ != "pos_embed_alpha"}
+    w = _normal(_gen(seed + 1), (vocab, C), C ** -0.5)
+    w[0] = 0.0
+    sd["embed_tokens.weight"] = w
+    return sd
+
+
+def fft_tokens(seed: int, B: int, T: int, vocab: int = 62, pad_tail: int = 0) -> Tensor:
+    """txt_tokens [B,T] int64 in [1, vocab); the last ``pad_tail`` positions of every odd batch row are the padding index 0."""
+    t = torch.randint(1, vocab, (B, T), generator=_gen(seed))
+    if pad_tail > 0:
+        t[1::2, T - pad_tail:] = 0
+    return t
+
+
 def fft_inputs(seed: int, B: int, T: int, C: int = 256, pad_tail: int = 0) -> Tensor:
     """decoder_inp [B,T,C] ~ N(0,1); the last ``pad_tail`` frames of every odd batch row are all-zero padding frames."""
     x = torch.randn((B, T, C), generator=_gen(seed))

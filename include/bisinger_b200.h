@@ -261,6 +261,15 @@ void bsg_fft_plan_destroy(bsg_fft_plan* plan);
 int bsg_fft_forward(bsg_fft_plan* plan, const float* x, const float* tgt_nonpad, int B, int T, float* hidden_out, float* mel_out,
                     void* stream);
 
+/* FFTBlocks.forward(x, padding_mask) (tts_modules.py:286-310) with the caller's mask instead of the all-zero-frame rule: the call
+ * FastspeechEncoder.forward / FastspeechMIDIEncoder.forward make after their embeddings (tts_modules.py:333-335,
+ * modules/diffsinger_midi/fs2.py:53-62; plan built with use_pos_embed = 0, num_layers = enc_layers, ffn_kernel = enc_ffn_kernel_size).
+ *   padding_mask  device u8 [B][T], 1 = padding (txt_tokens.eq(0)): those keys are not attended to and those rows are zeroed after
+ *                 every residual add and in the result; every utterance needs at least one non-padding position (the reference
+ *                 returns NaN otherwise).  Other arguments as bsg_fft_forward.                                           */
+int bsg_fft_forward_masked(bsg_fft_plan* plan, const float* x, const unsigned char* padding_mask, const float* tgt_nonpad, int B, int T,
+                           float* hidden_out, float* mel_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Kernel self-test: C[b][l][n] = bias[n] + sum_taps A[b][l+shift][:] . W[n][tap][:] through the same tcgen05
  * implicit-GEMM kernel the plans use.  Device pointers; A f32 [B][L][Cin], W f32 host [N][ntaps][Cin].

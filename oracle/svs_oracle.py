@@ -492,18 +492,19 @@ def fft_n_layers(p: Dict[str, Tensor]) -> int:
 
 
 def fft_decoder_forward(p: Dict[str, Tensor], x: Tensor, hp: Optional[dict] = None, mel_out: Optional[Dict[str, Tensor]] = None,
-                        tgt_nonpad: Optional[Tensor] = None):
+                        tgt_nonpad: Optional[Tensor] = None, padding_mask: Optional[Tensor] = None):
     """FastspeechDecoder.forward in eval mode (modules/fastspeech/tts_modules.py:286-310 FFTBlocks.forward, :340-347) over
     TransformerEncoderLayer -> EncSALayer (modules/commons/common_layers.py:696-731): x [B,T,C] -> hidden [B,T,C]; with
     ``mel_out`` = {'weight','bias'} also the projection and mask of FastSpeech2.run_decoder (modules/fastspeech/fs2.py:236-240).
     The attention is MultiheadAttention(self_attention=True, bias=False) -> F.multi_head_attention_forward (:321-345): no biases,
-    q scaled by head_dim^-0.5, key_padding_mask = the padding frames, softmax over the keys."""
+    q scaled by head_dim^-0.5, key_padding_mask = the padding frames, softmax over the keys.
+    ``padding_mask`` [B,T] bool = FFTBlocks.forward's explicit mask (the encoder passes txt_tokens.eq(0), :333-335)."""
     hp = {**FFT_HPARAMS, **(hp or {})}
     B, T, C = x.shape
     H = hp["num_heads"]
     d = C // H
     k = hp["dec_ffn_kernel_size"]
-    pad = x.abs().sum(-1).eq(0)                                        # tts_modules.py:291
+    pad = x.abs().sum(-1).eq(0) if padding_mask is None else padding_mask.bool()      # tts_modules.py:291
     nonpad = (~pad).float()[:, :, None]                                # :292 (as [B,T,1]; the reference works in [T,B,C])
     if hp["use_pos_embed"]:                                            # :293-296
         pos = pe_positions(x[..., 0])
@@ -535,6 +536,21 @@ def fft_decoder_forward(p: Dict[str, Tensor], x: Tensor, hp: Optional[dict] = No
     if tgt_nonpad is not None:
         m = m * tgt_nonpad[:, :, None]
     return x, m
+
+
+def fft_encoder_forward(p: Dict[str, Tensor], txt_tokens: Tensor, hp: Optional[dict] = None) -> Tensor:
+    """FastspeechEncoder.forward in eval mode (modules/fastspeech/tts_modules.py:327-346): x = sqrt(C) * embed_tokens(txt) +
+    SinusoidalPositionalEmbedding(txt_tokens) (positions count the non-padding tokens, padding_idx 0), then the FFT blocks with
+    use_pos_embed = False and the explicit padding mask txt_tokens.eq(0).  txt_tokens [B,T] int64 -> [B,T,C]."""
+    hp = {**FFT_HPARAMS, **(hp or {})}
+    w = p["embed_tokens.weight"]
+    C = w.shape[1]
+    x = math.sqrt(C) * F.embedding(txt_tokens, w, padding_idx=0)       # :340
+    if hp.get("use_pos_embed", True):                                  # :341-343 (hparams['use_pos_embed'], not the FFTBlocks flag)
+        pos = pe_positions(txt_tokens)
+        x = x + pe_pos_table(int(pos.max()) + 2, C).to(x.device)[pos]
+    blocks = {**hp, "use_pos_embed": False, "dec_ffn_kernel_size": hp.get("enc_ffn_kernel_size", hp["dec_ffn_kernel_size"])}
+    return fft_decoder_forward(p, x, blocks, padding_mask=txt_tokens.eq(0))
 
 
 def snr_db(ref: Tensor, out: Tensor) -> float:
