@@ -127,6 +127,8 @@ if __name__ == "__main__":
                 Scheme("cur but cp fp16", hf, 1, 2, per={**side, "cp": hf}),
                 Scheme("cur but cp bf16", hf, 1, 2, per={**side, "cp": bf})]
     schemes += [Scheme("cur + state fp16 (x carried as fp16(x+d))", hf, 1, 2, state16="fp16", per={**side, "gate": W52})]
+    schemes += [Scheme("cur + state fp16 + cp fp16 (shipped scheme with the hoisted conditioner projection stored as fp16)", hf, 1, 2, state16="fp16",
+                       per={**side, "gate": W52, "cp": hf})]
     WA = (hf, 1, "alt")
     schemes += [Scheme("alt: gate+res+skip fp16x1 alternating rounding, state fp16", hf, 1, 2, state16="fp16", per={**side, "gate": WA, "res": WA, "skip": WA}),
                 Scheme("alt: gate+res alternating, skip Wsplit, state fp16", hf, 1, 2, state16="fp16", per={**side, "gate": WA, "res": WA}),
