@@ -229,6 +229,44 @@ class B200FastspeechEncoder(B200FFTBlocks):
         return self.forward_blocks(self.forward_embedding(txt_tokens), txt_tokens.eq(self.padding_idx))
 
 
+def device_blocks_encoder(base_cls):
+    """Subclass factory for the reference's FFTBlocks-derived encoders (``FastspeechMIDIEncoder``, ``FastspeechEncoder``;
+    modules/diffsinger_midi/fs2.py:14-65, modules/fastspeech/tts_modules.py:310-346): the returned class IS the reference class --
+    constructor, parameters, state-dict keys, ``forward_embedding`` (token / MIDI / slur embeddings, ESM, positional table) and the
+    training-mode forward are inherited unchanged -- and in eval mode its block stack, the
+    ``super(FastspeechEncoder, self).forward(x, encoder_padding_mask)`` call, runs on the device plan.  The device twin is built from
+    the module's own weights on first use and dropped whenever they change.
+
+        FS_ENCODERS["fft"] = lambda esm, hp, emb, d: device_blocks_encoder(FastspeechMIDIEncoder)(
+            esm, emb, hp["hidden_size"], hp["enc_layers"], hp["enc_ffn_kernel_size"], num_heads=hp["num_heads"])
+    """
+
+    class _DeviceBlocksEncoder(base_cls):
+        def _b200_blocks(self) -> B200FFTBlocks:
+            twin = self.__dict__.get("_b200")                 # kept out of the module tree: no extra state-dict keys
+            if twin is None:
+                twin = self.__dict__["_b200"] = B200FFTBlocks.from_reference(self)
+            return twin
+
+        def load_state_dict(self, *a, **k):
+            self.__dict__.pop("_b200", None)
+            return super().load_state_dict(*a, **k)
+
+        def _apply(self, fn, *a, **k):
+            self.__dict__.pop("_b200", None)
+            return super()._apply(fn, *a, **k)
+
+        def forward(self, txt_tokens, *embeddings):
+            if self.training:
+                return super().forward(txt_tokens, *embeddings)
+            mask = txt_tokens.eq(self.padding_idx).data
+            x = self.forward_embedding(txt_tokens, *embeddings)
+            return self._b200_blocks().forward_blocks(x, mask)
+
+    _DeviceBlocksEncoder.__name__ = _DeviceBlocksEncoder.__qualname__ = "B200" + base_cls.__name__
+    return _DeviceBlocksEncoder
+
+
 class FftDecoderPlan:
     """Owner of one ``bsg_fft_plan`` handle."""
 

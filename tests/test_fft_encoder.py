@@ -157,3 +157,58 @@ def test_from_reference_copies_a_live_encoder_block_stack():
     own = B200FastspeechDecoder(hparams=FFT_HP)
     own.load_state_dict(dsd, strict=True)
     assert torch.equal(dtwin.flat_weights(), own.flat_weights())         # the same device blob either way
+
+
+def test_device_blocks_encoder_is_the_reference_midi_encoder_with_the_block_stack_rerouted(monkeypatch):
+    """device_blocks_encoder(FastspeechMIDIEncoder) on the executed reference (build container only), BiSinger's shipped
+    positional setting (rel_pos: true): same state-dict keys as the reference class, the training-mode forward is the reference's,
+    and the eval-mode forward hands (forward_embedding(...), txt_tokens.eq(0)) to forward_blocks -- checked numerically by answering
+    that call with the oracle's FFT blocks and comparing with the reference encoder's own eval forward."""
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from make_golden_fft import FFT_HP
+    ns = ref_shim.load()
+    ns.hparams.update({**FFT_HP, "rel_pos": True})
+    try:
+        from modules.commons.common_layers import ESM, Embedding  # type: ignore
+        from modules.diffsinger_midi.fs2 import FastspeechMIDIEncoder  # type: ignore
+        from bisinger_b200.fft import B200FFTBlocks, device_blocks_encoder
+        torch.manual_seed(3)
+        esm = ESM(d_model=256, nhead=8)
+        ref = FastspeechMIDIEncoder(esm, Embedding(62, 256, 0), 256, 4, 9, num_heads=2).eval()
+        cls = device_blocks_encoder(FastspeechMIDIEncoder)
+        assert cls.__name__ == "B200FastspeechMIDIEncoder" and issubclass(cls, FastspeechMIDIEncoder)
+        own = cls(esm, Embedding(62, 256, 0), 256, 4, 9, num_heads=2).eval()
+        own.load_state_dict(ref.state_dict(), strict=True)
+        assert list(own.state_dict().keys()) == list(ref.state_dict().keys())
+        B, T = 2, 23
+        tok = synth.fft_tokens(51, B, T, pad_tail=6)
+        g = torch.Generator().manual_seed(52)
+        emb = [0.1 * torch.randn((B, T, 256), generator=g) for _ in range(4)]     # midi, midi_dur, slur, lang embeddings
+        with torch.no_grad():
+            want = ref(tok, *emb)
+        seen = {}
+
+        def oracle_blocks(self, x, padding_mask=None):
+            seen["mask"] = padding_mask
+            sd = {k: v for k, v in self.state_dict().items()}
+            return O.fft_decoder_forward(sd, x, dict(use_pos_embed=False), padding_mask=padding_mask)
+
+        monkeypatch.setattr(B200FFTBlocks, "forward_blocks", oracle_blocks)
+        with torch.no_grad():
+            got = own(tok, *emb)
+        assert torch.equal(seen["mask"], tok.eq(0))
+        assert float((got - want).abs().max()) < 2e-5
+        assert list(own.state_dict().keys()) == list(ref.state_dict().keys())      # the twin did not join the module tree
+        twin = own._b200_blocks()
+        own.load_state_dict(ref.state_dict(), strict=True)
+        assert own._b200_blocks() is not twin                                       # rebuilt after the weights changed
+        own.train()
+        torch.manual_seed(9)
+        a = own(tok, *emb)
+        torch.manual_seed(9)
+        b = ref.train()(tok, *emb)
+        assert torch.equal(a, b)                                                    # training forward = the reference's, dropout included
+    finally:
+        ns.hparams.pop("rel_pos", None)
