@@ -387,47 +387,58 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
     // Keep a few shapes alive (buffers + captured graphs): utterance lengths vary from call to call, so evict ONE least-recently
     // used entry at a time -- when there are more than kMaxShapes, or while the cached workspaces plus the new one (~70 KB per mel
     // frame) would exceed the byte budget (BSG_WS_BUDGET_GB, default 48).
+    // The large buffers are sized for a capacity class of rows (next multiple of max(256, 2^ceil(log2 rows) / 8): at most 12.5 % more than
+    // needed) and come from / go back to the plan's pool: a new length of the same class reuses an evicted workspace's memory instead of
+    // paying cudaFree + cudaMalloc (tools/varying_length_latency.py: up to 700 ms per new length before, ~6 ms -- the graph capture -- now).
+    // Only sizes are quantised: every offset, tensor map and launch below uses the actual B and T.
+    const size_t rows = static_cast<size_t>(B) * T;
+    size_t p2 = 256;
+    while (p2 < rows) p2 <<= 1;
+    const size_t step = std::max<size_t>(256, p2 / 8);
+    const size_t cap = (rows + step - 1) / step * step;
+    static const double budget_gb = [] { const char* e = std::getenv("BSG_WS_BUDGET_GB"); return e ? std::atof(e) : 48.0; }();
+    auto total = [&] { size_t n = 0; for (auto& kv : ws) n += kv.second->bytes; return n; };
     {
-        static const double budget_gb = [] { const char* e = std::getenv("BSG_WS_BUDGET_GB"); return e ? std::atof(e) : 48.0; }();
-        const size_t need = static_cast<size_t>(B) * T * 72 * 1024;
-        auto total = [&] { size_t n = 0; for (auto& kv : ws) n += kv.second->bytes; return n; };
+        const size_t need = cap * 72 * 1024;
         while (!ws.empty() && (ws.size() >= static_cast<size_t>(kMaxShapes) || static_cast<double>(total() + need) > budget_gb * 1e9)) {
             auto lru = ws.begin();
             for (auto jt = ws.begin(); jt != ws.end(); ++jt)
                 if (jt->second->last_use < lru->second->last_use) lru = jt;
+            // its buffers are about to be handed to another shape, possibly on another stream: wait for the work that may still use them
+            // (cudaFree did the same implicitly before the pool existed)
+            B200_CUDA(cudaDeviceSynchronize());
             ws.erase(lru);
         }
     }
-    size_t free_before = 0, free_after = 0, total_mem = 0;
-    cudaMemGetInfo(&free_before, &total_mem);
     auto w = std::make_unique<Workspace>();
     w->last_use = ++use_clock;
     const int M = cfg.in_dims, H = cfg.hidden_size, C = cfg.residual_channels;
-    const size_t rows = static_cast<size_t>(B) * T;
+    size_t pooled_bytes = 0;
+    auto take = [&](DevBuf& b, size_t n) { b.alloc(n, &pool); pooled_bytes += n; };
     w->B = B;
     w->T = T;
     const bool lo = terms == 3, lo_side = terms_side == 3;
-    w->xt.alloc(rows * M * 4);
-    w->eps.alloc(rows * M * 4);
-    w->xin_hi.alloc(rows * M * 2);
-    w->cond_hi.alloc(rows * H * 2);
-    w->xres.alloc(rows * C * 4);
-    w->xa_hi.alloc(rows * C * 2);
-    w->z_hi.alloc(rows * cfg.residual_layers * C * 2);
-    w->s_hi.alloc(rows * C * 2);
-    w->h_hi.alloc(rows * C * 2);
-    w->mel.alloc(rows * M * 4);
-    w->mel2ph.alloc(rows * 8);
-    w->cp.alloc(static_cast<size_t>(cfg.residual_layers) * rows * 2 * C * 4);
+    take(w->xt, cap * M * 4);
+    take(w->eps, cap * M * 4);
+    take(w->xin_hi, cap * M * 2);
+    take(w->cond_hi, cap * H * 2);
+    take(w->xres, cap * C * 4);
+    take(w->xa_hi, cap * C * 2);
+    take(w->z_hi, cap * cfg.residual_layers * C * 2);
+    take(w->s_hi, cap * C * 2);
+    take(w->h_hi, cap * C * 2);
+    take(w->mel, cap * M * 4);
+    take(w->mel2ph, cap * 8);
+    take(w->cp, static_cast<size_t>(cfg.residual_layers) * cap * 2 * C * 4);
     if (lo) {
-        w->xa_lo.alloc(rows * C * 2);
-        w->z_lo.alloc(rows * cfg.residual_layers * C * 2);
+        take(w->xa_lo, cap * C * 2);
+        take(w->z_lo, cap * cfg.residual_layers * C * 2);
     }
     if (lo_side) {
-        w->xin_lo.alloc(rows * M * 2);
-        w->cond_lo.alloc(rows * H * 2);
-        w->s_lo.alloc(rows * C * 2);
-        w->h_lo.alloc(rows * C * 2);
+        take(w->xin_lo, cap * M * 2);
+        take(w->cond_lo, cap * H * 2);
+        take(w->s_lo, cap * C * 2);
+        take(w->h_lo, cap * C * 2);
     }
     auto mk = [&](CUtensorMap (&m)[2], const DevBuf& hi, const DevBuf& lo_, int ch, int box_rows = kTileM) {
         m[0] = make_act_tmap(hi.p, B, T, ch, 0, box_rows);
@@ -440,14 +451,14 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
     mk(w->m_s, w->s_hi, w->s_lo, C);
     mk(w->m_h, w->h_hi, w->h_lo, C);
     if (use_fused) {
-        w->xa8.alloc(rows * C);
+        take(w->xa8, cap * C);
         w->m_xa8 = make_act8_tmap(w->xa8.p, B, T, C, kXaBoxRows);
         if (skip_fp8) {
-            w->z8.alloc(rows * cfg.residual_layers * C);
+            take(w->z8, cap * cfg.residual_layers * C);
             w->m_z8 = make_act8_tmap(w->z8.p, B, T, cfg.residual_layers * C, kTileM);
         }
-        w->xa16_b.alloc(rows * C * 2);
-        w->xa8_b.alloc(rows * C);
+        take(w->xa16_b, cap * C * 2);
+        take(w->xa8_b, cap * C);
         w->m_xa16_b = make_act_tmap(w->xa16_b.p, B, T, C, 0, kXaBoxRows);
         w->m_xa8_b = make_act8_tmap(w->xa8_b.p, B, T, C, kXaBoxRows);
         w->m_xe[1] = make_epi16_tmap(w->xa16_b.p, B, T, C);
@@ -473,8 +484,11 @@ DiffusionPlan::Workspace& DiffusionPlan::workspace(int B, int T) {
         const int n_row_tiles = B * ((T + 2 * kTileM - 1) / (2 * kTileM));
         w->layer_flags.alloc(static_cast<size_t>(cfg.residual_layers) * n_row_tiles * sizeof(int));
     }
-    cudaMemGetInfo(&free_after, &total_mem);
-    w->bytes = free_before > free_after ? free_before - free_after : 0;
+    w->bytes = pooled_bytes;
+    {   // what the pool keeps beyond the live workspaces counts against the same budget
+        const double live = static_cast<double>(total() + w->bytes);
+        pool.trim(live < budget_gb * 1e9 ? static_cast<size_t>(budget_gb * 1e9 - live) : 0);
+    }
     auto& ref = *w;
     ws[key] = std::move(w);
     return ref;

@@ -65,6 +65,7 @@ private:
     DevBuf lut, d_spec_min, d_spec_max, d_seed;
     std::vector<StepCoef> sched;
     static constexpr int kMaxShapes = 6;   // cached (B, T) workspaces, least recently used evicted first
+    DevPool pool;                          // large buffers of evicted workspaces (declared before ws: destroyed after it)
     std::map<std::pair<int, int>, std::unique_ptr<Workspace>> ws;
     unsigned long long use_clock = 0;
     unsigned long long graph_nodes = 0;

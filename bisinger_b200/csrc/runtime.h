@@ -10,6 +10,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <iterator>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -35,27 +37,69 @@ struct Error : std::runtime_error {
         if (!(cond)) throw ::b200::Error(std::string("check failed: ") + #cond + ": " + (msg));          \
     } while (0)
 
+// Free list of device buffers by exact size (plan-owned).  The per-shape workspaces of a plan draw their large buffers from it and hand them
+// back when a shape is evicted: utterance lengths change from call to call, and cudaMalloc / cudaFree of gigabyte buffers cost up to
+// hundreds of milliseconds each time (tools/varying_length_latency.py).  Workspace sizes are quantised (capacity classes of rows), so
+// buffers of one class fit every shape of the class.  Must outlive every DevBuf that was allocated from it.
+struct DevPool {
+    std::multimap<size_t, void*> free_list;
+    size_t pooled = 0;
+    void* take(size_t n) {
+        auto it = free_list.find(n);
+        if (it == free_list.end()) return nullptr;
+        void* p = it->second;
+        free_list.erase(it);
+        pooled -= n;
+        return p;
+    }
+    void give(void* p, size_t n) {
+        free_list.emplace(n, p);
+        pooled += n;
+    }
+    void trim(size_t keep_bytes) {   // largest first
+        while (pooled > keep_bytes && !free_list.empty()) {
+            auto it = std::prev(free_list.end());
+            cudaFree(it->second);
+            pooled -= it->first;
+            free_list.erase(it);
+        }
+    }
+    ~DevPool() { trim(0); }
+};
+
 // RAII device allocation (plan-owned workspaces / packed weights)
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    DevPool* pool = nullptr;   // where the buffer goes on release (null: cudaFree)
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), pool(o.pool) { o.p = nullptr; o.bytes = 0; o.pool = nullptr; }
     DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; pool = o.pool; o.p = nullptr; o.bytes = 0; o.pool = nullptr; }
         return *this;
     }
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pool) pool->give(p, bytes);
+            else cudaFree(p);
+        }
         p = nullptr;
         bytes = 0;
+        pool = nullptr;
     }
-    void alloc(size_t n) {
+    // from != null: reuse a pooled buffer of exactly n bytes if there is one (contents are whatever its last user left), and return
+    // the buffer to that pool on release
+    void alloc(size_t n, DevPool* from = nullptr) {
         release();
         if (n == 0) n = 16;
+        pool = from;
+        if (from != nullptr && (p = from->take(n)) != nullptr) {
+            bytes = n;
+            return;
+        }
         B200_CUDA(cudaMalloc(&p, n));
         bytes = n;
         // debugging aid (BSG_ALLOC_FILL=<hex byte>): fill every fresh device buffer, e.g. ff = NaN patterns in f32 / f16 / e4m3, so a
