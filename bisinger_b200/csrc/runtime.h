@@ -100,7 +100,14 @@ struct DevBuf {
             bytes = n;
             return;
         }
-        B200_CUDA(cudaMalloc(&p, n));
+        cudaError_t err = cudaMalloc(&p, n);
+        if (err == cudaErrorMemoryAllocation && from != nullptr && from->pooled > 0) {   // the free list may be holding what is missing
+            cudaGetLastError();
+            from->trim(0);
+            err = cudaMalloc(&p, n);
+        }
+        if (err != cudaSuccess) p = nullptr;
+        B200_CUDA(err);
         bytes = n;
         // debugging aid (BSG_ALLOC_FILL=<hex byte>): fill every fresh device buffer, e.g. ff = NaN patterns in f32 / f16 / e4m3, so a
         // read of memory the path never wrote shows up in the results instead of depending on what the allocation held before
